@@ -1,0 +1,145 @@
+/*
+ * dcr.h — C ABI of libdcr.so, the B200 (sm_100a) library behind the reference's BFC / SDRF entry points.
+ *
+ * Reference = jakubbober/discrete-curvature-rewiring (read at /root/reference).  The reference has no FFI:
+ * its hot path is two numba.cuda kernels plus torch calls driven from Python.  Each function below names the
+ * reference interface (file:line) whose work it takes over; the Python modules that keep the reference's
+ * module paths and signatures (discrete-curvature-rewiring_b200/{curvature,rewiring,utils}) bind these
+ * symbols through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no host sync) unless
+ *     the comment says "synchronises"
+ *   - return value: 0 = ok, non-zero = error (message via dcr_last_error(), thread-local)
+ *   - graphs are undirected, simple (no self-loops, no multi-edges), node ids 0..n-1, given as a CSR with int32
+ *     row offsets and int32 SORTED column indices; a "directed entry" is one slot of colidx, an "undirected
+ *     edge" is a directed entry with row < col, numbered in CSR order (edge id)
+ */
+#ifndef DCR_H_
+#define DCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCR_VERSION 1
+
+/* status codes written by the SDRF loop into dcr_sdrf_result.status */
+#define DCR_SDRF_OK 0             /* all requested iterations ran (or the loop hit one of its own `break`s)      */
+#define DCR_SDRF_NEED_HOST 1      /* the uniform lies within `guard` of a CDF boundary: host must decide (App. E.3) */
+#define DCR_SDRF_PROB_NAN 2       /* softmax overflow/underflow -> NaN probabilities (numpy: ValueError)          */
+#define DCR_SDRF_PROB_SUM 3       /* probabilities do not sum to 1 (numpy: ValueError)                            */
+#define DCR_SDRF_REMOVE_NONEDGE 4 /* argmax fell on a non-edge and exceeded removal_bound (networkx: NetworkXError) */
+#define DCR_SDRF_NO_UNIFORM 5     /* ran out of host-supplied uniforms                                            */
+#define DCR_SDRF_ARENA_FULL 6     /* adjacency arena exhausted (create with a larger max_additions)               */
+
+const char* dcr_last_error(void);
+int dcr_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense <-> CSR for the legacy dense-matrix signatures.
+ * Replaces the dense `A` argument handling of curvature/bfc_cuda.py:51-57 and :144-150.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Pass 1: per-row non-zero counts of the fp32 row-major matrix A[n,n] into row_counts[n], and validation
+ * flags OR-ed into *flags: bit0 = some value is neither 0 nor 1, bit1 = non-zero diagonal, bit2 = asymmetric. */
+int dcr_dense_count(const float* A, int n, int32_t* row_counts, int32_t* flags, void* stream);
+/* Pass 2: fill sorted colidx given rowptr[n+1] (exclusive scan of row_counts, done by the caller). */
+int dcr_dense_fill(const float* A, int n, const int32_t* rowptr, int32_t* colidx, void* stream);
+/* C[n,n] = 0 everywhere, then C[row, colidx[p]] = vals[p] for every directed entry p
+ * (the dense `C` the reference returns, bfc_cuda.py:16-18,46-48,65). */
+int dcr_scatter_dense(const int32_t* rowptr, const int32_t* colidx, int n, const float* vals, float* C,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * cuda-flavour BFC over CSR.  Replaces _balanced_forman_curvature (curvature/bfc_cuda.py:11-48) and its host
+ * wrapper balanced_forman_curvature (:51-65) for symmetric 0/1 adjacency without self-loops.
+ * Outputs are per DIRECTED ENTRY p in [entry_lo, entry_hi) (arrays are indexed by p, full length nnz):
+ *   tri[p]    = A2[i,j]           (#common neighbours)           int32
+ *   sharp[p]  = sharp_ij          (bfc_cuda.py:31-44)            int32
+ *   lam[p]    = lambda_ij                                       int32
+ *   c64[p]    = the fp64 value before the fp32 stores            double   (may be NULL)
+ *   c32[p]    = the fp32 value the compiled kernel stores        float    (two roundings)
+ * `tri` must hold ALL entries' supports before the curvature pass: call dcr_bfc_support first (it fills
+ * tri[0..nnz)), then dcr_bfc_cuda_flavour for the wanted entry range.
+ * ---------------------------------------------------------------------------------------------------------- */
+int dcr_bfc_support(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, int64_t entry_lo,
+                    int64_t entry_hi, void* stream);
+int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* tri,
+                         int32_t* sharp, int32_t* lam, double* c64, float* c32, int64_t entry_lo,
+                         int64_t entry_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * paper-flavour BFC over CSR.  Replaces bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).
+ * Undirected edges are given explicitly: edge e = (esrc[e], edst[e]) with esrc < edst; the call processes
+ * edges order[lo..hi) (order = a permutation of edge ids, heavy edges first; NULL = identity) and writes
+ * out_*[e] at the edge id:  tri, sq_i (#squares at esrc), sq_j (#squares at edst), gamma (0 where the
+ * reference never computes it), bfc (fp64, evaluated left to right as bfc_naive.py:31-32,39-40).
+ * scratch: opaque device workspace of dcr_bfc_paper_scratch_bytes(n, max_degree) bytes.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree);
+/* work[e] = estimated 2-hop entries to scan for edge e (used for ordering / sharding), int64. */
+int dcr_bfc_paper_work(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc,
+                       const int32_t* edst, int64_t n_edges, int64_t* node_s, int64_t* work, void* stream);
+int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc, const int32_t* edst,
+                  const int32_t* order, int64_t lo, int64_t hi, int32_t* out_tri, int32_t* out_sq_i,
+                  int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Candidate scoring.  Replaces _balanced_forman_post_delta / balanced_forman_post_delta
+ * (curvature/bfc_cuda.py:68-141, :144-159): D[I,J] for i = i_nb[I], j = j_nb[J]; masked cells = -1000.
+ * `tri` = supports of all directed entries (dcr_bfc_support).  D is row-major [n_i, n_j] fp32.
+ * ---------------------------------------------------------------------------------------------------------- */
+int dcr_post_delta(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* tri, int x, int y,
+                   const int32_t* i_nb, int n_i, const int32_t* j_nb, int n_j, float* D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SDRF loop.  Replaces the loop body of sdrf_cuda_bfc (rewiring/sdrf_cuda_bfc.py:37-91) including
+ * utils/softmax.py:4-10 and the np.random.choice draw (:64-68), for is_undirected=True.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dcr_sdrf dcr_sdrf;
+
+typedef struct dcr_sdrf_result {
+    int32_t status;          /* DCR_SDRF_*                                                                      */
+    int32_t iterations_done; /* iterations fully executed by this call (log records written)                   */
+    int32_t draws_used;      /* uniforms consumed by this call                                                  */
+    int32_t stopped;         /* 1 if the loop took one of the reference's `break`s (:76-77, :89-91)            */
+    int32_t pending_n;       /* NEED_HOST: number of candidates of the pending iteration                        */
+    int32_t pending_x, pending_y;
+    int32_t reserved;
+} dcr_sdrf_result;
+
+/* One log record per executed iteration: int32[8] = {x, y, n_candidates, k, l, choice, removed_x, removed_y}
+ * (k = l = choice = -1 when nothing was added; removed_* = -1 when nothing was removed). */
+#define DCR_SDRF_LOG_INTS 8
+
+/* Build the device state from a host CSR in NETWORKX ADJACENCY ORDER (order_host[rowptr_host[v]..] lists the
+ * neighbours of v in insertion order, sdrf_cuda_bfc.py:31-33,45-46); synchronises.  max_additions bounds the
+ * number of edge insertions over the lifetime of the state (arena sizing). */
+int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host, int64_t max_additions,
+                    dcr_sdrf** out);
+void dcr_sdrf_destroy(dcr_sdrf* s);
+/* Run up to `loops` iterations.  uniforms[draw_offset + t] is the t-th uniform of this call (device, fp64).
+ * forced_choice >= 0 forces the candidate index of the FIRST iteration of this call (host re-decision after
+ * DCR_SDRF_NEED_HOST); guard = half-width of the CDF-boundary zone that triggers NEED_HOST (0 disables).
+ * log: device int32[loops][8]; result: device dcr_sdrf_result. */
+int dcr_sdrf_run(dcr_sdrf* s, int loops, int remove_edges, double removal_bound, double tau,
+                 const double* uniforms, int64_t n_uniforms, int forced_choice, double guard, int32_t* log,
+                 dcr_sdrf_result* result, void* stream);
+/* Improvements (fp64 of the fp32 differences, candidate order) of the pending iteration after NEED_HOST. */
+int dcr_sdrf_pending_improvements(dcr_sdrf* s, double* out, int64_t capacity, void* stream);
+/* Current number of directed entries (synchronises). */
+int64_t dcr_sdrf_nnz(dcr_sdrf* s);
+/* Export the current graph: rowptr[n+1], and per directed entry in NETWORKX ORDER the neighbour id
+ * (`order_out`), plus, in SORTED order per row, colidx / curvature (fp32, cuda flavour) / support. */
+int dcr_sdrf_export(dcr_sdrf* s, int32_t* rowptr, int32_t* order_out, int32_t* colidx_sorted, float* c32_sorted,
+                    int32_t* tri_sorted, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCR_H_ */

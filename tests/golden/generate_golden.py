@@ -1,0 +1,249 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` is not present on the GPU box):
+
+    python tests/golden/generate_golden.py
+
+What is executed, all imported from ``/root/reference`` without edits:
+  * ``curvature.bfc_naive.bfc_edge``                     (needs only an ``nx.adj_matrix`` shim under networkx>=3)
+  * ``curvature.bfc_cuda.balanced_forman_curvature`` /
+    ``balanced_forman_post_delta``                       under ``NUMBA_ENABLE_CUDASIM=1``; a proxy converts the
+                                                         torch arguments of the kernel launch to numpy (with
+                                                         torch arguments 0-d views alias under the simulator
+                                                         and ``A2_x_y += …`` corrupts ``A2`` — SURVEY.md App. F.4)
+  * ``rewiring.rewire.rewire(..., 'bfc', ...)``          with the ``torch_geometric`` stand-in of this repo and
+                                                         ``torch.Tensor.cuda = identity``; the add/remove sequence
+                                                         is captured by wrapping ``nx.Graph.add_edge/remove_edge``
+
+The simulator evaluates the closing formula in fp32 (numpy>=2), i.e. the oracle's ``"sim32"`` rounding model;
+the compiled kernel's fp64/two-rounding dataflow is pinned separately from its PTX.
+Outputs: ``paper_kat.npz``, ``cuda_kat.npz``, ``sdrf_seq.npz`` (a few hundred KB in total).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+os.environ["NUMBA_ENABLE_CUDASIM"] = "1"
+os.environ.setdefault("NUMBA_DISABLE_PERFORMANCE_WARNINGS", "1")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+PKG = os.path.join(REPO, "discrete-curvature-rewiring_b200")
+REFERENCE = "/root/reference"
+sys.path.insert(0, os.path.join(PKG, "standin"))
+sys.path.insert(0, REFERENCE)
+sys.path.insert(1, PKG)        # for dcr.synth only (the reference's own packages stay first)
+
+import networkx as nx  # noqa: E402
+import numpy as np  # noqa: E402
+import scipy.sparse  # noqa: E402
+import torch  # noqa: E402
+
+if not hasattr(nx, "adj_matrix"):
+    nx.adj_matrix = lambda G: scipy.sparse.csr_matrix(nx.adjacency_matrix(G))
+torch.Tensor.cuda = lambda self, *a, **k: self
+
+import curvature.bfc_cuda as ref_cuda  # noqa: E402
+import curvature.bfc_naive as ref_naive  # noqa: E402
+from torch_geometric.data import Data  # noqa: E402
+
+
+class _NumpyArgProxy:
+    """Forwards ``kernel[grid, block](*args)`` with torch tensors replaced by numpy views / scalars."""
+
+    def __init__(self, kernel):
+        self.kernel = kernel
+
+    def __getitem__(self, cfg):
+        launch = self.kernel[cfg]
+
+        def call(*args):
+            conv = []
+            for a in args:
+                if torch.is_tensor(a):
+                    conv.append(np.float32(a.item()) if a.dim() == 0 else a.numpy())
+                else:
+                    conv.append(a)
+            return launch(*conv)
+
+        return call
+
+
+ref_cuda._balanced_forman_curvature = _NumpyArgProxy(ref_cuda._balanced_forman_curvature)
+ref_cuda._balanced_forman_post_delta = _NumpyArgProxy(ref_cuda._balanced_forman_post_delta)
+
+import rewiring.sdrf_cuda_bfc as ref_sdrf  # noqa: E402
+from rewiring.rewire import rewire as ref_rewire  # noqa: E402
+
+ref_sdrf.tqdm = lambda it, *a, **k: it
+
+
+def relabel(G):
+    return nx.convert_node_labels_to_integers(G, ordering="sorted")
+
+
+def toy_graphs():
+    gs = {
+        "path4": nx.path_graph(4),
+        "star5": nx.star_graph(4),
+        "c3": nx.cycle_graph(3),
+        "c4": nx.cycle_graph(4),
+        "c5": nx.cycle_graph(5),
+        "k4": nx.complete_graph(4),
+        "k5": nx.complete_graph(5),
+        "k33": nx.complete_bipartite_graph(3, 3),
+        "grid3": relabel(nx.grid_2d_graph(3, 3)),
+        "petersen": nx.petersen_graph(),
+        "cube": relabel(nx.hypercube_graph(3)),
+        "barbell41": nx.barbell_graph(4, 1),
+        "wheel7": nx.wheel_graph(7),
+        "lollipop": nx.lollipop_graph(5, 3),
+    }
+    return gs
+
+
+def sorted_symmetric_edge_index(G):
+    e = np.array([(u, v) for u, v in G.edges() if u != v], dtype=np.int64).reshape(-1, 2)
+    src = np.concatenate([e[:, 0], e[:, 1]])
+    dst = np.concatenate([e[:, 1], e[:, 0]])
+    order = np.lexsort((dst, src))
+    return np.stack([src[order], dst[order]])
+
+
+def graph_from_edge_index(ei, n):
+    G = nx.Graph()
+    G.add_nodes_from(range(n))
+    G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+    return G
+
+
+def gen_paper(out):
+    from dcr.synth import named_graph
+
+    graphs = {k: (sorted_symmetric_edge_index(g), g.number_of_nodes()) for k, g in toy_graphs().items()}
+    for seed in range(24):
+        n = 12 + seed
+        g = nx.gnp_random_graph(n, 0.12 + 0.015 * (seed % 12), seed=seed)
+        graphs[f"gnp{seed}"] = (sorted_symmetric_edge_index(g), n)
+    for name in ("cornell", "wisconsin"):
+        graphs[name] = named_graph(name)
+    pack = {"names": np.array(sorted(graphs))}
+    for name, (ei, n) in graphs.items():
+        G = graph_from_edge_index(ei, n)
+        m = ei[0] < ei[1]
+        edges = np.stack([ei[0][m], ei[1][m]], axis=1)
+        vals = np.array([float(ref_naive.bfc_edge(G, int(a), int(b))) for a, b in edges], dtype=np.float64)
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/edges"] = edges
+        pack[f"{name}/bfc"] = vals
+    np.savez_compressed(out, **pack)
+    print("paper_kat:", len(graphs), "graphs")
+
+
+def dense_from_edge_index(ei, n):
+    A = torch.zeros(n, n)
+    A[ei[0], ei[1]] = 1.0
+    return A
+
+
+def gen_cuda(out):
+    graphs = {k: (sorted_symmetric_edge_index(g), g.number_of_nodes()) for k, g in toy_graphs().items()}
+    for seed in range(14):
+        n = 10 + 2 * seed
+        g = nx.gnp_random_graph(n, 0.2 + 0.03 * (seed % 5), seed=100 + seed)
+        graphs[f"gnp{seed}"] = (sorted_symmetric_edge_index(g), n)
+    pack = {"names": np.array(sorted(graphs))}
+    rng = np.random.default_rng(7)
+    for name, (ei, n) in graphs.items():
+        t0 = time.time()
+        A = dense_from_edge_index(ei, n)
+        C = ref_cuda.balanced_forman_curvature(A.clone())
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/C"] = C.numpy().copy()
+        # post_delta on the argmin edge (what SDRF asks for) and on two random edges, SDRF-style neighbour lists
+        G = graph_from_edge_index(ei, n)
+        ix = int(C.argmin())
+        picks = [(ix // n, ix % n)]
+        m = np.flatnonzero(ei[0] < ei[1])
+        for e in rng.choice(m, size=min(2, m.size), replace=False):
+            picks.append((int(ei[0][e]), int(ei[1][e])))
+        for q, (x, y) in enumerate(picks):
+            xn = list(G.neighbors(x)) + [x]
+            yn = list(G.neighbors(y)) + [y]
+            D = ref_cuda.balanced_forman_post_delta(A.clone(), x, y, xn, yn)
+            pack[f"{name}/pd{q}/xy"] = np.array([x, y], dtype=np.int64)
+            pack[f"{name}/pd{q}/xn"] = np.array(xn, dtype=np.int64)
+            pack[f"{name}/pd{q}/yn"] = np.array(yn, dtype=np.int64)
+            pack[f"{name}/pd{q}/D"] = D.numpy().copy()
+        pack[f"{name}/npd"] = np.int64(len(picks))
+        print(f"  cuda {name}: n={n} {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(out, **pack)
+    print("cuda_kat:", len(graphs), "graphs")
+
+
+def run_reference_rewire(ei, n, loops, bound, tau, seed):
+    """Unmodified ``rewire(..., 'bfc', ...)``; returns (edge_index_out, mutation log, uniforms)."""
+    log = []
+    orig_add, orig_rm = nx.Graph.add_edge, nx.Graph.remove_edge
+
+    def add_edge(self, u, v, **kw):
+        log.append((1, int(u), int(v)))
+        return orig_add(self, u, v, **kw)
+
+    def remove_edge(self, u, v):
+        log.append((-1, int(u), int(v)))
+        return orig_rm(self, u, v)
+
+    data = Data(edge_index=torch.from_numpy(ei).long())
+    data.num_nodes = n
+    np.random.seed(seed)
+    uniforms = np.random.RandomState(seed).random_sample(loops)
+    nx.Graph.add_edge, nx.Graph.remove_edge = add_edge, remove_edge
+    try:
+        out = ref_rewire(data, "bfc", loops, bound, tau)
+    finally:
+        nx.Graph.add_edge, nx.Graph.remove_edge = orig_add, orig_rm
+    return out.numpy().copy(), np.array(log, dtype=np.int64).reshape(-1, 3), uniforms
+
+
+def gen_sdrf(out):
+    cases = []
+    # (name, graph, loops, removal_bound, tau, seed)
+    cases.append(("gnp14_greedy", nx.gnp_random_graph(14, 0.25, seed=3), 6, 0.5, float("inf"), 11))
+    cases.append(("gnp14_tau12", nx.gnp_random_graph(14, 0.25, seed=3), 6, 0.5, 12, 12))
+    cases.append(("gnp16_tau3", nx.gnp_random_graph(16, 0.22, seed=5), 6, 0.3, 3, 13))
+    cases.append(("barbell_greedy", nx.barbell_graph(5, 2), 6, 1.2, float("inf"), 14))
+    cases.append(("grid_tau50", relabel(nx.grid_2d_graph(3, 4)), 5, 0.1, 50, 15))
+    cases.append(("tree_greedy", nx.balanced_tree(2, 3), 5, 0.9, float("inf"), 16))
+    cases.append(("gnp18_nobound", nx.gnp_random_graph(18, 0.2, seed=9), 6, 100.0, float("inf"), 17))
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, g, loops, bound, tau, seed in cases:
+        t0 = time.time()
+        ei = sorted_symmetric_edge_index(g)
+        n = g.number_of_nodes()
+        eo, log, uni = run_reference_rewire(ei, n, loops, bound, tau, seed)
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/loops"] = np.int64(loops)
+        pack[f"{name}/bound"] = np.float64(bound)
+        pack[f"{name}/tau"] = np.float64(tau)
+        pack[f"{name}/uniforms"] = uni
+        pack[f"{name}/out"] = eo
+        pack[f"{name}/log"] = log
+        print(f"  sdrf {name}: n={n} loops={loops} log={len(log)} {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(out, **pack)
+    print("sdrf_seq:", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["paper", "cuda", "sdrf"]
+    if "paper" in which:
+        gen_paper(os.path.join(HERE, "paper_kat.npz"))
+    if "cuda" in which:
+        gen_cuda(os.path.join(HERE, "cuda_kat.npz"))
+    if "sdrf" in which:
+        gen_sdrf(os.path.join(HERE, "sdrf_seq.npz"))
