@@ -1,0 +1,423 @@
+// dcr_bfc_paper.cu — paper-flavour Balanced Forman curvature over a sorted CSR (the headline kernel).
+//
+// Takes over bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).  Per undirected edge (i,j), with
+//   M_i = N(i) \ N(j) \ {j},  M_j = N(j) \ N(i) \ {i}            (the "pure" neighbours of each endpoint)
+// the reference's sets are
+//   triangles = N(i) ∩ N(j)                                                   (:25)
+//   squares_1 = {k in M_i : N(k) ∩ M_j != {}},  squares_2 mirrored            (:26-29)
+//   gamma     = max over squares of |N(k) ∩ M_j| resp. |N(m) ∩ M_i|           (:36-37; the "-1" removes i / j)
+// i.e. everything is a function of cnt(m) = |N(m) ∩ M_i| for m in M_j and cnt(k) = |N(k) ∩ M_j| for k in M_i.
+//
+// Mapping to the GPU.  One TEAM per edge — a warp for edges with d_i + d_j <= 512, a whole CTA above that:
+//   1. the team builds ONE open-addressing hash table in shared memory holding N(i) ∪ N(j) \ {i,j}, each key
+//      tagged 1 (only in N(i)), 2 (only in N(j)) or 3 (both = triangle node); #tag-3 keys = #triangles;
+//   2. pass A: for every m with tag 2 a warp streams the neighbour list N(m) with coalesced 128-byte loads,
+//      4 independent loads in flight per lane, one shared-memory probe per element, ballot/popc count;
+//   3. pass B: the mirrored scan (skipped when pass A found no square: the bipartite graph M_i–M_j is empty).
+// Global traffic is exactly the algorithmic gather of SURVEY.md §8d: the two endpoint lists once and every 2-hop
+// list once per edge; the CSR of the benchmark graphs is L2-resident, so the kernel is bound by L2->SM gather
+// bandwidth and shared-memory probe throughput, not by DRAM.
+// Edges are bucketed by class and by log2(work) on the device (heavy first) and teams pull edges from a global
+// counter, so power-law hubs do not serialise the tail.  Grids are persistent: a multiple of the SM count.
+#include "dcr_common.cuh"
+
+namespace dcr {
+
+constexpr uint32_t EMPTY = 0xffffffffu;
+constexpr uint32_t KEYMASK = 0x3fffffffu;
+constexpr int WARP_SLOTS = 1024;             // per-warp table: 4 KB, d_i + d_j <= 512
+constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
+constexpr int CTA_SLOTS = 32768;             // per-CTA table: 128 KB, d_i + d_j <= 16384
+constexpr int CTA_THREADS = 512;
+constexpr int N_CLASSES = 3;                 // 0 = warp team, 1 = CTA team (smem table), 2 = CTA team (global table)
+constexpr int BUCKETS_PER_CLASS = 64;
+constexpr int N_BUCKETS = N_CLASSES * BUCKETS_PER_CLASS;
+constexpr int UNROLL = 4;
+
+struct PaperPlan {           // lives at the head of the scratch buffer
+    unsigned int hist[N_BUCKETS];
+    unsigned int cursor[N_BUCKETS];
+    unsigned int bucket_off[N_BUCKETS + 1];
+    unsigned int class_begin[N_CLASSES + 1];
+    unsigned int next[N_CLASSES];      // work-stealing counters
+    unsigned int pad[3];
+};
+
+struct PaperArgs {
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const int32_t* esrc;
+    const int32_t* edst;
+    int64_t e_first, e_stride, count;  // this call handles edges e = e_first + t*e_stride, t in [0,count)
+    int32_t* out_tri;
+    int32_t* out_sq_i;
+    int32_t* out_sq_j;
+    int32_t* out_gamma;
+    double* out_bfc;
+    PaperPlan* plan;
+    const int64_t* node_s;
+    uint8_t* bucket;       // [count]
+    uint32_t* order;       // [count] local indices t grouped by bucket
+    uint32_t* gtables;     // class-2 tables in global memory, gslots per CTA
+    uint32_t gslots;
+};
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
+
+// tag of `key` in the table (0 = absent)
+__device__ __forceinline__ uint32_t probe(const uint32_t* tab, uint32_t mask, int shift, uint32_t key) {
+    uint32_t h = hash_slot(key, shift);
+    while (true) {
+        const uint32_t v = tab[h];
+        if (v == EMPTY) return 0u;
+        if ((v & KEYMASK) == key) return v >> 30;
+        h = (h + 1) & mask;
+    }
+}
+
+// insert key with `tag`, or OR the tag into an existing entry; returns true if the key was already present
+__device__ __forceinline__ bool insert_or_tag(uint32_t* tab, uint32_t mask, int shift, uint32_t key, uint32_t tag) {
+    uint32_t h = hash_slot(key, shift);
+    const uint32_t val = key | (tag << 30);
+    while (true) {
+        uint32_t v = tab[h];
+        if (v == EMPTY) {
+            v = atomicCAS(&tab[h], EMPTY, val);
+            if (v == EMPTY) return false;
+        }
+        if ((v & KEYMASK) == key) {
+            atomicOr(&tab[h], tag << 30);
+            return true;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// bfc_naive.py:31-32 / :39-40 evaluated left to right in fp64 with explicitly rounded operations
+__device__ __forceinline__ double paper_value(int d1, int d2, int tri, int sq1, int sq2, int gamma) {
+    const int dmax = max(d1, d2), dmin = min(d1, d2);
+    double t = __ddiv_rn(2.0, (double)d1);
+    t = __dadd_rn(t, __ddiv_rn(2.0, (double)d2));
+    t = __dadd_rn(t, -2.0);
+    t = __dadd_rn(t, __ddiv_rn((double)(2 * (long long)tri), (double)dmax));
+    t = __dadd_rn(t, __ddiv_rn((double)tri, (double)dmin));
+    if (sq1 > 0 && sq2 > 0) {
+        double u = __ddiv_rn(1.0, (double)gamma);
+        u = __ddiv_rn(u, (double)dmax);
+        u = __dmul_rn(u, (double)(sq1 + sq2));
+        t = __dadd_rn(t, u);
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// planning kernels: S_v, per-edge class/bucket, bucket offsets, order
+// ------------------------------------------------------------------------------------------------------------
+__global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                              int64_t* __restrict__ node_s) {
+    const int lane = threadIdx.x & 31;
+    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (v >= n) return;
+    const int b = rowptr[v], e = rowptr[v + 1];
+    int64_t s = 0;
+    for (int p = b + lane; p < e; p += 32) {
+        const int k = colidx[p];
+        s += rowptr[k + 1] - rowptr[k];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) node_s[v] = s;
+}
+
+__global__ void classify_kernel(PaperArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const int64_t e = a.e_first + t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+    if (min(di, dj) <= 1) {  // bfc_naive.py:18-19: deg_min == 1 -> 0 (no triangle is possible either)
+        a.out_tri[t] = 0; a.out_sq_i[t] = 0; a.out_sq_j[t] = 0; a.out_gamma[t] = 0; a.out_bfc[t] = 0.0;
+        a.bucket[t] = 255;
+        return;
+    }
+    const long long work = (a.node_s[i] - dj) + (a.node_s[j] - di) + di + dj;
+    const int need = di + dj;
+    int cls = need * 2 <= WARP_SLOTS ? 0 : (need * 2 <= CTA_SLOTS ? 1 : 2);
+    int lg = 63 - __clzll(work | 1);
+    int b = cls * BUCKETS_PER_CLASS + (BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1));  // heavy first
+    a.bucket[t] = (uint8_t)b;
+    atomicAdd(&a.plan->hist[b], 1u);
+}
+
+__global__ void bucket_scan_kernel(PaperPlan* plan) {
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int b = 0; b < N_BUCKETS; ++b) {
+            if (b % BUCKETS_PER_CLASS == 0) plan->class_begin[b / BUCKETS_PER_CLASS] = acc;
+            plan->bucket_off[b] = acc;
+            acc += plan->hist[b];
+        }
+        plan->bucket_off[N_BUCKETS] = acc;
+        plan->class_begin[N_CLASSES] = acc;
+    }
+}
+
+__global__ void order_kernel(PaperArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const int b = a.bucket[t];
+    if (b == 255) return;
+    const unsigned int pos = a.plan->bucket_off[b] + atomicAdd(&a.plan->cursor[b], 1u);
+    a.order[pos] = (uint32_t)t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the edge kernel.  CTA_TEAM = false: each warp is a team with a private table slice; true: the CTA is the team.
+// ------------------------------------------------------------------------------------------------------------
+template <bool CTA_TEAM>
+__device__ __forceinline__ void team_sync() {
+    if (CTA_TEAM) __syncthreads(); else __syncwarp();
+}
+
+// Stream the neighbour lists of all keys of `list` (a row of the CSR) that carry `scan_tag`, counting per list
+// the elements that carry `hit_tag`.  Returns per-warp partial (#lists with a hit, max hits); chunk c of 32 list
+// heads is handled by warp (c mod team_warps).
+template <bool CTA_TEAM>
+__device__ __forceinline__ void scan_side(const PaperArgs& a, const uint32_t* tab, uint32_t mask, int shift,
+                                          int list_begin, int list_len, uint32_t scan_tag, uint32_t hit_tag,
+                                          int team_warp, int team_warps, int lane, int& sq, int& gmax) {
+    const int32_t* __restrict__ rowptr = a.rowptr;
+    const int32_t* __restrict__ colidx = a.colidx;
+    for (int c0 = team_warp * 32; c0 < list_len; c0 += team_warps * 32) {
+        const int t = c0 + lane;
+        int m = -1, mb = 0, md = 0;
+        if (t < list_len) {
+            m = colidx[list_begin + t];
+            if (probe(tab, mask, shift, (uint32_t)m) == scan_tag) {
+                mb = rowptr[m];
+                md = rowptr[m + 1] - mb;
+            } else {
+                m = -1;
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, m >= 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int beg = __shfl_sync(FULL, mb, src);
+            const int deg = __shfl_sync(FULL, md, src);
+            int cnt = 0;
+            for (int base = 0; base < deg; base += 32 * UNROLL) {
+                int k[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int idx = base + u * 32 + lane;
+                    k[u] = idx < deg ? colidx[beg + idx] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const bool hit = k[u] >= 0 && probe(tab, mask, shift, (uint32_t)k[u]) == hit_tag;
+                    cnt += __popc(__ballot_sync(FULL, hit));
+                }
+            }
+            sq += cnt > 0;
+            gmax = max(gmax, cnt);
+        }
+    }
+}
+
+template <bool CTA_TEAM, bool GLOBAL_TABLE>
+__global__ void __launch_bounds__(CTA_TEAM ? CTA_THREADS : WARP_TEAM_WARPS * 32)
+paper_edge_kernel(PaperArgs a, int cls) {
+    extern __shared__ uint32_t smem_tab[];
+    __shared__ unsigned int s_idx;
+    __shared__ int s_red[5];  // tri, sqA, gA, sqB, gB
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int team_warps = CTA_TEAM ? (CTA_THREADS / 32) : 1;
+    const int team_warp = CTA_TEAM ? warp : 0;
+    const int team_threads = team_warps * 32;
+    const int team_tid = CTA_TEAM ? (int)threadIdx.x : lane;
+    uint32_t* tab = GLOBAL_TABLE ? a.gtables + (size_t)blockIdx.x * a.gslots
+                                 : (CTA_TEAM ? smem_tab : smem_tab + warp * WARP_SLOTS);
+    const unsigned int cbeg = a.plan->class_begin[cls];
+    const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
+
+    while (true) {
+        unsigned int idx;
+        if (CTA_TEAM) {
+            if (threadIdx.x == 0) {
+                s_idx = atomicAdd(&a.plan->next[cls], 1u);
+                s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
+            }
+            __syncthreads();
+            idx = s_idx;
+        } else {
+            idx = 0;
+            if (lane == 0) idx = atomicAdd(&a.plan->next[cls], 1u);
+            idx = __shfl_sync(FULL, idx, 0);
+        }
+        if (idx >= cnum) break;
+        const uint32_t t = a.order[cbeg + idx];
+        const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+        const int i = a.esrc[e], j = a.edst[e];
+        const int si = a.rowptr[i], di = a.rowptr[i + 1] - si;
+        const int sj = a.rowptr[j], dj = a.rowptr[j + 1] - sj;
+
+        // table size: power of two >= 2*(d_i+d_j), at least 64 slots
+        const int need = 2 * (di + dj);
+        int lg = 32 - __clz(max(need, 64) - 1);
+        const uint32_t slots = 1u << lg;
+        const uint32_t mask = slots - 1;
+        const int shift = 32 - lg;
+
+        for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
+        team_sync<CTA_TEAM>();
+        for (int p = team_tid; p < di; p += team_threads) {
+            const int k = a.colidx[si + p];
+            if (k != j) insert_or_tag(tab, mask, shift, (uint32_t)k, 1u);
+        }
+        team_sync<CTA_TEAM>();
+        int tri = 0;
+        for (int p = team_tid; p < dj; p += team_threads) {
+            const int k = a.colidx[sj + p];
+            if (k != i) tri += insert_or_tag(tab, mask, shift, (uint32_t)k, 2u);
+        }
+        tri = warp_sum(tri);
+        if (CTA_TEAM) {
+            if (lane == 0 && tri) atomicAdd(&s_red[0], tri);
+        }
+        team_sync<CTA_TEAM>();
+
+        // pass A: lists of m in M_j (tag 2), hits in M_i (tag 1)  -> squares at j
+        int sqA = 0, gA = 0, sqB = 0, gB = 0;
+        scan_side<CTA_TEAM>(a, tab, mask, shift, sj, dj, 2u, 1u, team_warp, team_warps, lane, sqA, gA);
+        if (CTA_TEAM) {
+            if (lane == 0 && sqA) { atomicAdd(&s_red[1], sqA); atomicMax(&s_red[2], gA); }
+            __syncthreads();
+            sqA = s_red[1]; gA = s_red[2]; tri = s_red[0];
+        }
+        // pass B: lists of k in M_i (tag 1), hits in M_j (tag 2)  -> squares at i; empty iff pass A was empty
+        if (sqA > 0) {
+            scan_side<CTA_TEAM>(a, tab, mask, shift, si, di, 1u, 2u, team_warp, team_warps, lane, sqB, gB);
+            if (CTA_TEAM) {
+                if (lane == 0 && sqB) { atomicAdd(&s_red[3], sqB); atomicMax(&s_red[4], gB); }
+                __syncthreads();
+                sqB = s_red[3]; gB = s_red[4];
+            }
+        }
+        if (team_tid == 0) {
+            const int gamma = (sqA > 0 && sqB > 0) ? max(gA, gB) : 0;
+            a.out_tri[t] = tri;
+            a.out_sq_i[t] = sqB;
+            a.out_sq_j[t] = sqA;
+            a.out_gamma[t] = gamma;
+            a.out_bfc[t] = paper_value(di, dj, tri, sqB, sqA, gamma);
+        }
+        team_sync<CTA_TEAM>();  // table / s_red reuse
+    }
+}
+
+}  // namespace dcr
+
+using namespace dcr;
+
+static inline uint32_t next_pow2_u32(uint64_t v) {
+    uint32_t p = 64;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ScratchLayout {
+    size_t plan, node_s, bucket, order, gtables, total;
+    uint32_t gslots;
+    int g_ctas;
+};
+
+static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
+    ScratchLayout L;
+    size_t off = 0;
+    L.plan = off; off = align_up(off + sizeof(PaperPlan), 256);
+    L.node_s = off; off = align_up(off + (size_t)n * sizeof(int64_t), 256);
+    L.bucket = off; off = align_up(off + (size_t)count, 256);
+    L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
+    L.gslots = 0;
+    L.g_ctas = 0;
+    L.gtables = off;
+    if ((int64_t)max_degree * 4 > CTA_SLOTS) {  // some edge may need a table beyond shared memory
+        L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
+        L.g_ctas = sm_count();
+        off = align_up(off + (size_t)L.g_ctas * L.gslots * sizeof(uint32_t), 256);
+    }
+    L.total = off;
+    return L;
+}
+
+extern "C" int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t count) {
+    return (int64_t)scratch_layout(n, max_degree, count).total;
+}
+
+extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
+                             const int32_t* esrc, const int32_t* edst, int64_t e_first, int64_t e_stride,
+                             int64_t count, int32_t* out_tri, int32_t* out_sq_i, int32_t* out_sq_j,
+                             int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
+                             void* stream) {
+    if (count <= 0 || n <= 0) return 0;
+    if (count > 0xfffffff0LL) { set_error("dcr_bfc_paper: more than 2^32 edges per call"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const ScratchLayout L = scratch_layout(n, max_degree, count);
+    if ((int64_t)L.total > scratch_bytes) {
+        set_error("dcr_bfc_paper: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)L.total);
+        return 1;
+    }
+    char* base = (char*)scratch;
+    PaperArgs a;
+    a.rowptr = rowptr; a.colidx = colidx; a.esrc = esrc; a.edst = edst;
+    a.e_first = e_first; a.e_stride = e_stride; a.count = count;
+    a.out_tri = out_tri; a.out_sq_i = out_sq_i; a.out_sq_j = out_sq_j; a.out_gamma = out_gamma; a.out_bfc = out_bfc;
+    a.plan = (PaperPlan*)(base + L.plan);
+    int64_t* node_s = (int64_t*)(base + L.node_s);
+    a.node_s = node_s;
+    a.bucket = (uint8_t*)(base + L.bucket);
+    a.order = (uint32_t*)(base + L.order);
+    a.gtables = (uint32_t*)(base + L.gtables);
+    a.gslots = L.gslots;
+
+    DCR_CUDA(cudaMemsetAsync(a.plan, 0, sizeof(PaperPlan), st));
+    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s);
+    DCR_LAUNCH_CHECK();
+    const unsigned tb = (unsigned)((count + 255) / 256);
+    classify_kernel<<<tb, 256, 0, st>>>(a);
+    DCR_LAUNCH_CHECK();
+    bucket_scan_kernel<<<1, 32, 0, st>>>(a.plan);
+    DCR_LAUNCH_CHECK();
+    order_kernel<<<tb, 256, 0, st>>>(a);
+    DCR_LAUNCH_CHECK();
+
+    const int sms = sm_count();
+    // heavy classes first: they own the long tail
+    if (L.gslots) {
+        paper_edge_kernel<true, true><<<L.g_ctas, CTA_THREADS, 0, st>>>(a, 2);
+        DCR_LAUNCH_CHECK();
+    }
+    {
+        static bool attr_done = false;
+        const int smem = CTA_SLOTS * (int)sizeof(uint32_t);
+        if (!attr_done) {
+            DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<true, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_done = true;
+        }
+        paper_edge_kernel<true, false><<<sms, CTA_THREADS, smem, st>>>(a, 1);
+        DCR_LAUNCH_CHECK();
+    }
+    {
+        const int smem = WARP_TEAM_WARPS * WARP_SLOTS * (int)sizeof(uint32_t);  // 32 KB per CTA
+        paper_edge_kernel<false, false><<<sms * 6, WARP_TEAM_WARPS * 32, smem, st>>>(a, 0);
+        DCR_LAUNCH_CHECK();
+    }
+    return 0;
+}

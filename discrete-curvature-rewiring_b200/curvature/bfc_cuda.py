@@ -1,0 +1,40 @@
+"""Drop-in for the reference's ``curvature/bfc_cuda.py`` (same module path, names, arguments, return values).
+
+``balanced_forman_curvature(A, C=None)``                              reference: curvature/bfc_cuda.py:51-65
+``balanced_forman_post_delta(A, x, y, i_neighbors, j_neighbors, D=None)``           curvature/bfc_cuda.py:144-159
+
+The reference multiplies dense ``A @ A`` (:53, :146) and runs an O(N^3) numba kernel.  Here the dense fp32 ``A`` is
+converted on the device to a sorted CSR (one streaming pass), the hand-written sm_100a kernels of ``libdcr.so``
+compute the same numbers from sorted-list intersections, and the dense ``C`` / ``D`` the callers expect is written
+back.  Values are the fp32 numbers the compiled reference kernel stores (fp64 arithmetic, two fp32 roundings).
+Covered: symmetric 0/1 ``A`` without self-loops (what ``is_undirected=True`` produces, sdrf_cuda_bfc.py:26-29);
+anything else raises ``NotImplementedError`` — there is no CPU or dense fallback.
+"""
+import torch
+
+from dcr import bfc as _bfc
+
+
+def balanced_forman_curvature(A, C=None):
+    N = A.shape[0]
+    csr = _bfc.DeviceCSR.from_dense(A)
+    out = _bfc.cuda_flavour(csr, want_fields=False)
+    if C is None:
+        C = torch.empty(N, N, dtype=torch.float32, device=A.device)   # every element is written by the scatter
+    elif C.dtype != torch.float32 or not C.is_contiguous() or C.shape != (N, N):
+        raise ValueError("C must be a contiguous float32 [N, N] tensor")
+    _bfc.scatter_dense(csr, out["c32"], C)
+    return C
+
+
+def balanced_forman_post_delta(A, x, y, i_neighbors, j_neighbors, D=None):
+    csr = _bfc.DeviceCSR.from_dense(A)
+    tri = _bfc.support(csr)
+    i_nb = torch.as_tensor(list(i_neighbors), dtype=torch.int32).to(A.device)
+    j_nb = torch.as_tensor(list(j_neighbors), dtype=torch.int32).to(A.device)
+    if D is None:
+        D = torch.zeros(len(i_neighbors), len(j_neighbors), dtype=torch.float32, device=A.device)
+    elif D.dtype != torch.float32 or not D.is_contiguous() or D.shape != (len(i_neighbors), len(j_neighbors)):
+        raise ValueError("D must be a contiguous float32 [len(i_neighbors), len(j_neighbors)] tensor")
+    _bfc.post_delta(csr, tri, int(x), int(y), i_nb, j_nb, D)
+    return D

@@ -1,0 +1,161 @@
+"""Device-side BFC entry points over a sorted CSR (thin wrappers: allocate outputs, call the C ABI).
+
+PyTorch owns every buffer; the kernels are launched on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+class DeviceCSR:
+    """Symmetric, self-loop-free, sorted CSR resident in HBM: ``rowptr`` int32 ``[n+1]``, ``colidx`` int32."""
+
+    def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, n: int, max_degree: int | None = None):
+        self.rowptr = rowptr
+        self.colidx = colidx
+        self.n = int(n)
+        self.nnz = int(colidx.numel())
+        if max_degree is None:
+            max_degree = int((rowptr[1:] - rowptr[:-1]).max().item()) if n > 0 else 0
+        self.max_degree = int(max_degree)
+        self._edges = None
+
+    @classmethod
+    def from_host(cls, rowptr: np.ndarray, colidx: np.ndarray, device="cuda") -> "DeviceCSR":
+        L.require_cuda()
+        rp = torch.from_numpy(np.ascontiguousarray(rowptr, dtype=np.int32)).to(device)
+        ci = torch.from_numpy(np.ascontiguousarray(colidx, dtype=np.int32)).to(device)
+        deg = np.diff(np.asarray(rowptr, dtype=np.int64))
+        return cls(rp, ci, len(rowptr) - 1, int(deg.max()) if deg.size else 0)
+
+    @classmethod
+    def from_dense(cls, A: torch.Tensor, validate: bool = True) -> "DeviceCSR":
+        """CSR of a dense fp32 ``[N,N]`` CUDA adjacency (the reference's ``A``).  One host sync (nnz)."""
+        L.require_cuda()
+        if not (A.is_cuda and A.dim() == 2 and A.shape[0] == A.shape[1]):
+            raise ValueError("A must be a square CUDA tensor")
+        if A.dtype != torch.float32 or not A.is_contiguous():
+            A = A.to(torch.float32).contiguous()
+        n = A.shape[0]
+        lib = L.load()
+        st = L.current_stream()
+        counts = torch.empty(max(n, 1), dtype=torch.int32, device=A.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=A.device)
+        L.check(lib.dcr_dense_count(A.data_ptr(), n, counts.data_ptr(), flags.data_ptr(), st), "dcr_dense_count")
+        rowptr = torch.zeros(n + 1, dtype=torch.int32, device=A.device)
+        rowptr[1:] = torch.cumsum(counts[:n], 0, dtype=torch.int32)
+        host = torch.stack([rowptr[n], flags[0], counts[:n].max() if n else rowptr[n]]).cpu()
+        nnz, fl, maxdeg = int(host[0]), int(host[1]), int(host[2])
+        if validate and fl:
+            what = [s for b, s in ((1, "entries other than 0/1"), (2, "a non-zero diagonal (self-loops)"),
+                                   (4, "asymmetry (directed graph)")) if fl & b]
+            raise NotImplementedError(
+                "the B200 BFC kernels cover symmetric 0/1 adjacency without self-loops (is_undirected=True, the only "
+                "mode the reference's callers use); A has " + ", ".join(what))
+        colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=A.device)[:nnz]
+        L.check(lib.dcr_dense_fill(A.data_ptr(), n, rowptr.data_ptr(), colidx.data_ptr(), st), "dcr_dense_fill")
+        return cls(rowptr, colidx, n, maxdeg)
+
+    def undirected_edges(self):
+        """``(esrc, edst, entry)`` int32/int32/int64 device tensors: entries with row < col, in CSR order."""
+        if self._edges is None:
+            deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            rows = torch.repeat_interleave(torch.arange(self.n, device=self.rowptr.device, dtype=torch.int32), deg)
+            entry = torch.nonzero(rows < self.colidx, as_tuple=False).flatten()
+            self._edges = (rows[entry].contiguous(), self.colidx[entry].contiguous(), entry)
+        return self._edges
+
+
+def support(csr: DeviceCSR, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``A2[i,j]`` (#common neighbours) of every directed entry, int32 ``[nnz]``."""
+    lib = L.load()
+    tri = out if out is not None else torch.empty(max(csr.nnz, 1), dtype=torch.int32, device=csr.colidx.device)[:csr.nnz]
+    L.check(lib.dcr_bfc_support(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(), 0, csr.nnz,
+                                L.current_stream()), "dcr_bfc_support")
+    return tri
+
+
+def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None, want_fields: bool = True,
+                 tri: torch.Tensor | None = None) -> dict:
+    """cuda-flavour BFC per directed entry: ``tri, sharp, lam`` (int32), ``c64`` (fp64), ``c32`` (fp32)."""
+    lib = L.load()
+    dev = csr.colidx.device
+    nnz = csr.nnz
+    hi = nnz if entry_hi is None else entry_hi
+    if tri is None:
+        tri = support(csr)
+    alloc = lambda dt: torch.zeros(max(nnz, 1), dtype=dt, device=dev)[:nnz]
+    c32 = alloc(torch.float32)
+    sharp = alloc(torch.int32) if want_fields else None
+    lam = alloc(torch.int32) if want_fields else None
+    c64 = alloc(torch.float64) if want_fields else None
+    L.check(lib.dcr_bfc_cuda_flavour(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(),
+                                     L.ptr(sharp), L.ptr(lam), L.ptr(c64), c32.data_ptr(), entry_lo, hi,
+                                     L.current_stream()), "dcr_bfc_cuda_flavour")
+    return {"tri": tri, "sharp": sharp, "lam": lam, "c64": c64, "c32": c32}
+
+
+class PaperWorkspace:
+    """Reusable outputs + scratch of the paper-flavour kernel for one (graph, shard) shape."""
+
+    def __init__(self, csr: DeviceCSR, count: int):
+        lib = L.load()
+        dev = csr.colidx.device
+        self.count = int(count)
+        c = max(self.count, 1)
+        self.tri = torch.empty(c, dtype=torch.int32, device=dev)
+        self.sq_i = torch.empty(c, dtype=torch.int32, device=dev)
+        self.sq_j = torch.empty(c, dtype=torch.int32, device=dev)
+        self.gamma = torch.empty(c, dtype=torch.int32, device=dev)
+        self.bfc = torch.empty(c, dtype=torch.float64, device=dev)
+        self.scratch_bytes = int(lib.dcr_bfc_paper_scratch_bytes(csr.n, csr.max_degree, self.count))
+        self.scratch = torch.empty(max(self.scratch_bytes, 256), dtype=torch.uint8, device=dev)
+
+
+def shard_count(n_edges: int, rank: int, world: int) -> int:
+    """Number of edges ``e = rank + t*world`` below ``n_edges``."""
+    return max(0, (n_edges - rank + world - 1) // world)
+
+
+def paper_flavour(csr: DeviceCSR, rank: int = 0, world: int = 1, ws: PaperWorkspace | None = None,
+                  edges=None) -> dict:
+    """Paper-flavour BFC for the undirected edges ``e = rank + t*world`` (compact outputs indexed by ``t``).
+
+    ``edges``: optional ``(esrc, edst)`` int32 device tensors replacing the CSR's own ``row < col`` edge list.
+    """
+    lib = L.load()
+    if edges is None:
+        esrc, edst, _ = csr.undirected_edges()
+    else:
+        esrc, edst = edges
+    n_edges = int(esrc.numel())
+    count = shard_count(n_edges, rank, world)
+    if ws is None:
+        ws = PaperWorkspace(csr, count)
+    if count > 0:
+        L.check(lib.dcr_bfc_paper(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, csr.max_degree,
+                                  esrc.data_ptr(), edst.data_ptr(), rank, world, count, ws.tri.data_ptr(),
+                                  ws.sq_i.data_ptr(), ws.sq_j.data_ptr(), ws.gamma.data_ptr(), ws.bfc.data_ptr(),
+                                  ws.scratch.data_ptr(), ws.scratch_bytes, L.current_stream()), "dcr_bfc_paper")
+    return {"esrc": esrc, "edst": edst, "count": count, "tri": ws.tri[:count], "sq_i": ws.sq_i[:count],
+            "sq_j": ws.sq_j[:count], "gamma": ws.gamma[:count], "bfc": ws.bfc[:count], "ws": ws}
+
+
+def scatter_dense(csr: DeviceCSR, vals: torch.Tensor, C: torch.Tensor) -> torch.Tensor:
+    """Write the legacy dense ``[N,N]`` fp32 matrix (zeros off the entries) in place."""
+    lib = L.load()
+    L.check(lib.dcr_scatter_dense(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, vals.data_ptr(),
+                                  C.data_ptr(), L.current_stream()), "dcr_scatter_dense")
+    return C
+
+
+def post_delta(csr: DeviceCSR, tri: torch.Tensor, x: int, y: int, i_nb: torch.Tensor, j_nb: torch.Tensor,
+               D: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    L.check(lib.dcr_post_delta(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(), int(x), int(y),
+                               i_nb.data_ptr(), int(i_nb.numel()), j_nb.data_ptr(), int(j_nb.numel()), D.data_ptr(),
+                               L.current_stream()), "dcr_post_delta")
+    return D

@@ -78,13 +78,18 @@ def chung_lu_graph(n: int, e: int, alpha: float, p_tri: float, seed: int) -> np.
         k = max(1024, int((e_base - keys.size) * 1.3))
         keys = add_pairs(keys, sample_nodes(k), sample_nodes(k), e_base)
 
-    # attach isolated nodes with one edge each to a weight-sampled partner
-    deg = np.bincount(np.concatenate([keys // n, keys % n]), minlength=n)
-    iso = np.flatnonzero(deg == 0)
+    # attach isolated nodes with one edge each to a weight-sampled partner; if the edge budget cannot hold the
+    # base edges plus one edge per isolated node, give back the most recently drawn base edges until it can
+    def isolated(k):
+        return np.flatnonzero(np.bincount(np.concatenate([k // n, k % n]), minlength=n) == 0)
+
+    iso = isolated(keys)
+    while keys.size + iso.size > e and keys.size > 0:
+        keys = keys[: max(0, e - iso.size - max(1, iso.size // 8))]
+        iso = isolated(keys)
     while iso.size and keys.size < e:
         keys = add_pairs(keys, iso, sample_nodes(iso.size), e)
-        deg = np.bincount(np.concatenate([keys // n, keys % n]), minlength=n)
-        iso = np.flatnonzero(deg == 0)
+        iso = isolated(keys)
 
     # triangle closure: pick a random directed edge (u,v) and a random neighbour w of v, add (u,w)
     stall = 0

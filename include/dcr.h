@@ -35,6 +35,7 @@ extern "C" {
 #define DCR_SDRF_REMOVE_NONEDGE 4 /* argmax fell on a non-edge and exceeded removal_bound (networkx: NetworkXError) */
 #define DCR_SDRF_NO_UNIFORM 5     /* ran out of host-supplied uniforms                                            */
 #define DCR_SDRF_ARENA_FULL 6     /* adjacency arena exhausted (create with a larger max_additions)               */
+#define DCR_SDRF_TOO_MANY_CANDIDATES 7 /* (deg x+1)(deg y+1) exceeds the candidate scratch of the state          */
 
 const char* dcr_last_error(void);
 int dcr_version(void);
@@ -74,20 +75,19 @@ int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx, int n, co
 
 /* ------------------------------------------------------------------------------------------------------------
  * paper-flavour BFC over CSR.  Replaces bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).
- * Undirected edges are given explicitly: edge e = (esrc[e], edst[e]) with esrc < edst; the call processes
- * edges order[lo..hi) (order = a permutation of edge ids, heavy edges first; NULL = identity) and writes
- * out_*[e] at the edge id:  tri, sq_i (#squares at esrc), sq_j (#squares at edst), gamma (0 where the
- * reference never computes it), bfc (fp64, evaluated left to right as bfc_naive.py:31-32,39-40).
- * scratch: opaque device workspace of dcr_bfc_paper_scratch_bytes(n, max_degree) bytes.
+ * Undirected edges are given explicitly: edge e = (esrc[e], edst[e]).  One call handles the strided subset
+ * e = e_first + t*e_stride, t in [0,count) (single GPU: e_first=0, e_stride=1, count=E; rank r of W ranks:
+ * e_first=r, e_stride=W) and writes the COMPACT outputs out_*[t]:  tri, sq_i (#squares at esrc), sq_j
+ * (#squares at edst), gamma (0 where the reference never computes it), bfc (fp64, evaluated left to right
+ * as bfc_naive.py:31-32,39-40).  Edges are classed and ordered heavy-first on the device inside the call.
+ * scratch: opaque device workspace of dcr_bfc_paper_scratch_bytes(n, max_degree, count) bytes;
+ * max_degree = the largest row length of the CSR.
  * ---------------------------------------------------------------------------------------------------------- */
-int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree);
-/* work[e] = estimated 2-hop entries to scan for edge e (used for ordering / sharding), int64. */
-int dcr_bfc_paper_work(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc,
-                       const int32_t* edst, int64_t n_edges, int64_t* node_s, int64_t* work, void* stream);
-int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc, const int32_t* edst,
-                  const int32_t* order, int64_t lo, int64_t hi, int32_t* out_tri, int32_t* out_sq_i,
-                  int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
-                  void* stream);
+int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t count);
+int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree, const int32_t* esrc,
+                  const int32_t* edst, int64_t e_first, int64_t e_stride, int64_t count, int32_t* out_tri,
+                  int32_t* out_sq_i, int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc, void* scratch,
+                  int64_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Candidate scoring.  Replaces _balanced_forman_post_delta / balanced_forman_post_delta

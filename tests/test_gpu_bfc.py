@@ -1,0 +1,252 @@
+"""GPU parity, BFC: the CUDA kernels (through the C ABI) against the oracle and the golden fixtures.
+
+Bars: integer counts bit-exact; paper-flavour fp64 value bit-exact (same operation order, explicit rounding);
+cuda-flavour fp32 image bit-exact against the compiled-dataflow oracle and within 1e-6 of the simulator goldens.
+"""
+import numpy as np
+import pytest
+
+from helpers import dense_of, gnp, golden, sym_edge_index, toy_graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _csr(ei, n):
+    from dcr import bfc, graph
+    rowptr, col = graph.undirected_csr(ei, n)
+    return bfc.DeviceCSR.from_host(rowptr, col)
+
+
+def _paper_gpu(ei, n):
+    from dcr import bfc
+    csr = _csr(ei, n)
+    out = bfc.paper_flavour(csr)
+    f = {k: out[k].cpu().numpy() for k in ("tri", "sq_i", "sq_j", "gamma", "bfc")}
+    f["edges"] = np.stack([out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()], axis=1).astype(np.int64)
+    return f
+
+
+def _check_paper(ei, n, tag):
+    from oracle.paper_flavour import bfc_paper
+    got = _paper_gpu(ei, n)
+    ref = bfc_paper(ei, n, got["edges"])
+    for k in ("tri", "sq_i", "sq_j", "gamma"):
+        assert np.array_equal(got[k], ref[k]), (tag, k, np.flatnonzero(got[k] != ref[k])[:5])
+    assert np.array_equal(got["bfc"], ref["bfc"]), (tag, np.abs(got["bfc"] - ref["bfc"]).max())
+    return got
+
+
+def test_paper_flavour_golden_reference_values():
+    z = golden("paper_kat.npz")
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        if ei.shape[1] == 0:
+            continue
+        got = _paper_gpu(ei, n)
+        assert np.array_equal(got["edges"], z[f"{name}/edges"]), name
+        assert np.array_equal(got["bfc"], z[f"{name}/bfc"]), name     # unmodified bfc_naive.bfc_edge, bit for bit
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_paper_flavour_random_graphs(seed):
+    n = 20 + 17 * seed
+    _check_paper(gnp(n, [0.05, 0.1, 0.2, 0.4][seed % 4], seed), n, f"gnp{seed}")
+
+
+def test_paper_flavour_edge_cases():
+    # single edge, star (deg_min == 1 everywhere), disjoint union with isolated nodes, complete graph
+    _check_paper(sym_edge_index([(0, 1)], 2), 2, "k2")
+    _check_paper(sym_edge_index([(0, i) for i in range(1, 40)], 45), 45, "star+isolated")
+    _check_paper(sym_edge_index([(i, j) for i in range(24) for j in range(i + 1, 24)], 24), 24, "k24")
+    for name, (ei, n) in toy_graphs().items():
+        _check_paper(ei, n, name)
+
+
+def test_paper_flavour_cta_team_and_global_table_paths():
+    # hubs push d_i + d_j past 512 (CTA team, shared-memory table) and past 16384 (CTA team, global table)
+    rng = np.random.default_rng(5)
+    n = 3000
+    pairs = [(0, i) for i in range(1, 700)] + [(1, i) for i in range(2, 900)]
+    extra = rng.integers(0, n, size=(6000, 2))
+    ei = sym_edge_index(pairs + [tuple(p) for p in extra.tolist()], n)
+    _check_paper(ei, n, "hubs-cta")
+    n = 20000
+    pairs = [(0, i) for i in range(1, 17000)] + [(1, i) for i in range(2, 9000)]
+    extra = rng.integers(0, n, size=(30000, 2))
+    ei = sym_edge_index(pairs + [tuple(p) for p in extra.tolist()], n)
+    from dcr import bfc
+    from oracle.paper_flavour import adjacency_sets, bfc_edge_fields
+    csr = _csr(ei, n)
+    out = bfc.paper_flavour(csr)
+    es, ed = out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()
+    adj = adjacency_sets(ei, n)
+    pick = np.concatenate([np.flatnonzero((es == 0) & (ed == 1)), rng.choice(es.size, 60, replace=False)])
+    got = {k: out[k].cpu().numpy() for k in ("tri", "sq_i", "sq_j", "gamma", "bfc")}
+    for e in pick.tolist():
+        f = bfc_edge_fields(adj, int(es[e]), int(ed[e]))
+        assert (got["tri"][e], got["sq_i"][e], got["sq_j"][e], got["gamma"][e]) == f[2:6], e
+        assert got["bfc"][e] == float(f[6])
+
+
+def test_paper_flavour_named_shapes_vs_oracle():
+    from dcr.synth import named_graph
+    for name in ("cornell", "wisconsin", "cora"):
+        ei, n = named_graph(name)
+        _check_paper(ei, n, name)
+
+
+def test_paper_flavour_strided_shards_reassemble():
+    from dcr import bfc
+    from dcr.synth import named_graph
+    ei, n = named_graph("cora")
+    csr = _csr(ei, n)
+    full = bfc.paper_flavour(csr)
+    E = full["count"]
+    for world in (2, 3, 8):
+        for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+            merged = np.zeros(E, dtype=full[key].cpu().numpy().dtype)
+            for r in range(world):
+                part = bfc.paper_flavour(csr, rank=r, world=world)
+                merged[r::world] = part[key].cpu().numpy()
+            assert np.array_equal(merged, full[key].cpu().numpy()), (world, key)
+
+
+def _cuda_gpu(ei, n):
+    import torch
+    from dcr import bfc
+    csr = _csr(ei, n)
+    out = bfc.cuda_flavour(csr)
+    C = torch.full((n, n), 7.0, device="cuda")
+    bfc.scatter_dense(csr, out["c32"], C)
+    return csr, out, C.cpu().numpy()
+
+
+def _check_cuda(ei, n, tag):
+    from oracle.cuda_flavour import bfc_cuda_dense
+    csr, out, C = _cuda_gpu(ei, n)
+    ref = bfc_cuda_dense(dense_of(ei, n), "compiled")
+    assert np.array_equal(C.view(np.uint32), ref["C"].view(np.uint32)), (tag, np.abs(C - ref["C"]).max())
+    rows = np.repeat(np.arange(n), np.diff(csr.rowptr.cpu().numpy()))
+    cols = csr.colidx.cpu().numpy()
+    assert np.array_equal(out["tri"].cpu().numpy(), ref["a2"][rows, cols].astype(np.int32)), tag
+    assert np.array_equal(out["sharp"].cpu().numpy(), ref["sharp"][rows, cols].astype(np.int32)), tag
+    assert np.array_equal(out["lam"].cpu().numpy(), ref["lam"][rows, cols].astype(np.int32)), tag
+    c64 = out["c64"].cpu().numpy()
+    assert np.allclose(c64, ref["C"][rows, cols], rtol=1e-6, atol=1e-7)
+    return C
+
+
+def test_cuda_flavour_golden_simulator_values():
+    z = golden("cuda_kat.npz")
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        C = _check_cuda(ei, n, name)
+        assert np.abs(C - z[f"{name}/C"]).max() <= 1e-6, name     # simulator (all-fp32) within fp32 noise
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cuda_flavour_random_graphs(seed):
+    n = 16 + 23 * seed
+    _check_cuda(gnp(n, [0.08, 0.15, 0.3][seed % 3], 50 + seed), n, f"gnp{seed}")
+
+
+def test_cuda_flavour_named_shapes_vs_oracle():
+    from dcr.synth import named_graph
+    for name in ("cornell", "wisconsin"):
+        ei, n = named_graph(name)
+        _check_cuda(ei, n, name)
+
+
+def test_post_delta_golden_and_oracle():
+    import torch
+    from dcr import bfc
+    from oracle.cuda_flavour import post_delta_dense
+    z = golden("cuda_kat.npz")
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        csr = _csr(ei, n)
+        tri = bfc.support(csr)
+        A = dense_of(ei, n)
+        for q in range(int(z[f"{name}/npd"])):
+            x, y = (int(v) for v in z[f"{name}/pd{q}/xy"])
+            xn, yn = z[f"{name}/pd{q}/xn"], z[f"{name}/pd{q}/yn"]
+            D = torch.zeros(len(xn), len(yn), device="cuda")
+            bfc.post_delta(csr, tri, x, y, torch.from_numpy(xn.astype(np.int32)).cuda(),
+                           torch.from_numpy(yn.astype(np.int32)).cuda(), D)
+            ref = post_delta_dense(A, x, y, xn.tolist(), yn.tolist(), "compiled")
+            got = D.cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (name, q, np.abs(got - ref).max())
+            assert np.abs(got - z[f"{name}/pd{q}/D"]).max() <= 1e-6
+
+
+def test_post_delta_arbitrary_lists_and_non_edges():
+    # generic lists (not N(x)+[x]) and (x,y) that is not an edge, incl. the (0,0) fallback of the SDRF loop
+    import torch
+    from dcr import bfc
+    from oracle.cuda_flavour import post_delta_dense
+    rng = np.random.default_rng(11)
+    for seed in range(6):
+        n = 18 + 4 * seed
+        ei = gnp(n, 0.22, 200 + seed)
+        csr = _csr(ei, n)
+        tri = bfc.support(csr)
+        A = dense_of(ei, n)
+        for _ in range(4):
+            x, y = (int(v) for v in rng.integers(0, n, 2))
+            if _ == 0:
+                x = y = 0
+            xn = rng.permutation(n)[: rng.integers(1, n)].astype(np.int32)
+            yn = rng.permutation(n)[: rng.integers(1, n)].astype(np.int32)
+            D = torch.zeros(len(xn), len(yn), device="cuda")
+            bfc.post_delta(csr, tri, x, y, torch.from_numpy(xn).cuda(), torch.from_numpy(yn).cuda(), D)
+            ref = post_delta_dense(A, x, y, xn.tolist(), yn.tolist(), "compiled")
+            got = D.cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (seed, x, y, np.abs(got - ref).max())
+
+
+def test_dense_roundtrip_and_validation():
+    import torch
+    from dcr import bfc
+    n = 300
+    ei = gnp(n, 0.05, 9)
+    A = torch.from_numpy(dense_of(ei, n)).cuda()
+    csr = bfc.DeviceCSR.from_dense(A)
+    from dcr import graph
+    rowptr, col = graph.undirected_csr(ei, n)
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(csr.colidx.cpu().numpy(), col)
+    B = A.clone()
+    B[3, 5] = 1.0 - B[3, 5]
+    with pytest.raises(NotImplementedError):
+        bfc.DeviceCSR.from_dense(B)
+    B = A.clone()
+    B[7, 7] = 1.0
+    with pytest.raises(NotImplementedError):
+        bfc.DeviceCSR.from_dense(B)
+
+
+def test_full_size_properties_squirrel_shape():
+    """Config-4 size: size-independent properties + oracle spot checks (the dense oracle is too slow here)."""
+    from dcr import bfc
+    from dcr.synth import named_graph
+    from oracle.paper_flavour import adjacency_sets, bfc_edge_fields
+    ei, n = named_graph("squirrel")
+    csr = _csr(ei, n)
+    out = bfc.paper_flavour(csr)
+    tri = out["tri"].cpu().numpy().astype(np.int64)
+    sq_i, sq_j = out["sq_i"].cpu().numpy(), out["sq_j"].cpu().numpy()
+    gamma = out["gamma"].cpu().numpy()
+    # every triangle is seen from its three edges; cross-check with the support kernel of the other flavour
+    supp = bfc.support(csr).cpu().numpy().astype(np.int64)
+    assert tri.sum() % 3 == 0 and supp.sum() == 2 * tri.sum()
+    # the bipartite square graph between the pure neighbourhoods is empty on one side iff on the other
+    assert np.array_equal(sq_i > 0, sq_j > 0)
+    assert np.array_equal(gamma > 0, sq_i > 0)
+    es, ed = out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()
+    adj = adjacency_sets(ei, n)
+    rng = np.random.default_rng(0)
+    bfcv = out["bfc"].cpu().numpy()
+    for e in rng.choice(es.size, 200, replace=False).tolist():
+        f = bfc_edge_fields(adj, int(es[e]), int(ed[e]))
+        assert (tri[e], sq_i[e], sq_j[e], gamma[e]) == f[2:6], e
+        assert bfcv[e] == float(f[6])

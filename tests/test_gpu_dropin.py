@@ -1,0 +1,78 @@
+"""GPU: the drop-in modules keep the reference's module paths, signatures and return conventions."""
+import numpy as np
+import pytest
+
+from helpers import dense_of, gnp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_balanced_forman_curvature_signature_and_inplace_semantics():
+    import torch
+    from curvature.bfc_cuda import balanced_forman_curvature
+    from oracle.cuda_flavour import bfc_cuda_dense
+    n = 60
+    ei = gnp(n, 0.12, 1)
+    A = torch.from_numpy(dense_of(ei, n)).cuda()
+    C = balanced_forman_curvature(A)
+    assert C.shape == (n, n) and C.dtype == torch.float32 and C.is_cuda
+    ref = bfc_cuda_dense(dense_of(ei, n))["C"]
+    assert np.array_equal(C.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    C2 = torch.full((n, n), 3.0, device="cuda")
+    out = balanced_forman_curvature(A, C=C2)
+    assert out is C2 and torch.equal(C2, C)          # written in place and returned (bfc_cuda.py:56-57,65)
+
+
+def test_balanced_forman_post_delta_signature():
+    import torch
+    from curvature.bfc_cuda import balanced_forman_post_delta
+    from oracle.cuda_flavour import post_delta_dense
+    n = 30
+    ei = gnp(n, 0.2, 2)
+    An = dense_of(ei, n)
+    A = torch.from_numpy(An).cuda()
+    x, y = int(ei[0][0]), int(ei[1][0])
+    xn = np.flatnonzero(An[x]).tolist() + [x]
+    yn = np.flatnonzero(An[y]).tolist() + [y]
+    D = balanced_forman_post_delta(A, x, y, xn, yn)
+    assert D.shape == (len(xn), len(yn))
+    ref = post_delta_dense(An, x, y, xn, yn)
+    assert np.array_equal(D.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_bfc_naive_dropin_on_networkx_graph():
+    nx = pytest.importorskip("networkx")
+    from curvature.bfc_naive import bfc, bfc_edge
+    from oracle.paper_flavour import adjacency_sets, bfc_edge_fields
+    G = nx.gnp_random_graph(40, 0.15, seed=4)
+    ei = np.array([(u, v) for u, v in G.edges] + [(v, u) for u, v in G.edges]).T
+    adj = adjacency_sets(ei, 40)
+    bfc(G)
+    for u, v in G.edges:
+        want = bfc_edge_fields(adj, u, v)[6]
+        assert G[u][v]["bfc"] == want
+        assert type(G[u][v]["bfc"]) is type(want)     # int 0 when deg_min == 1, else float
+    u, v = next(iter(G.edges))
+    assert bfc_edge(G, u, v) == bfc_edge_fields(adj, u, v)[6]
+
+
+def test_rewire_dropin_returns_edge_index_and_consumes_numpy_stream():
+    import torch
+    from dcr.synth import named_graph
+    from oracle.sdrf import sdrf_oracle
+    from rewiring.rewire import rewire
+    from torch_geometric.data import Data
+    ei, n = named_graph("texas")
+    data = Data(edge_index=torch.from_numpy(ei))
+    data.num_nodes = n
+    loops = 20
+    np.random.seed(123)
+    out = rewire(data, "bfc", loops, 1.64, 22)
+    after = np.random.random_sample()
+    assert isinstance(out, torch.Tensor) and out.dtype == torch.long and out.shape[0] == 2
+    uni = np.random.RandomState(123).random_sample(loops + 1)
+    want, wlog = sdrf_oracle(ei, n, loops, True, 1.64, 22, uni)
+    assert np.array_equal(out.numpy(), want)
+    draws = sum(r["n_candidates"] > 0 for r in wlog)
+    assert after == uni[draws]        # the global generator advanced by exactly the reference's number of draws
+    assert rewire(data, None, loops, 1.64, 22) is data.edge_index

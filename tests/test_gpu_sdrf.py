@@ -1,0 +1,160 @@
+"""GPU parity, SDRF: add/remove sequences of the device loop against the oracle (compiled rounding model)."""
+import numpy as np
+import pytest
+
+from helpers import dense_of, gnp, golden, sym_edge_index, toy_graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_log_tuples(log):
+    return [(r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
+             -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
+            for r in log]
+
+
+def _run_both(ei, n, loops, bound, tau, seed, remove_edges=True, guard=1e-9):
+    from dcr import sdrf
+    from oracle.sdrf import sdrf_oracle
+    uni = np.random.RandomState(seed).random_sample(loops)
+    got, glog = sdrf.sdrf(ei, n, loops, remove_edges, bound, tau, uniforms=uni, return_log=True, guard=guard)
+    want, wlog = sdrf_oracle(ei, n, loops, remove_edges, bound, tau, uni, rounding="compiled")
+    assert [tuple(int(v) for v in r) for r in glog] == _oracle_log_tuples(wlog)
+    assert np.array_equal(got, want)
+    return glog
+
+
+@pytest.mark.parametrize("tau", [float("inf"), 12, 3, 60])
+@pytest.mark.parametrize("seed", range(4))
+def test_sdrf_small_graphs_match_oracle(seed, tau):
+    n = 14 + 5 * seed
+    _run_both(gnp(n, 0.2 + 0.02 * seed, 300 + seed), n, 12, [0.5, 0.3, 1.2, 0.05][seed], tau, 40 + seed)
+
+
+def test_sdrf_toy_graphs_with_ties():
+    # highly symmetric graphs: every decision is a tie broken by row-major order / candidate order / fp32 rounding
+    for name, (ei, n) in toy_graphs().items():
+        for tau in (float("inf"), 20):
+            _run_both(ei, n, 8, 0.4, tau, 7)
+
+
+def test_sdrf_golden_sequences_where_rounding_models_agree():
+    from dcr import sdrf
+    z = golden("sdrf_seq.npz")
+    agree = {"gnp14_greedy", "gnp14_tau12", "gnp16_tau3", "grid_tau50", "gnp18_nobound"}
+    for name in (str(s) for s in z["names"]):
+        if name not in agree:
+            continue   # symmetric graphs where simulator fp32 and compiled fp64 arithmetic break ties differently
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        got, log = sdrf.sdrf(ei, n, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]), float(z[f"{name}/tau"]),
+                             uniforms=z[f"{name}/uniforms"], return_log=True)
+        seq = []
+        for r in log:
+            if r[3] >= 0:
+                seq.append((1, int(r[3]), int(r[4])))
+            if r[6] >= 0:
+                seq.append((-1, int(r[6]), int(r[7])))
+        assert np.array_equal(np.array(seq).reshape(-1, 3), z[f"{name}/log"]), name
+        assert np.array_equal(got, z[f"{name}/out"]), name
+
+
+def test_sdrf_named_shapes_reference_hyperparameters():
+    from dcr.synth import SDRF_PARAMS, named_graph
+    for name in ("cornell", "texas", "wisconsin"):
+        ei, n = named_graph(name)
+        loops, tau, bound = SDRF_PARAMS[name]
+        _run_both(ei, n, min(loops, 40), bound, tau, 5)
+        _run_both(ei, n, min(loops, 40), bound, float("inf"), 5)
+
+
+def test_sdrf_without_removal_and_early_exit():
+    ei, n = toy_graphs()["k5"]
+    # complete graph: no candidates -> can_add False; remove_edges False -> immediate break
+    _run_both(ei, n, 5, 0.5, float("inf"), 1, remove_edges=False)
+    # with removal and a bound nothing exceeds: break through the second exit
+    _run_both(ei, n, 5, 100.0, float("inf"), 1, remove_edges=True)
+    ei = gnp(20, 0.2, 4)
+    _run_both(ei, 20, 10, 0.5, 5, 2, remove_edges=False)
+
+
+def test_sdrf_host_redecision_path_agrees_with_device_draw():
+    # guard = 2 sends EVERY stochastic draw to the host (numpy softmax + searchsorted): must give the same sequence
+    n = 22
+    ei = gnp(n, 0.2, 77)
+    a = _run_both(ei, n, 10, 0.4, 7, 3, guard=1e-9)
+    b = _run_both(ei, n, 10, 0.4, 7, 3, guard=2.0)
+    assert np.array_equal(a, b)
+
+
+def test_sdrf_incremental_curvature_equals_full_recompute():
+    from dcr import graph, sdrf
+    from oracle.cuda_flavour import bfc_cuda_dense
+    n = 40
+    ei = gnp(n, 0.15, 12)
+    uni = np.random.RandomState(1).random_sample(64)
+    for loops in (1, 2, 5, 17, 40):
+        keep = []
+        got = sdrf.sdrf(ei, n, loops, True, 0.3, 9, uniforms=uni, state_out=keep)
+        rowptr, order, col, c32, tri = keep[0].export(with_curvature=True)
+        keep[0].close()
+        rows = np.repeat(np.arange(n), np.diff(rowptr))
+        A = np.zeros((n, n), dtype=np.float32)
+        A[rows, col] = 1
+        ref = bfc_cuda_dense(A, "compiled")
+        assert np.array_equal(c32.view(np.uint32), ref["C"][rows, col].view(np.uint32)), loops
+        assert np.array_equal(tri, ref["a2"][rows, col].astype(np.int32)), loops
+        assert np.array_equal(A, A.T)
+        assert np.array_equal(np.sort(got[0] * n + got[1]), np.flatnonzero(A.ravel()))
+
+
+def test_sdrf_softmax_overflow_raises_value_error():
+    from dcr import sdrf
+    ei, n = toy_graphs()["barbell41"]
+    with pytest.raises(ValueError, match="NaN"):
+        sdrf.sdrf(ei, n, 3, True, 0.5, 5000, uniforms=np.array([0.3, 0.3, 0.3]))
+
+
+def test_sdrf_unsorted_input_uses_networkx_insertion_order():
+    # shuffled, non-symmetric edge_index: candidate order (hence tie-breaks) follows networkx insertion order
+    rng = np.random.default_rng(8)
+    n = 18
+    ei = gnp(n, 0.22, 31)
+    half = ei[:, ei[0] < ei[1]]
+    half = half[:, rng.permutation(half.shape[1])]
+    flip = rng.random(half.shape[1]) < 0.5
+    half[:, flip] = half[::-1][:, flip]
+    for tau in (float("inf"), 4):
+        _run_both(half, n, 10, 0.4, tau, 9)
+
+
+def test_sdrf_cora_shape_long_run_properties():
+    """Config 3: 1000+ iterations on the cora-shaped graph; oracle prefix + invariants of the final state."""
+    from dcr import sdrf
+    from dcr.synth import named_graph
+    from oracle.sdrf import sdrf_oracle
+    ei, n = named_graph("cora")
+    loops = 1200
+    uni = np.random.RandomState(3).random_sample(loops)
+    keep = []
+    got, log = sdrf.sdrf(ei, n, loops, True, 0.95, 163, uniforms=uni, return_log=True, state_out=keep)
+    assert len(log) == loops
+    # the first iterations against the dense oracle (full length would take ~10 minutes of CPU)
+    want, wlog = sdrf_oracle(ei, n, 25, True, 0.95, 163, uni, rounding="compiled")
+    assert [tuple(int(v) for v in r) for r in log[:25]] == _oracle_log_tuples(wlog)
+    # replay the log on a set: the exported graph is exactly initial + additions - removals
+    edges = set(map(tuple, ei.T.tolist()))
+    for r in log:
+        if r[3] >= 0:
+            assert (int(r[3]), int(r[4])) not in edges
+            edges |= {(int(r[3]), int(r[4])), (int(r[4]), int(r[3]))}
+        if r[6] >= 0:
+            edges -= {(int(r[6]), int(r[7])), (int(r[7]), int(r[6]))}
+    assert set(map(tuple, got.T.tolist())) == edges
+    rowptr, order, col, c32, tri = keep[0].export(with_curvature=True)
+    keep[0].close()
+    # incremental curvature after 1200 edits == a fresh full computation on the final graph (CUDA kernels)
+    from dcr import bfc
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    fresh = bfc.cuda_flavour(csr)
+    assert np.array_equal(fresh["c32"].cpu().numpy().view(np.uint32), c32.view(np.uint32))
+    assert np.array_equal(fresh["tri"].cpu().numpy(), tri)

@@ -1,0 +1,124 @@
+"""CPU suite, part 2: host-side logic of the package (graph set-up, drop-in softmax, C-ABI surface)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import PKG, REPO
+from dcr import graph as G
+from dcr.synth import SHAPES, chung_lu_graph, csr_from_edge_index
+from oracle.sdrf import dense_adjacency, edge_index_from_adjacency, networkx_adjacency
+
+
+def test_graph_setup_matches_networkx_semantics():
+    rng = np.random.default_rng(0)
+    for trial in range(150):
+        n = int(rng.integers(2, 30))
+        ei = rng.integers(0, n, size=(2, int(rng.integers(1, 80))))
+        ei = ei[:, ei[0] != ei[1]]
+        if ei.shape[1] == 0:
+            continue
+        if trial % 3 == 0:   # sorted + symmetric, the form the reference's datasets come in
+            ei = np.concatenate([ei, ei[::-1]], axis=1)
+            k = np.unique(ei[0] * n + ei[1])
+            ei = np.stack([k // n, k % n])
+        adj = networkx_adjacency(ei, n)
+        rp, od = G.networkx_order(ei, n)
+        assert [list(a) for a in adj] == [od[rp[v]:rp[v + 1]].tolist() for v in range(n)]
+        assert np.array_equal(G.from_networkx_order(rp, od), edge_index_from_adjacency(adj))
+        rp2, c2 = G.undirected_csr(ei)
+        A = dense_adjacency(ei)
+        for v in range(A.shape[0]):
+            assert np.array_equal(np.flatnonzero(A[v]), c2[rp2[v]:rp2[v + 1]])
+
+
+def test_networkx_order_against_real_networkx():
+    nx = pytest.importorskip("networkx")
+    rng = np.random.default_rng(1)
+    for trial in range(30):
+        n = int(rng.integers(3, 25))
+        ei = rng.integers(0, n, size=(2, int(rng.integers(2, 60))))
+        ei = ei[:, ei[0] != ei[1]]
+        D = nx.DiGraph()
+        D.add_nodes_from(range(n))
+        for u, v in ei.T.tolist():
+            D.add_edge(u, v)
+        U = D.to_undirected()
+        rp, od = G.networkx_order(ei, n)
+        assert [list(U.neighbors(v)) for v in range(n)] == [od[rp[v]:rp[v + 1]].tolist() for v in range(n)]
+
+
+def test_sorted_symmetric_input_gives_ascending_adjacency():
+    ei = chung_lu_graph(60, 150, 0.8, 0.2, 3)
+    rp, od = G.networkx_order(ei, 60)
+    for v in range(60):
+        row = od[rp[v]:rp[v + 1]]
+        assert np.all(np.diff(row) > 0)
+
+
+def test_synthetic_graphs_have_the_named_shapes():
+    for name in ("cornell", "texas", "wisconsin", "cora"):
+        n, e, alpha, p_tri, seed = SHAPES[name]
+        ei = chung_lu_graph(n, e, alpha, p_tri, seed)
+        assert ei.shape == (2, 2 * e)
+        assert int(ei.max()) < n
+        key = ei[0] * n + ei[1]
+        assert np.all(np.diff(key) > 0)                       # sorted, no duplicates
+        assert np.array_equal(np.sort(ei[1] * n + ei[0]), key)  # symmetric
+        assert not np.any(ei[0] == ei[1])
+        rowptr, col = csr_from_edge_index(ei, n)
+        assert (np.diff(rowptr) > 0).all()                    # no isolated nodes
+        assert np.array_equal(chung_lu_graph(n, e, alpha, p_tri, seed), ei)   # deterministic
+
+
+def test_dropin_softmax_matches_reference_semantics():
+    from oracle.sdrf import softmax as oracle_softmax
+    from utils.softmax import softmax
+    rng = np.random.default_rng(3)
+    for tau in (float("inf"), 1, 12, 145):
+        a = rng.normal(size=17)
+        assert np.array_equal(softmax(a, tau), oracle_softmax(a, tau))
+    a = np.array([0.5, 0.5, 0.1])
+    assert softmax(a, float("inf")).tolist() == [1.0, 0.0, 0.0]    # first argmax
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "dcr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dcr import lib as L
+    path = L.LIB_PATH
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/dcr.h but not exported"
+    assert set(L.SIGNATURES) == set(names)
+    assert L.load().dcr_version() == 1
+
+
+def test_product_path_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under the package may reference it
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(root, f)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from dcr import lib as L
+    from dcr.bfc import DeviceCSR
+    with pytest.raises(L.DcrError):
+        DeviceCSR.from_host(np.array([0, 1, 2], dtype=np.int32), np.array([1, 0], dtype=np.int32))
