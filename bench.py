@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py — BFC edges/s (full-graph paper-flavour BFC, arxiv-shaped synthetic graph) and SDRF iterations/s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libdcr.so, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle's C port on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one full pass of the hot path over the whole graph: plan + edge
+kernels (+ all-gather and re-interleave when N > 1).  Timing: CUDA events per step on the launching stream, an L2
+flush (256 MiB memset) between steps outside the events, barrier + synchronize around the timed region, max over
+ranks.  See DESIGN.md §Measurement for the definitions of `value`, `e2e`, `roofline` and `cpu_baseline`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "discrete-curvature-rewiring_b200")
+for _p in (PKG, REPO):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "arxiv": "arxiv-shaped synthetic graph (N=169343, E=1166243, Chung-Lu alpha=0.6, p_tri=0.1, seed 169343): "
+             "full-graph paper-flavour BFC (deg, #tri, #sq_i, #sq_j, gamma_max, fp64 value per undirected edge)",
+    "squirrel": "squirrel-shaped synthetic graph (N=5201, E=198000): full-graph paper-flavour BFC",
+    "cora": "cora-shaped synthetic graph (N=2708, E=5278): full-graph paper-flavour BFC",
+}
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(rowptr: np.ndarray, col: np.ndarray, esrc: np.ndarray, edst: np.ndarray):
+    """B_gather(e) = 16 + 4(d_i+d_j) + 4((S_i-d_j)+(S_j-d_i)) + 24, S_v = sum of neighbour degrees.
+    Also B_compulsory = 4(N+1) + 4*2E + 24E (CSR once + results once)."""
+    deg = np.diff(rowptr.astype(np.int64))
+    n = deg.size
+    rows = np.repeat(np.arange(n), deg)
+    S = np.bincount(rows, weights=deg[col].astype(np.float64), minlength=n).astype(np.int64)
+    di, dj = deg[esrc], deg[edst]
+    per_edge = 16 + 4 * (di + dj) + 4 * ((S[esrc] - dj) + (S[edst] - di)) + 24
+    compulsory = 4 * (n + 1) + 4 * col.size + 24 * esrc.size
+    return per_edge, int(compulsory)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_bfc_rate(rowptr, col, esrc, edst, threads: int, budget_s: float, seed: int = 0):
+    """Time the oracle's C port (bfc_naive restated, pthreads) on a seeded uniform sample of the edges sized for
+    about `budget_s` seconds.  Returns (edges/s, sample size, seconds)."""
+    from oracle.c_port import bfc_paper_c
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(esrc.size)
+    probe = perm[: min(esrc.size, 4096)]
+    t0 = time.perf_counter()
+    bfc_paper_c(rowptr, col, esrc[probe], edst[probe], threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    m = int(min(esrc.size, max(4096, budget_s * probe.size / dt)))
+    pick = perm[:m]
+    t0 = time.perf_counter()
+    bfc_paper_c(rowptr, col, esrc[pick], edst[pick], threads)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    return m / dt, m, dt
+
+
+def build_graph(workload: str):
+    from dcr import graph
+    from dcr.synth import named_graph
+    ei, n = named_graph(workload)
+    rowptr, col = graph.undirected_csr(ei, n)
+    m = ei[0] < ei[1]
+    esrc = ei[0][m].astype(np.int32)
+    edst = ei[1][m].astype(np.int32)
+    return ei, n, rowptr, col, esrc, edst
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU implementation of the path on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__
+    __graft_entry__.build()
+    ei, n, rowptr, col, esrc, edst = build_graph(args.workload)
+    threads = host_threads()
+    steps = max(1, args.steps)
+    budget = min(20.0, 120.0 / (steps + args.warmup))       # whole run stays within a few minutes
+    rates, m = [], 0
+    for s in range(args.warmup + steps):
+        rate, m, dt = cpu_bfc_rate(rowptr, col, esrc, edst, threads, budget, seed=s)
+        if s >= args.warmup:
+            rates.append((m, dt))
+    tot_m = sum(a for a, _ in rates)
+    tot_t = sum(b for _, b in rates)
+    value = tot_m / tot_t
+    sample = (f"oracle C port of curvature/bfc_naive.py (oracle/c/bfc_paper_csr.c), {threads} pthreads, per step a "
+              f"seeded uniform sample of {m} of the {esrc.size} undirected edges")
+    line = {
+        "impl": "reference", "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts + f64 value", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "sample_edges_per_step": m},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def sdrf_bench(args, torch):
+    """SDRF iterations/s on the cora-shaped graph (config 3), device loop vs the dense CPU restatement."""
+    from dcr import graph, sdrf
+    from dcr.synth import named_graph
+    from oracle.sdrf import sdrf_oracle
+    ei, n = named_graph("cora")
+    loops, tau, bound = args.sdrf_loops, 163, 0.95
+    uni = np.random.RandomState(3).random_sample(loops)
+    out = {"workload": f"cora-shaped synthetic graph (N=2708, E=5278), {loops} iterations, tau={tau}, "
+                       f"removal_bound={bound} (utils/hyperparams.py Cora), stochastic draw with host uniforms"}
+    # device-resident loop only (state already built): CUDA events around the single persistent-kernel launch
+    rowptr_o, order = graph.networkx_order(ei, n)
+    best = None
+    for rep in range(3):
+        st = sdrf.SdrfState(rowptr_o, order, max_additions=loops)
+        u_dev = torch.from_numpy(uni).cuda()
+        log = torch.empty((loops, 8), dtype=torch.int32, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        res, _ = st.run(loops, True, bound, tau, u_dev, log=log)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        done = res["iterations_done"]
+        st.close()
+        if res["status"] == 0 and (best is None or ms < best[0]):
+            best = (ms, done)
+    if best is not None:
+        out["iters_per_s"] = best[1] / (best[0] * 1e-3)
+        out["iterations"] = best[1]
+        out["ms_total"] = best[0]
+    # end to end through the public entry point: host edge_index in, host edge_index out (set-up + loop + export)
+    t0 = time.perf_counter()
+    got, glog = sdrf.sdrf(ei, n, loops, True, bound, tau, uniforms=uni, return_log=True)
+    dt = time.perf_counter() - t0
+    out["e2e_iters_per_s"] = len(glog) / dt
+    out["e2e_s"] = dt
+    # CPU: dense restatement of bfc_cuda.py + sdrf_cuda_bfc.py (two A@A per iteration, like the reference)
+    cpu_iters = args.sdrf_cpu_iters
+    t0 = time.perf_counter()
+    want, wlog = sdrf_oracle(ei, n, cpu_iters, True, bound, tau, uni, rounding="compiled", incremental_a2=False)
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": len(wlog) / dt, "unit": "iterations/s", "cores": host_threads(), "kind": "port",
+                           "sample": f"first {cpu_iters} iterations of the same run, dense numpy restatement "
+                                     "(oracle/sdrf.py, BLAS A@A + per-entry numpy loops)"}
+    same = [tuple(int(v) for v in r) for r in glog[:cpu_iters]] == [
+        (r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
+         -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
+        for r in wlog]
+    out["prefix_matches_cpu"] = bool(same)
+    if "iters_per_s" in out:
+        out["speedup_vs_cpu"] = out["iters_per_s"] / out["cpu_baseline"]["value"]
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        __graft_entry__.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libdcr has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from dcr import bfc
+    from dcr import lib as L
+    from dcr.dist import ShardedPaperBFC
+    L.load()
+
+    ei, n, rowptr, col, esrc, edst = build_graph(args.workload)
+    E = int(esrc.size)
+    per_edge_bytes, b_compulsory = algorithmic_bytes(rowptr, col, esrc, edst)
+    b_gather_total = int(per_edge_bytes.sum())
+    b_gather_rank = int(per_edge_bytes[rank::world].sum())
+    peak, peak_src = load_peaks()
+
+    dev = torch.device("cuda", local)
+    csr = bfc.DeviceCSR.from_host(rowptr, col, device=dev)
+    csr._edges = (torch.from_numpy(esrc).to(dev), torch.from_numpy(edst).to(dev), None)
+    sh = ShardedPaperBFC(csr)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev_edge = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for e in ev_edge:
+        e.record()      # materialise the cudaEvent handles
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        sh.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_ms, edge_ms = [], []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = sh.run(events=ev_edge)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        edge_ms.append(ev_edge[0].elapsed_time(ev_edge[1]))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(float(np.sum(step_ms)))
+    ms_per_step = total_ms / args.steps
+    value = E / (ms_per_step * 1e-3)
+    edge_ms_avg = float(np.mean(edge_ms))
+
+    # ---- end to end: host CSR in (pinned), host results out, copies inside the timed region -------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rowptr, h_col, h_esrc, h_edst = pin(rowptr), pin(col), pin(esrc), pin(edst)
+    h_out = torch.empty(E * 24, dtype=torch.uint8).pin_memory()
+    d_rowptr = torch.empty_like(h_rowptr, device=dev)
+    d_col = torch.empty_like(h_col, device=dev)
+    d_esrc = torch.empty_like(h_esrc, device=dev)
+    d_edst = torch.empty_like(h_edst, device=dev)
+    csr2 = bfc.DeviceCSR(d_rowptr, d_col, n, csr.max_degree)
+    csr2._edges = (d_esrc, d_edst, None)
+    sh2 = ShardedPaperBFC(csr2)
+    h2d = sum(int(t.numel() * t.element_size()) for t in (h_rowptr, h_col, h_esrc, h_edst))
+    d2h = E * 24
+
+    def e2e_step():
+        d_rowptr.copy_(h_rowptr, non_blocking=True)
+        d_col.copy_(h_col, non_blocking=True)
+        d_esrc.copy_(h_esrc, non_blocking=True)
+        d_edst.copy_(h_edst, non_blocking=True)
+        r = sh2.run()
+        o = 0
+        for key in ("bfc", "tri", "sq_i", "sq_j", "gamma"):
+            src = r[key].view(torch.uint8)
+            h_out[o:o + src.numel()].copy_(src, non_blocking=True)
+            o += src.numel()
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_step()
+        e1.record()
+        e1.synchronize()
+        e2e_ms.append(e0.elapsed_time(e1))
+    barrier()
+    e2e_total = max_over_ranks(float(np.sum(e2e_ms)))
+    e2e_value = E / (e2e_total / args.steps * 1e-3)
+
+    # parity spot check of what was just timed (full check lives in tests/): first 2000 edges vs the C oracle
+    checked = None
+    if rank == 0:
+        from oracle.c_port import bfc_paper_c
+        k = min(E, 2000)
+        ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
+        checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
+
+    launches_per_step = 4 + 2 + (1 if csr.max_degree * 4 > 32768 else 0) + 1
+    line = {
+        "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32 counts + f64 value", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "nodes": n, "undirected_edges": E,
+                   "sharding": f"edge e -> rank e % {world}, graph replicated, one all-gather" if world > 1 else "single GPU",
+                   "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
+                   "timing": "sum of per-step CUDA-event times, max over ranks", "wall_s_timed_region": wall,
+                   "parity_spot_check_vs_c_oracle": checked},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_total / args.steps,
+                "what": "dcr.dist.ShardedPaperBFC.run on host (pinned) CSR + edge list; results copied back to pinned host memory"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {
+            "bound": "hbm", "kernel": "paper_edge_kernel (CTA-team + warp-team launches of one step)",
+            "achieved": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+            "traffic": None, "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
+            "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
+            "note": "algorithmic bytes = SURVEY.md §8d B_gather of this rank's edges (every 2-hop list once per edge, "
+                    "no cross-edge reuse charged); the CSR is L2-resident so DRAM traffic is far below it — see "
+                    "profiles/ for dram__bytes and lts__t_bytes",
+        },
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        thr = host_threads()
+        rate, m, dt = cpu_bfc_rate(rowptr, col, esrc, edst, thr, args.cpu_budget)
+        line["cpu_baseline"] = {"value": rate, "unit": "edges/s", "cores": thr, "kind": "port",
+                                "sample": f"oracle C port of curvature/bfc_naive.py (oracle/c/bfc_paper_csr.c), {thr} "
+                                          f"pthreads, seeded uniform sample of {m} of {E} edges, {dt:.1f} s"}
+    if rank == 0 and not args.no_sdrf:
+        line["sdrf"] = sdrf_bench(args, torch)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--sdrf-loops", type=int, default=1000)
+    ap.add_argument("--sdrf-cpu-iters", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sdrf", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

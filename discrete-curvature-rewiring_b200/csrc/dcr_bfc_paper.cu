@@ -19,6 +19,8 @@
 // bandwidth and shared-memory probe throughput, not by DRAM.
 // Edges are bucketed by class and by log2(work) on the device (heavy first) and teams pull edges from a global
 // counter, so power-law hubs do not serialise the tail.  Grids are persistent: a multiple of the SM count.
+#include <algorithm>
+
 #include "dcr_common.cuh"
 
 namespace dcr {
@@ -64,11 +66,13 @@ struct PaperArgs {
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
 
-// tag of `key` in the table (0 = absent)
+// tag of `key` in the table (0 = absent).  A table in GLOBAL memory is filled with L2 atomics by other warps of
+// the CTA, so it is read with ld.global.cg (L2) — an L1 line fetched during the build phase may be stale.
+template <bool GLOBAL>
 __device__ __forceinline__ uint32_t probe(const uint32_t* tab, uint32_t mask, int shift, uint32_t key) {
     uint32_t h = hash_slot(key, shift);
     while (true) {
-        const uint32_t v = tab[h];
+        const uint32_t v = GLOBAL ? __ldcg(tab + h) : tab[h];
         if (v == EMPTY) return 0u;
         if ((v & KEYMASK) == key) return v >> 30;
         h = (h + 1) & mask;
@@ -76,11 +80,12 @@ __device__ __forceinline__ uint32_t probe(const uint32_t* tab, uint32_t mask, in
 }
 
 // insert key with `tag`, or OR the tag into an existing entry; returns true if the key was already present
+template <bool GLOBAL>
 __device__ __forceinline__ bool insert_or_tag(uint32_t* tab, uint32_t mask, int shift, uint32_t key, uint32_t tag) {
     uint32_t h = hash_slot(key, shift);
     const uint32_t val = key | (tag << 30);
     while (true) {
-        uint32_t v = tab[h];
+        uint32_t v = GLOBAL ? __ldcg(tab + h) : tab[h];
         if (v == EMPTY) {
             v = atomicCAS(&tab[h], EMPTY, val);
             if (v == EMPTY) return false;
@@ -182,7 +187,7 @@ __device__ __forceinline__ void team_sync() {
 // Stream the neighbour lists of all keys of `list` (a row of the CSR) that carry `scan_tag`, counting per list
 // the elements that carry `hit_tag`.  Returns per-warp partial (#lists with a hit, max hits); chunk c of 32 list
 // heads is handled by warp (c mod team_warps).
-template <bool CTA_TEAM>
+template <bool CTA_TEAM, bool GLOBAL>
 __device__ __forceinline__ void scan_side(const PaperArgs& a, const uint32_t* tab, uint32_t mask, int shift,
                                           int list_begin, int list_len, uint32_t scan_tag, uint32_t hit_tag,
                                           int team_warp, int team_warps, int lane, int& sq, int& gmax) {
@@ -193,7 +198,7 @@ __device__ __forceinline__ void scan_side(const PaperArgs& a, const uint32_t* ta
         int m = -1, mb = 0, md = 0;
         if (t < list_len) {
             m = colidx[list_begin + t];
-            if (probe(tab, mask, shift, (uint32_t)m) == scan_tag) {
+            if (probe<GLOBAL>(tab, mask, shift, (uint32_t)m) == scan_tag) {
                 mb = rowptr[m];
                 md = rowptr[m + 1] - mb;
             } else {
@@ -216,7 +221,7 @@ __device__ __forceinline__ void scan_side(const PaperArgs& a, const uint32_t* ta
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
-                    const bool hit = k[u] >= 0 && probe(tab, mask, shift, (uint32_t)k[u]) == hit_tag;
+                    const bool hit = k[u] >= 0 && probe<GLOBAL>(tab, mask, shift, (uint32_t)k[u]) == hit_tag;
                     cnt += __popc(__ballot_sync(FULL, hit));
                 }
             }
@@ -276,13 +281,13 @@ paper_edge_kernel(PaperArgs a, int cls) {
         team_sync<CTA_TEAM>();
         for (int p = team_tid; p < di; p += team_threads) {
             const int k = a.colidx[si + p];
-            if (k != j) insert_or_tag(tab, mask, shift, (uint32_t)k, 1u);
+            if (k != j) insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 1u);
         }
         team_sync<CTA_TEAM>();
         int tri = 0;
         for (int p = team_tid; p < dj; p += team_threads) {
             const int k = a.colidx[sj + p];
-            if (k != i) tri += insert_or_tag(tab, mask, shift, (uint32_t)k, 2u);
+            if (k != i) tri += insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 2u);
         }
         tri = warp_sum(tri);
         if (CTA_TEAM) {
@@ -292,7 +297,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
 
         // pass A: lists of m in M_j (tag 2), hits in M_i (tag 1)  -> squares at j
         int sqA = 0, gA = 0, sqB = 0, gB = 0;
-        scan_side<CTA_TEAM>(a, tab, mask, shift, sj, dj, 2u, 1u, team_warp, team_warps, lane, sqA, gA);
+        scan_side<CTA_TEAM, GLOBAL_TABLE>(a, tab, mask, shift, sj, dj, 2u, 1u, team_warp, team_warps, lane, sqA, gA);
         if (CTA_TEAM) {
             if (lane == 0 && sqA) { atomicAdd(&s_red[1], sqA); atomicMax(&s_red[2], gA); }
             __syncthreads();
@@ -300,7 +305,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
         }
         // pass B: lists of k in M_i (tag 1), hits in M_j (tag 2)  -> squares at i; empty iff pass A was empty
         if (sqA > 0) {
-            scan_side<CTA_TEAM>(a, tab, mask, shift, si, di, 1u, 2u, team_warp, team_warps, lane, sqB, gB);
+            scan_side<CTA_TEAM, GLOBAL_TABLE>(a, tab, mask, shift, si, di, 1u, 2u, team_warp, team_warps, lane, sqB, gB);
             if (CTA_TEAM) {
                 if (lane == 0 && sqB) { atomicAdd(&s_red[3], sqB); atomicMax(&s_red[4], gB); }
                 __syncthreads();
@@ -364,7 +369,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
                              const int32_t* esrc, const int32_t* edst, int64_t e_first, int64_t e_stride,
                              int64_t count, int32_t* out_tri, int32_t* out_sq_i, int32_t* out_sq_j,
                              int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
-                             void* stream) {
+                             void* ev_edge_begin, void* ev_edge_end, void* stream) {
     if (count <= 0 || n <= 0) return 0;
     if (count > 0xfffffff0LL) { set_error("dcr_bfc_paper: more than 2^32 edges per call"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -398,6 +403,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     DCR_LAUNCH_CHECK();
 
     const int sms = sm_count();
+    if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
     // heavy classes first: they own the long tail
     if (L.gslots) {
         paper_edge_kernel<true, true><<<L.g_ctas, CTA_THREADS, 0, st>>>(a, 2);
@@ -419,5 +425,41 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         paper_edge_kernel<false, false><<<sms * 6, WARP_TEAM_WARPS * 32, smem, st>>>(a, 0);
         DCR_LAUNCH_CHECK();
     }
+    if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU: re-interleave the all-gathered per-rank shards (rank r holds edges e = r + t*world at local t)
+// ------------------------------------------------------------------------------------------------------------
+namespace dcr {
+__global__ void unshard_kernel(const unsigned char* __restrict__ gathered, int world, int64_t chunk, int64_t n_edges,
+                               int32_t* __restrict__ tri, int32_t* __restrict__ sq_i, int32_t* __restrict__ sq_j,
+                               int32_t* __restrict__ gamma, double* __restrict__ bfc) {
+    // per-rank block layout (bytes): bfc[chunk] f64 | tri[chunk] | sq_i[chunk] | sq_j[chunk] | gamma[chunk] i32
+    const int64_t block = chunk * 24;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e % world);
+        const int64_t t = e / world;
+        const unsigned char* base = gathered + r * block;
+        bfc[e] = ((const double*)base)[t];
+        const int32_t* ints = (const int32_t*)(base + chunk * 8);
+        tri[e] = ints[t];
+        sq_i[e] = ints[chunk + t];
+        sq_j[e] = ints[2 * chunk + t];
+        gamma[e] = ints[3 * chunk + t];
+    }
+}
+}  // namespace dcr
+
+extern "C" int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t chunk, int64_t n_edges, int32_t* out_tri,
+                                     int32_t* out_sq_i, int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc,
+                                     void* stream) {
+    if (n_edges <= 0) return 0;
+    if (world <= 0 || chunk * world < n_edges) { set_error("dcr_bfc_paper_unshard: bad shard geometry"); return 1; }
+    const int ctas = (int)std::min<int64_t>((n_edges + 255) / 256, (int64_t)sm_count() * 8);
+    unshard_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)gathered, world, chunk, n_edges,
+                                                          out_tri, out_sq_i, out_sq_j, out_gamma, out_bfc);
+    DCR_LAUNCH_CHECK();
     return 0;
 }

@@ -99,19 +99,23 @@ def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None,
 
 
 class PaperWorkspace:
-    """Reusable outputs + scratch of the paper-flavour kernel for one (graph, shard) shape."""
+    """Reusable outputs + scratch of the paper-flavour kernel for one (graph, shard) shape.
 
-    def __init__(self, csr: DeviceCSR, count: int):
+    The five output arrays are views into ONE contiguous block (``bfc`` f64 first, then the four int32 arrays),
+    so a rank's whole result is a single buffer for the all-gather of the multi-GPU path (no packing copy).
+    """
+
+    def __init__(self, csr: DeviceCSR, count: int, chunk: int | None = None):
         lib = L.load()
         dev = csr.colidx.device
         self.count = int(count)
-        c = max(self.count, 1)
-        self.tri = torch.empty(c, dtype=torch.int32, device=dev)
-        self.sq_i = torch.empty(c, dtype=torch.int32, device=dev)
-        self.sq_j = torch.empty(c, dtype=torch.int32, device=dev)
-        self.gamma = torch.empty(c, dtype=torch.int32, device=dev)
-        self.bfc = torch.empty(c, dtype=torch.float64, device=dev)
-        self.scratch_bytes = int(lib.dcr_bfc_paper_scratch_bytes(csr.n, csr.max_degree, self.count))
+        self.chunk = max(int(chunk if chunk is not None else count), 1)
+        c = self.chunk
+        self.block = torch.zeros(c * 24, dtype=torch.uint8, device=dev)
+        self.bfc = self.block[: c * 8].view(torch.float64)
+        ints = self.block[c * 8:].view(torch.int32)
+        self.tri, self.sq_i, self.sq_j, self.gamma = ints[:c], ints[c:2 * c], ints[2 * c:3 * c], ints[3 * c:4 * c]
+        self.scratch_bytes = int(lib.dcr_bfc_paper_scratch_bytes(csr.n, csr.max_degree, max(self.count, 1)))
         self.scratch = torch.empty(max(self.scratch_bytes, 256), dtype=torch.uint8, device=dev)
 
 
@@ -121,10 +125,11 @@ def shard_count(n_edges: int, rank: int, world: int) -> int:
 
 
 def paper_flavour(csr: DeviceCSR, rank: int = 0, world: int = 1, ws: PaperWorkspace | None = None,
-                  edges=None) -> dict:
+                  edges=None, events=None) -> dict:
     """Paper-flavour BFC for the undirected edges ``e = rank + t*world`` (compact outputs indexed by ``t``).
 
     ``edges``: optional ``(esrc, edst)`` int32 device tensors replacing the CSR's own ``row < col`` edge list.
+    ``events``: optional pair of recorded-once ``torch.cuda.Event(enable_timing=True)`` bracketing the edge kernels.
     """
     lib = L.load()
     if edges is None:
@@ -135,13 +140,35 @@ def paper_flavour(csr: DeviceCSR, rank: int = 0, world: int = 1, ws: PaperWorksp
     count = shard_count(n_edges, rank, world)
     if ws is None:
         ws = PaperWorkspace(csr, count)
+    ev0 = ev1 = 0
+    if events is not None:
+        ev0, ev1 = events[0].cuda_event, events[1].cuda_event
     if count > 0:
         L.check(lib.dcr_bfc_paper(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, csr.max_degree,
                                   esrc.data_ptr(), edst.data_ptr(), rank, world, count, ws.tri.data_ptr(),
                                   ws.sq_i.data_ptr(), ws.sq_j.data_ptr(), ws.gamma.data_ptr(), ws.bfc.data_ptr(),
-                                  ws.scratch.data_ptr(), ws.scratch_bytes, L.current_stream()), "dcr_bfc_paper")
+                                  ws.scratch.data_ptr(), ws.scratch_bytes, ev0, ev1, L.current_stream()),
+                "dcr_bfc_paper")
     return {"esrc": esrc, "edst": edst, "count": count, "tri": ws.tri[:count], "sq_i": ws.sq_i[:count],
             "sq_j": ws.sq_j[:count], "gamma": ws.gamma[:count], "bfc": ws.bfc[:count], "ws": ws}
+
+
+def unshard(gathered: torch.Tensor, world: int, chunk: int, n_edges: int, out: PaperWorkspace | None = None,
+            csr: DeviceCSR | None = None) -> dict:
+    """Full-graph arrays (indexed by edge id) from the all-gathered per-rank blocks."""
+    lib = L.load()
+    dev = gathered.device
+    c = max(n_edges, 1)
+    tri = torch.empty(c, dtype=torch.int32, device=dev)
+    sq_i = torch.empty(c, dtype=torch.int32, device=dev)
+    sq_j = torch.empty(c, dtype=torch.int32, device=dev)
+    gamma = torch.empty(c, dtype=torch.int32, device=dev)
+    val = torch.empty(c, dtype=torch.float64, device=dev)
+    L.check(lib.dcr_bfc_paper_unshard(gathered.data_ptr(), int(world), int(chunk), int(n_edges), tri.data_ptr(),
+                                      sq_i.data_ptr(), sq_j.data_ptr(), gamma.data_ptr(), val.data_ptr(),
+                                      L.current_stream()), "dcr_bfc_paper_unshard")
+    return {"tri": tri[:n_edges], "sq_i": sq_i[:n_edges], "sq_j": sq_j[:n_edges], "gamma": gamma[:n_edges],
+            "bfc": val[:n_edges]}
 
 
 def scatter_dense(csr: DeviceCSR, vals: torch.Tensor, C: torch.Tensor) -> torch.Tensor:

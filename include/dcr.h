@@ -87,7 +87,15 @@ int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t count);
 int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree, const int32_t* esrc,
                   const int32_t* edst, int64_t e_first, int64_t e_stride, int64_t count, int32_t* out_tri,
                   int32_t* out_sq_i, int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc, void* scratch,
-                  int64_t scratch_bytes, void* stream);
+                  int64_t scratch_bytes, void* ev_edge_begin, void* ev_edge_end, void* stream);
+/* ev_edge_begin / ev_edge_end: optional cudaEvent_t (NULL = none) recorded on `stream` around the edge kernels
+ * (the gather-bound part; the planning kernels before them are O(E)) — used by bench.py for the roofline. */
+
+/* Multi-GPU epilogue: `gathered` = the all-gathered per-rank result blocks, rank r's block at byte offset
+ * r*chunk*24 laid out as bfc[chunk] f64 | tri[chunk] | sq_i[chunk] | sq_j[chunk] | gamma[chunk] int32, where
+ * local index t of rank r is edge e = r + t*world.  Writes the full-graph arrays indexed by edge id. */
+int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t chunk, int64_t n_edges, int32_t* out_tri,
+                          int32_t* out_sq_i, int32_t* out_sq_j, int32_t* out_gamma, double* out_bfc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Candidate scoring.  Replaces _balanced_forman_post_delta / balanced_forman_post_delta
