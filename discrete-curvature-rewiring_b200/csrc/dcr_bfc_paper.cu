@@ -9,14 +9,20 @@
 // i.e. everything is a function of cnt(m) = |N(m) ∩ M_i| for m in M_j and cnt(k) = |N(k) ∩ M_j| for k in M_i.
 //
 // Mapping to the GPU.  One TEAM per edge — a warp for edges with d_i + d_j <= 512, a whole CTA above that:
-//   1. the team builds ONE open-addressing hash table in shared memory holding N(i) ∪ N(j) \ {i,j}, each key
-//      tagged 1 (only in N(i)), 2 (only in N(j)) or 3 (both = triangle node); #tag-3 keys = #triangles;
-//   2. pass A: for every m with tag 2 a warp streams the neighbour list N(m) with coalesced 128-byte loads,
-//      4 independent loads in flight per lane, one shared-memory probe per element, ballot/popc count;
-//   3. pass B: the mirrored scan (skipped when pass A found no square: the bipartite graph M_i–M_j is empty).
-// Global traffic is exactly the algorithmic gather of SURVEY.md §8d: the two endpoint lists once and every 2-hop
-// list once per edge; the CSR of the benchmark graphs is L2-resident, so the kernel is bound by L2->SM gather
-// bandwidth and shared-memory probe throughput, not by DRAM.
+//   1. the team builds ONE open-addressing hash table in shared memory holding N(a) ∪ N(b) \ {a,b}, each key
+//      tagged 1 (only in N(a)), 2 (only in N(b)) or 3 (both = triangle node); #tag-3 keys = #triangles.
+//      (a,b) = (i,j) or (j,i): b is the endpoint whose 2-hop lists are CHEAPER to stream (smaller S_b - d_a);
+//   2. ONE scan: for every m with tag 2 the neighbour list N(m) is streamed.  Every match (k in N(m) with tag 1)
+//      is an edge of the bipartite graph M_a–M_b, and it is counted TWICE: in a per-list counter (-> cnt(m)) and
+//      in a 16-bit counter attached to k's table slot (-> cnt(k)); so the expensive side is never streamed;
+//   3. a sweep over the table slots turns the slot counters into (#squares, max) of endpoint a, the per-list
+//      counters give those of endpoint b.
+// The lists of 32 heads at a time are processed as ONE flat stream (prefix sums of the list lengths in shared
+// memory, lane f handles flat element f): coalesced where lists are long, and no idle lanes where they are short
+// — half of the 2-hop lists of a power-law graph have fewer than 20 entries.
+// Global traffic is at most the algorithmic gather of SURVEY.md §8d (which charges BOTH sides' 2-hop lists): the
+// two endpoint lists once and the cheaper side's 2-hop lists once per edge.  The CSR of the benchmark graphs is
+// L2-resident, so the kernel is bound by instruction issue / L1 gathers / shared-memory probes, not by DRAM.
 // Edges are bucketed by class and by log2(work) on the device (heavy first) and teams pull edges from a global
 // counter, so power-law hubs do not serialise the tail.  Grids are persistent: a multiple of the SM count.
 #include <algorithm>
@@ -27,10 +33,11 @@ namespace dcr {
 
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
-constexpr int WARP_SLOTS = 1024;             // per-warp table: 4 KB, d_i + d_j <= 512
+constexpr int WARP_SLOTS = 1024;             // per-warp table: 4 KB keys + 2 KB counters, d_i + d_j <= 512
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int CTA_SLOTS = 32768;             // per-CTA table: 128 KB, d_i + d_j <= 16384
+constexpr int CTA_SLOTS = 32768;             // per-CTA table: 128 KB keys + 64 KB counters, d_i + d_j <= 16384
 constexpr int CTA_THREADS = 512;
+constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
 constexpr int N_CLASSES = 3;                 // 0 = warp team, 1 = CTA team (smem table), 2 = CTA team (global table)
 constexpr int BUCKETS_PER_CLASS = 64;
 constexpr int N_BUCKETS = N_CLASSES * BUCKETS_PER_CLASS;
@@ -66,15 +73,15 @@ struct PaperArgs {
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
 
-// tag of `key` in the table (0 = absent).  A table in GLOBAL memory is filled with L2 atomics by other warps of
-// the CTA, so it is read with ld.global.cg (L2) — an L1 line fetched during the build phase may be stale.
+// slot of `key` in the table, or -1.  A table in GLOBAL memory is filled with L2 atomics by other warps of the
+// CTA, so it is read with ld.global.cg (L2) — an L1 line fetched during the build phase may be stale.
 template <bool GLOBAL>
-__device__ __forceinline__ uint32_t probe(const uint32_t* tab, uint32_t mask, int shift, uint32_t key) {
+__device__ __forceinline__ int probe_slot(const uint32_t* tab, uint32_t mask, int shift, uint32_t key, uint32_t& val) {
     uint32_t h = hash_slot(key, shift);
     while (true) {
         const uint32_t v = GLOBAL ? __ldcg(tab + h) : tab[h];
-        if (v == EMPTY) return 0u;
-        if ((v & KEYMASK) == key) return v >> 30;
+        if (v == EMPTY) return -1;
+        if ((v & KEYMASK) == key) { val = v; return (int)h; }
         h = (h + 1) & mask;
     }
 }
@@ -145,7 +152,8 @@ __global__ void classify_kernel(PaperArgs a) {
         a.bucket[t] = 255;
         return;
     }
-    const long long work = (a.node_s[i] - dj) + (a.node_s[j] - di) + di + dj;
+    const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
+    const long long work = min(ca, cb) + 4LL * (di + dj);
     const int need = di + dj;
     int cls = need * 2 <= WARP_SLOTS ? 0 : (need * 2 <= CTA_SLOTS ? 1 : 2);
     int lg = 63 - __clzll(work | 1);
@@ -184,68 +192,116 @@ __device__ __forceinline__ void team_sync() {
     if (CTA_TEAM) __syncthreads(); else __syncwarp();
 }
 
-// Stream the neighbour lists of all keys of `list` (a row of the CSR) that carry `scan_tag`, counting per list
-// the elements that carry `hit_tag`.  Returns per-warp partial (#lists with a hit, max hits); chunk c of 32 list
-// heads is handled by warp (c mod team_warps).
-template <bool CTA_TEAM, bool GLOBAL>
-__device__ __forceinline__ void scan_side(const PaperArgs& a, const uint32_t* tab, uint32_t mask, int shift,
-                                          int list_begin, int list_len, uint32_t scan_tag, uint32_t hit_tag,
-                                          int team_warp, int team_warps, int lane, int& sq, int& gmax) {
+// Slot counters: 16 bit per slot packed in 32-bit words for the shared-memory tables (a count is at most the
+// degree of the scanned endpoint, < 16384 there), 32 bit per slot for the global-memory tables.
+template <bool GLOBAL>
+__device__ __forceinline__ void slot_count_add(uint32_t* cnt, int h) {
+    if (GLOBAL) atomicAdd(&cnt[h], 1u);
+    else atomicAdd(&cnt[h >> 1], (h & 1) ? 0x10000u : 1u);
+}
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t slot_count_get(const uint32_t* cnt, uint32_t h) {
+    if (GLOBAL) return __ldcg(cnt + h);
+    return (cnt[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
+}
+
+// Flat-stream scan of the neighbour lists of the heads list[c0 .. c0+32) that carry tag 2.  `st` = this warp's
+// stream state in shared memory.  Matches (tag 1) bump the list's counter and the matched key's slot counter.
+// Returns (through sq, gmax) the number of lists with a match and the largest per-list count.
+template <bool GLOBAL>
+__device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
+                                           int shift, int list_begin, int list_len, int c0, int* st, int lane,
+                                           int& sq, int& gmax) {
     const int32_t* __restrict__ rowptr = a.rowptr;
     const int32_t* __restrict__ colidx = a.colidx;
-    for (int c0 = team_warp * 32; c0 < list_len; c0 += team_warps * 32) {
-        const int t = c0 + lane;
-        int m = -1, mb = 0, md = 0;
-        if (t < list_len) {
-            m = colidx[list_begin + t];
-            if (probe<GLOBAL>(tab, mask, shift, (uint32_t)m) == scan_tag) {
-                mb = rowptr[m];
-                md = rowptr[m + 1] - mb;
-            } else {
-                m = -1;
-            }
-        }
-        unsigned todo = __ballot_sync(FULL, m >= 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int beg = __shfl_sync(FULL, mb, src);
-            const int deg = __shfl_sync(FULL, md, src);
-            int cnt = 0;
-            for (int base = 0; base < deg; base += 32 * UNROLL) {
-                int k[UNROLL];
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const int idx = base + u * 32 + lane;
-                    k[u] = idx < deg ? colidx[beg + idx] : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const bool hit = k[u] >= 0 && probe<GLOBAL>(tab, mask, shift, (uint32_t)k[u]) == hit_tag;
-                    cnt += __popc(__ballot_sync(FULL, hit));
-                }
-            }
-            sq += cnt > 0;
-            gmax = max(gmax, cnt);
+    int* pre = st;            // [33] exclusive prefix of the list lengths
+    int* beg = st + 33;       // [32] first CSR slot of each list
+    int* lcnt = st + 65;      // [32] per-list match counters
+    const int t = c0 + lane;
+    int mb = 0, md = 0;
+    if (t < list_len) {
+        const int m = colidx[list_begin + t];
+        uint32_t v;
+        if (probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)m, v) >= 0 && (v >> 30) == 2u) {
+            mb = rowptr[m];
+            md = rowptr[m + 1] - mb;
         }
     }
+    int inc = md;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += up;
+    }
+    const int total = __shfl_sync(FULL, inc, 31);
+    if (total == 0) return;
+    pre[lane + 1] = inc;
+    if (lane == 0) pre[0] = 0;
+    beg[lane] = mb;
+    lcnt[lane] = 0;
+    __syncwarp();
+    int l = 0;
+    for (int f0 = lane; f0 < total; f0 += 32 * UNROLL) {
+        int k[UNROLL], lu[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int f = f0 + 32 * u;
+            k[u] = -1;
+            lu[u] = 0;
+            if (f < total) {
+                while (pre[l + 1] <= f) ++l;         // monotone in f: amortised O(1)
+                lu[u] = l;
+                k[u] = colidx[beg[l] + (f - pre[l])];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (k[u] >= 0) {
+                uint32_t v;
+                const int h = probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)k[u], v);
+                if (h >= 0 && (v >> 30) == 1u) {
+                    atomicAdd(&lcnt[lu[u]], 1);
+                    slot_count_add<GLOBAL>(cnt, h);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int c = lcnt[lane];
+    sq += c > 0;
+    gmax = max(gmax, c);
+    __syncwarp();
 }
 
 template <bool CTA_TEAM, bool GLOBAL_TABLE>
-__global__ void __launch_bounds__(CTA_TEAM ? CTA_THREADS : WARP_TEAM_WARPS * 32)
+__global__ void __launch_bounds__(CTA_TEAM ? CTA_THREADS : WARP_TEAM_WARPS * 32, CTA_TEAM ? 1 : 4)
 paper_edge_kernel(PaperArgs a, int cls) {
-    extern __shared__ uint32_t smem_tab[];
+    extern __shared__ uint32_t smem_dyn[];
     __shared__ unsigned int s_idx;
-    __shared__ int s_red[5];  // tri, sqA, gA, sqB, gB
+    __shared__ int s_chunk;
+    __shared__ int s_red[5];  // tri, sq(lists), g(lists), sq(slots), g(slots)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int team_warps = CTA_TEAM ? (CTA_THREADS / 32) : 1;
-    const int team_warp = CTA_TEAM ? warp : 0;
-    const int team_threads = team_warps * 32;
+    constexpr int team_warps = CTA_TEAM ? (CTA_THREADS / 32) : 1;
+    constexpr int team_threads = team_warps * 32;
+    constexpr int nwarps = CTA_TEAM ? (CTA_THREADS / 32) : WARP_TEAM_WARPS;
     const int team_tid = CTA_TEAM ? (int)threadIdx.x : lane;
-    uint32_t* tab = GLOBAL_TABLE ? a.gtables + (size_t)blockIdx.x * a.gslots
-                                 : (CTA_TEAM ? smem_tab : smem_tab + warp * WARP_SLOTS);
+    // shared-memory carve-up: [stream state per warp][table keys][slot counters]
+    int* st = (int*)smem_dyn + warp * STREAM_INTS;
+    uint32_t* sm_tab = smem_dyn + nwarps * STREAM_INTS;
+    uint32_t* tab;
+    uint32_t* cnt;
+    if (GLOBAL_TABLE) {
+        tab = a.gtables + (size_t)blockIdx.x * a.gslots * 2;
+        cnt = tab + a.gslots;
+    } else if (CTA_TEAM) {
+        tab = sm_tab;
+        cnt = sm_tab + CTA_SLOTS;
+    } else {
+        tab = sm_tab + warp * (WARP_SLOTS + WARP_SLOTS / 2);
+        cnt = tab + WARP_SLOTS;
+    }
     const unsigned int cbeg = a.plan->class_begin[cls];
     const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
 
@@ -255,6 +311,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
             if (threadIdx.x == 0) {
                 s_idx = atomicAdd(&a.plan->next[cls], 1u);
                 s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
+                s_chunk = 0;
             }
             __syncthreads();
             idx = s_idx;
@@ -267,27 +324,32 @@ paper_edge_kernel(PaperArgs a, int cls) {
         const uint32_t t = a.order[cbeg + idx];
         const int64_t e = a.e_first + (int64_t)t * a.e_stride;
         const int i = a.esrc[e], j = a.edst[e];
-        const int si = a.rowptr[i], di = a.rowptr[i + 1] - si;
-        const int sj = a.rowptr[j], dj = a.rowptr[j + 1] - sj;
+        const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+        // (va, vb): vb = endpoint whose 2-hop lists are streamed (the cheaper side), va = the tested side
+        const bool swapped = (a.node_s[i] - dj) < (a.node_s[j] - di);
+        const int va = swapped ? j : i, vb = swapped ? i : j;
+        const int sa = a.rowptr[va], da = swapped ? dj : di;
+        const int sb = a.rowptr[vb], db = swapped ? di : dj;
 
         // table size: power of two >= 2*(d_i+d_j), at least 64 slots
         const int need = 2 * (di + dj);
-        int lg = 32 - __clz(max(need, 64) - 1);
+        const int lg = 32 - __clz(max(need, 64) - 1);
         const uint32_t slots = 1u << lg;
         const uint32_t mask = slots - 1;
         const int shift = 32 - lg;
 
         for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
+        for (uint32_t s = team_tid; s < (GLOBAL_TABLE ? slots : slots / 2); s += team_threads) cnt[s] = 0u;
         team_sync<CTA_TEAM>();
-        for (int p = team_tid; p < di; p += team_threads) {
-            const int k = a.colidx[si + p];
-            if (k != j) insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 1u);
+        for (int p = team_tid; p < da; p += team_threads) {
+            const int k = a.colidx[sa + p];
+            if (k != vb) insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 1u);
         }
         team_sync<CTA_TEAM>();
         int tri = 0;
-        for (int p = team_tid; p < dj; p += team_threads) {
-            const int k = a.colidx[sj + p];
-            if (k != i) tri += insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 2u);
+        for (int p = team_tid; p < db; p += team_threads) {
+            const int k = a.colidx[sb + p];
+            if (k != va) tri += insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 2u);
         }
         tri = warp_sum(tri);
         if (CTA_TEAM) {
@@ -295,30 +357,54 @@ paper_edge_kernel(PaperArgs a, int cls) {
         }
         team_sync<CTA_TEAM>();
 
-        // pass A: lists of m in M_j (tag 2), hits in M_i (tag 1)  -> squares at j
-        int sqA = 0, gA = 0, sqB = 0, gB = 0;
-        scan_side<CTA_TEAM, GLOBAL_TABLE>(a, tab, mask, shift, sj, dj, 2u, 1u, team_warp, team_warps, lane, sqA, gA);
+        // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
+        int sqL = 0, gL = 0, sqS = 0, gS = 0;
         if (CTA_TEAM) {
-            if (lane == 0 && sqA) { atomicAdd(&s_red[1], sqA); atomicMax(&s_red[2], gA); }
+            while (true) {       // warps pull chunks of 32 heads
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk, 1);
+                c = __shfl_sync(FULL, c, 0);
+                if (c * 32 >= db) break;
+                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c * 32, st, lane, sqL, gL);
+            }
+            sqL = warp_sum(sqL);
+            gL = warp_max(gL);
+            if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
             __syncthreads();
-            sqA = s_red[1]; gA = s_red[2]; tri = s_red[0];
+            sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
+        } else {
+            for (int c0 = 0; c0 < db; c0 += 32)
+                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, st, lane, sqL, gL);
+            sqL = warp_sum(sqL);
+            gL = warp_max(gL);
+            __syncwarp();
         }
-        // pass B: lists of k in M_i (tag 1), hits in M_j (tag 2)  -> squares at i; empty iff pass A was empty
-        if (sqA > 0) {
-            scan_side<CTA_TEAM, GLOBAL_TABLE>(a, tab, mask, shift, si, di, 1u, 2u, team_warp, team_warps, lane, sqB, gB);
+        // the sweep: slot counters of the tag-1 keys -> squares at va (empty iff the scan found nothing)
+        if (sqL > 0) {
+            for (uint32_t s = team_tid; s < slots; s += team_threads) {
+                const uint32_t v = GLOBAL_TABLE ? __ldcg(tab + s) : tab[s];
+                if ((v >> 30) == 1u) {
+                    const int c = (int)slot_count_get<GLOBAL_TABLE>(cnt, s);
+                    sqS += c > 0;
+                    gS = max(gS, c);
+                }
+            }
+            sqS = warp_sum(sqS);
+            gS = warp_max(gS);
             if (CTA_TEAM) {
-                if (lane == 0 && sqB) { atomicAdd(&s_red[3], sqB); atomicMax(&s_red[4], gB); }
+                if (lane == 0 && sqS) { atomicAdd(&s_red[3], sqS); atomicMax(&s_red[4], gS); }
                 __syncthreads();
-                sqB = s_red[3]; gB = s_red[4];
+                sqS = s_red[3]; gS = s_red[4];
             }
         }
         if (team_tid == 0) {
-            const int gamma = (sqA > 0 && sqB > 0) ? max(gA, gB) : 0;
+            const int sq_i = swapped ? sqL : sqS, sq_j = swapped ? sqS : sqL;
+            const int gamma = (sqL > 0 && sqS > 0) ? max(gL, gS) : 0;
             a.out_tri[t] = tri;
-            a.out_sq_i[t] = sqB;
-            a.out_sq_j[t] = sqA;
+            a.out_sq_i[t] = sq_i;
+            a.out_sq_j[t] = sq_j;
             a.out_gamma[t] = gamma;
-            a.out_bfc[t] = paper_value(di, dj, tri, sqB, sqA, gamma);
+            a.out_bfc[t] = paper_value(di, dj, tri, sq_i, sq_j, gamma);
         }
         team_sync<CTA_TEAM>();  // table / s_red reuse
     }
@@ -355,7 +441,7 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     if ((int64_t)max_degree * 4 > CTA_SLOTS) {  // some edge may need a table beyond shared memory
         L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
         L.g_ctas = sm_count();
-        off = align_up(off + (size_t)L.g_ctas * L.gslots * sizeof(uint32_t), 256);
+        off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
     }
     L.total = off;
     return L;
@@ -406,12 +492,13 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
     // heavy classes first: they own the long tail
     if (L.gslots) {
-        paper_edge_kernel<true, true><<<L.g_ctas, CTA_THREADS, 0, st>>>(a, 2);
+        const int smem = (CTA_THREADS / 32) * STREAM_INTS * (int)sizeof(int);
+        paper_edge_kernel<true, true><<<L.g_ctas, CTA_THREADS, smem, st>>>(a, 2);
         DCR_LAUNCH_CHECK();
     }
     {
         static bool attr_done = false;
-        const int smem = CTA_SLOTS * (int)sizeof(uint32_t);
+        const int smem = ((CTA_THREADS / 32) * STREAM_INTS + CTA_SLOTS + CTA_SLOTS / 2) * (int)sizeof(uint32_t);
         if (!attr_done) {
             DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<true, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -421,8 +508,14 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_LAUNCH_CHECK();
     }
     {
-        const int smem = WARP_TEAM_WARPS * WARP_SLOTS * (int)sizeof(uint32_t);  // 32 KB per CTA
-        paper_edge_kernel<false, false><<<sms * 6, WARP_TEAM_WARPS * 32, smem, st>>>(a, 0);
+        static bool attr_done = false;
+        const int smem = WARP_TEAM_WARPS * (STREAM_INTS + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);  // 51 KB
+        if (!attr_done) {
+            DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<false, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_done = true;
+        }
+        paper_edge_kernel<false, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem, st>>>(a, 0);
         DCR_LAUNCH_CHECK();
     }
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
