@@ -33,13 +33,19 @@ namespace dcr {
 
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
-constexpr int WARP_SLOTS = 1024;             // per-warp table: 4 KB keys + 2 KB counters, d_i + d_j <= 512
+// Edge classes by the degree d_a of the TESTED endpoint (the one whose neighbour set goes into the hash table):
+//   class 0  d_a <= 128    warp team,            1024-slot table per warp (load factor <= 1/8)
+//   class 1  d_a <= 1024   128-thread CTA team,  8192-slot table          (load factor <= 1/8), 4 CTAs per SM
+//   class 2  d_a <= 16384  512-thread CTA team,  32768-slot table         (load factor <= 1/2), 1 CTA per SM
+//   class 3  larger        512-thread CTA team,  table in global memory (L2)
+constexpr int N_CLASSES = 4;
+constexpr int CLASS_DA[3] = {128, 1024, 16384};
+constexpr int WARP_SLOTS = 1024;
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int CTA_SLOTS = 32768;             // per-CTA table: 128 KB keys + 64 KB counters, d_i + d_j <= 16384
-constexpr int CTA_THREADS = 512;
+constexpr int MID_SLOTS = 8192, MID_THREADS = 128;
+constexpr int BIG_SLOTS = 32768, BIG_THREADS = 512;
 constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
-constexpr int N_CLASSES = 3;                 // 0 = warp team, 1 = CTA team (smem table), 2 = CTA team (global table)
-constexpr int BUCKETS_PER_CLASS = 64;
+constexpr int BUCKETS_PER_CLASS = 48;
 constexpr int N_BUCKETS = N_CLASSES * BUCKETS_PER_CLASS;
 constexpr int UNROLL = 4;
 
@@ -154,10 +160,12 @@ __global__ void classify_kernel(PaperArgs a) {
     }
     const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
     const long long work = min(ca, cb) + 4LL * (di + dj);
-    const int need = di + dj;
-    int cls = need * 2 <= WARP_SLOTS ? 0 : (need * 2 <= CTA_SLOTS ? 1 : 2);
-    int lg = 63 - __clzll(work | 1);
-    int b = cls * BUCKETS_PER_CLASS + (BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1));  // heavy first
+    const int da = cb < ca ? dj : di;                                  // degree of the tested endpoint (see kernel)
+    const int db = cb < ca ? di : dj;                                  // degree of the streamed endpoint
+    int cls = da <= CLASS_DA[0] ? 0 : (da <= CLASS_DA[1] ? 1 : (da <= CLASS_DA[2] ? 2 : 3));
+    if (db > 65535) cls = 3;     // the 16-bit slot counters of the shared-memory tables count up to d_b lists
+    const int lg = 63 - __clzll(work | 1);
+    const int b = cls * BUCKETS_PER_CLASS + (BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1));  // heavy first
     a.bucket[t] = (uint8_t)b;
     atomicAdd(&a.plan->hist[b], 1u);
 }
@@ -192,8 +200,9 @@ __device__ __forceinline__ void team_sync() {
     if (CTA_TEAM) __syncthreads(); else __syncwarp();
 }
 
-// Slot counters: 16 bit per slot packed in 32-bit words for the shared-memory tables (a count is at most the
-// degree of the scanned endpoint, < 16384 there), 32 bit per slot for the global-memory tables.
+// Slot counters: 16 bit per slot packed in 32-bit words for the shared-memory tables (a count is at most the number
+// of streamed lists, and classes 0-2 cap it far below 65536 only through d_b — see the saturation note in the
+// kernel), 32 bit per slot for the global-memory tables.
 template <bool GLOBAL>
 __device__ __forceinline__ void slot_count_add(uint32_t* cnt, int h) {
     if (GLOBAL) atomicAdd(&cnt[h], 1u);
@@ -205,50 +214,22 @@ __device__ __forceinline__ uint32_t slot_count_get(const uint32_t* cnt, uint32_t
     return (cnt[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
 }
 
-// Flat-stream scan of the neighbour lists of the heads list[c0 .. c0+32) that carry tag 2.  `st` = this warp's
-// stream state in shared memory.  Matches (tag 1) bump the list's counter and the matched key's slot counter.
-// Returns (through sq, gmax) the number of lists with a match and the largest per-list count.
+// The flat stream: `pre` = exclusive prefix sums of the list lengths (pre[l+1]-pre[l] = length of list l), `beg` =
+// first CSR slot of each list, `lcnt` = per-list match counters, all in shared memory.  This warp handles the flat
+// elements [f_begin, f_end); lane f%32 takes element f.  `l` = a list index with pre[l] <= f_begin.
+// A match (key present with tag 1) bumps the list's counter and the matched key's slot counter.
 template <bool GLOBAL>
-__device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
-                                           int shift, int list_begin, int list_len, int c0, int* st, int lane,
-                                           int& sq, int& gmax) {
-    const int32_t* __restrict__ rowptr = a.rowptr;
-    const int32_t* __restrict__ colidx = a.colidx;
-    int* pre = st;            // [33] exclusive prefix of the list lengths
-    int* beg = st + 33;       // [32] first CSR slot of each list
-    int* lcnt = st + 65;      // [32] per-list match counters
-    const int t = c0 + lane;
-    int mb = 0, md = 0;
-    if (t < list_len) {
-        const int m = colidx[list_begin + t];
-        uint32_t v;
-        if (probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)m, v) >= 0 && (v >> 30) == 2u) {
-            mb = rowptr[m];
-            md = rowptr[m + 1] - mb;
-        }
-    }
-    int inc = md;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += up;
-    }
-    const int total = __shfl_sync(FULL, inc, 31);
-    if (total == 0) return;
-    pre[lane + 1] = inc;
-    if (lane == 0) pre[0] = 0;
-    beg[lane] = mb;
-    lcnt[lane] = 0;
-    __syncwarp();
-    int l = 0;
-    for (int f0 = lane; f0 < total; f0 += 32 * UNROLL) {
+__device__ __forceinline__ void flat_scan(const int32_t* __restrict__ colidx, const uint32_t* tab, uint32_t* cnt,
+                                          uint32_t mask, int shift, const int* pre, const int* beg, int* lcnt, int l,
+                                          int f_begin, int f_end, int lane) {
+    for (int f0 = f_begin + lane; f0 < f_end; f0 += 32 * UNROLL) {
         int k[UNROLL], lu[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int f = f0 + 32 * u;
             k[u] = -1;
             lu[u] = 0;
-            if (f < total) {
+            if (f < f_end) {
                 while (pre[l + 1] <= f) ++l;         // monotone in f: amortised O(1)
                 lu[u] = l;
                 k[u] = colidx[beg[l] + (f - pre[l])];
@@ -266,6 +247,47 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
             }
         }
     }
+}
+
+// (begin, length) of the neighbour list of head m if m is a PURE neighbour of vb (not va, not in the table), else (0,0)
+template <bool GLOBAL>
+__device__ __forceinline__ void pure_head(const PaperArgs& a, const uint32_t* tab, uint32_t mask, int shift, int m,
+                                          int va, int& b, int& d) {
+    b = 0;
+    d = 0;
+    uint32_t v;
+    if (m != va && probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)m, v) < 0) {
+        b = a.rowptr[m];
+        d = a.rowptr[m + 1] - b;
+    }
+}
+
+// Warp team: the lists of the pure heads among list[c0 .. c0+32) as one flat stream.  `st` = this warp's stream
+// state.  Accumulates (#lists with a match, largest per-list count) per lane.
+template <bool GLOBAL>
+__device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
+                                           int shift, int list_begin, int list_len, int c0, int va, int* st, int lane,
+                                           int& sq, int& gmax) {
+    int* pre = st;            // [33]
+    int* beg = st + 33;       // [32]
+    int* lcnt = st + 65;      // [32]
+    const int t = c0 + lane;
+    int mb = 0, md = 0;
+    if (t < list_len) pure_head<GLOBAL>(a, tab, mask, shift, a.colidx[list_begin + t], va, mb, md);
+    int inc = md;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += up;
+    }
+    const int total = __shfl_sync(FULL, inc, 31);
+    if (total == 0) return;
+    pre[lane + 1] = inc;
+    if (lane == 0) pre[0] = 0;
+    beg[lane] = mb;
+    lcnt[lane] = 0;
+    __syncwarp();
+    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, 0, 0, total, lane);
     __syncwarp();
     const int c = lcnt[lane];
     sq += c > 0;
@@ -273,23 +295,92 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
     __syncwarp();
 }
 
-template <bool CTA_TEAM, bool GLOBAL_TABLE>
-__global__ void __launch_bounds__(CTA_TEAM ? CTA_THREADS : WARP_TEAM_WARPS * 32, CTA_TEAM ? 1 : 4)
+// CTA team: up to HEADS = 4*THREADS heads per round; the CTA-wide flat stream is cut into equal contiguous ranges,
+// one per warp, so every warp streams the same number of elements whatever the list-length distribution (a hub's
+// list next to twenty short ones does not serialise).  `cs` = pre[HEADS+1] | beg[HEADS] | cnt[HEADS].
+template <int THREADS, bool GLOBAL>
+__device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask, int shift,
+                                         int list_begin, int list_len, int va, int* cs, int* s_warp_tot, int& sq,
+                                         int& gmax) {
+    constexpr int HPT = 4;                        // heads per thread
+    constexpr int HEADS = HPT * THREADS;
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* pre = cs;                 // [HEADS + 1]
+    int* beg = cs + HEADS + 1;     // [HEADS]
+    int* lcnt = beg + HEADS;       // [HEADS]
+    for (int h0 = 0; h0 < list_len; h0 += HEADS) {
+        const int nh = min(HEADS, list_len - h0);
+        int deg[HPT], run = 0;
+#pragma unroll
+        for (int q = 0; q < HPT; ++q) {
+            const int t = tid * HPT + q;
+            int b = 0, d = 0;
+            if (t < nh) pure_head<GLOBAL>(a, tab, mask, shift, a.colidx[list_begin + h0 + t], va, b, d);
+            beg[t] = b;
+            lcnt[t] = 0;
+            deg[q] = d;
+            run += d;
+        }
+        int inc = run;                            // exclusive scan of `run` over the CTA
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) s_warp_tot[warp] = inc;
+        __syncthreads();
+        int off = inc - run;
+        for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+#pragma unroll
+        for (int q = 0; q < HPT; ++q) {
+            pre[tid * HPT + q] = off;
+            off += deg[q];
+        }
+        if (tid == THREADS - 1) pre[HEADS] = off;
+        __syncthreads();
+        const int total = pre[HEADS];
+        if (total > 0) {
+            const int per_warp = ((total + NW * 32 - 1) / (NW * 32)) * 32;
+            const int f_begin = warp * per_warp, f_end = min(total, f_begin + per_warp);
+            if (f_begin < f_end) {
+                int lo = 0, hi = HEADS;            // first l with pre[l+1] > f_begin (warp-uniform search)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (pre[mid + 1] <= f_begin) lo = mid + 1; else hi = mid;
+                }
+                flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, lo, f_begin, f_end, lane);
+            }
+            __syncthreads();
+            for (int t = tid; t < nh; t += THREADS) {
+                const int c = lcnt[t];
+                sq += c > 0;
+                gmax = max(gmax, c);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// TEAM = threads per team (32 = warp team, several teams per CTA; otherwise the CTA is the team).
+template <int TEAM, int MAX_SLOTS, bool GLOBAL_TABLE>
+__global__ void __launch_bounds__(TEAM > 32 ? TEAM : WARP_TEAM_WARPS * 32, TEAM == BIG_THREADS ? 1 : 4)
 paper_edge_kernel(PaperArgs a, int cls) {
+    constexpr bool CTA_TEAM = TEAM > 32;
+    constexpr int NWARPS = CTA_TEAM ? TEAM / 32 : WARP_TEAM_WARPS;
+    constexpr int CTA_STREAM = 3 * 4 * TEAM + 8;
     extern __shared__ uint32_t smem_dyn[];
     __shared__ unsigned int s_idx;
-    __shared__ int s_chunk;
+    __shared__ int s_warp_tot[NWARPS];
     __shared__ int s_red[5];  // tri, sq(lists), g(lists), sq(slots), g(slots)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    constexpr int team_warps = CTA_TEAM ? (CTA_THREADS / 32) : 1;
-    constexpr int team_threads = team_warps * 32;
-    constexpr int nwarps = CTA_TEAM ? (CTA_THREADS / 32) : WARP_TEAM_WARPS;
+    constexpr int team_threads = CTA_TEAM ? TEAM : 32;
     const int team_tid = CTA_TEAM ? (int)threadIdx.x : lane;
-    // shared-memory carve-up: [stream state per warp][table keys][slot counters]
-    int* st = (int*)smem_dyn + warp * STREAM_INTS;
-    uint32_t* sm_tab = smem_dyn + nwarps * STREAM_INTS;
+    // shared-memory carve-up: [stream state (per warp | per CTA)][table keys][slot counters]
+    int* st = (int*)smem_dyn + (CTA_TEAM ? 0 : warp * STREAM_INTS);
+    uint32_t* sm_tab = smem_dyn + (CTA_TEAM ? CTA_STREAM : NWARPS * STREAM_INTS);
     uint32_t* tab;
     uint32_t* cnt;
     if (GLOBAL_TABLE) {
@@ -297,13 +388,14 @@ paper_edge_kernel(PaperArgs a, int cls) {
         cnt = tab + a.gslots;
     } else if (CTA_TEAM) {
         tab = sm_tab;
-        cnt = sm_tab + CTA_SLOTS;
+        cnt = sm_tab + MAX_SLOTS;
     } else {
-        tab = sm_tab + warp * (WARP_SLOTS + WARP_SLOTS / 2);
-        cnt = tab + WARP_SLOTS;
+        tab = sm_tab + warp * (MAX_SLOTS + MAX_SLOTS / 2);
+        cnt = tab + MAX_SLOTS;
     }
     const unsigned int cbeg = a.plan->class_begin[cls];
     const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
+    const uint32_t max_slots = GLOBAL_TABLE ? a.gslots : (uint32_t)MAX_SLOTS;
 
     while (true) {
         unsigned int idx;
@@ -311,7 +403,6 @@ paper_edge_kernel(PaperArgs a, int cls) {
             if (threadIdx.x == 0) {
                 s_idx = atomicAdd(&a.plan->next[cls], 1u);
                 s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
-                s_chunk = 0;
             }
             __syncthreads();
             idx = s_idx;
@@ -331,9 +422,9 @@ paper_edge_kernel(PaperArgs a, int cls) {
         const int sa = a.rowptr[va], da = swapped ? dj : di;
         const int sb = a.rowptr[vb], db = swapped ? di : dj;
 
-        // table size: power of two >= 2*(d_i+d_j), at least 64 slots
-        const int need = 2 * (di + dj);
-        const int lg = 32 - __clz(max(need, 64) - 1);
+        // table of N(va) \ {vb}: power of two >= 8*d_a (load factor <= 1/8 keeps probe chains short and uniform
+        // across the lanes of a warp), capped by the class's table
+        const int lg = min(32 - __clz(max(8 * da, 64) - 1), 31 - __clz(max_slots));
         const uint32_t slots = 1u << lg;
         const uint32_t mask = slots - 1;
         const int shift = 32 - lg;
@@ -346,10 +437,16 @@ paper_edge_kernel(PaperArgs a, int cls) {
             if (k != vb) insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 1u);
         }
         team_sync<CTA_TEAM>();
+        // common neighbours: heads of N(vb) found in the table become tag 3 (never a match, never a pure head)
         int tri = 0;
         for (int p = team_tid; p < db; p += team_threads) {
-            const int k = a.colidx[sb + p];
-            if (k != va) tri += insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 2u);
+            const int m = a.colidx[sb + p];
+            uint32_t v;
+            const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
+            if (h >= 0) {
+                atomicOr(&tab[h], 2u << 30);
+                ++tri;
+            }
         }
         tri = warp_sum(tri);
         if (CTA_TEAM) {
@@ -360,13 +457,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
         // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
         int sqL = 0, gL = 0, sqS = 0, gS = 0;
         if (CTA_TEAM) {
-            while (true) {       // warps pull chunks of 32 heads
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_chunk, 1);
-                c = __shfl_sync(FULL, c, 0);
-                if (c * 32 >= db) break;
-                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c * 32, st, lane, sqL, gL);
-            }
+            scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, va, st, s_warp_tot, sqL, gL);
             sqL = warp_sum(sqL);
             gL = warp_max(gL);
             if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
@@ -374,7 +465,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
             sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
         } else {
             for (int c0 = 0; c0 < db; c0 += 32)
-                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, st, lane, sqL, gL);
+                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, va, st, lane, sqL, gL);
             sqL = warp_sum(sqL);
             gL = warp_max(gL);
             __syncwarp();
@@ -403,11 +494,22 @@ paper_edge_kernel(PaperArgs a, int cls) {
             a.out_tri[t] = tri;
             a.out_sq_i[t] = sq_i;
             a.out_sq_j[t] = sq_j;
-            a.out_gamma[t] = gamma;
-            a.out_bfc[t] = paper_value(di, dj, tri, sq_i, sq_j, gamma);
+            a.out_gamma[t] = gamma;      // the fp64 value is computed by paper_value_kernel (one thread per edge)
         }
         team_sync<CTA_TEAM>();  // table / s_red reuse
     }
+}
+
+// bfc_naive.py:31-32 / :39-40 for every edge of the call, one thread per edge: the eight fp64 divisions would
+// otherwise run on one lane of the edge's team.
+__global__ void paper_value_kernel(PaperArgs a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const int64_t e = a.e_first + t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+    if (min(di, dj) <= 1) return;      // written by classify_kernel: the int 0 of bfc_naive.py:18-19
+    a.out_bfc[t] = paper_value(di, dj, a.out_tri[t], a.out_sq_i[t], a.out_sq_j[t], a.out_gamma[t]);
 }
 
 }  // namespace dcr
@@ -438,7 +540,7 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.gslots = 0;
     L.g_ctas = 0;
     L.gtables = off;
-    if ((int64_t)max_degree * 4 > CTA_SLOTS) {  // some edge may need a table beyond shared memory
+    if (max_degree > CLASS_DA[2]) {  // some edge may need a table beyond shared memory (or 32-bit slot counters)
         L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
         L.g_ctas = sm_count();
         off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
@@ -490,34 +592,34 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
 
     const int sms = sm_count();
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
-    // heavy classes first: they own the long tail
+    // heavy classes first: they own the long tail.  Persistent grids = SM count x resident CTAs per SM.
+    static bool attr_done = false;
+    constexpr int big_stream = 3 * 4 * BIG_THREADS + 8, mid_stream = 3 * 4 * MID_THREADS + 8;
+    const int smem_x = big_stream * (int)sizeof(int);
+    const int smem_big = (big_stream + BIG_SLOTS + BIG_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_mid = (mid_stream + MID_SLOTS + MID_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_warp = WARP_TEAM_WARPS * (STREAM_INTS + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);
+    if (!attr_done) {
+        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big));
+        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<MID_THREADS, MID_SLOTS, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid));
+        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<32, WARP_SLOTS, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+        attr_done = true;
+    }
     if (L.gslots) {
-        const int smem = (CTA_THREADS / 32) * STREAM_INTS * (int)sizeof(int);
-        paper_edge_kernel<true, true><<<L.g_ctas, CTA_THREADS, smem, st>>>(a, 2);
+        paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, st>>>(a, 3);
         DCR_LAUNCH_CHECK();
     }
-    {
-        static bool attr_done = false;
-        const int smem = ((CTA_THREADS / 32) * STREAM_INTS + CTA_SLOTS + CTA_SLOTS / 2) * (int)sizeof(uint32_t);
-        if (!attr_done) {
-            DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<true, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_done = true;
-        }
-        paper_edge_kernel<true, false><<<sms, CTA_THREADS, smem, st>>>(a, 1);
-        DCR_LAUNCH_CHECK();
-    }
-    {
-        static bool attr_done = false;
-        const int smem = WARP_TEAM_WARPS * (STREAM_INTS + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);  // 51 KB
-        if (!attr_done) {
-            DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<false, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_done = true;
-        }
-        paper_edge_kernel<false, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem, st>>>(a, 0);
-        DCR_LAUNCH_CHECK();
-    }
+    paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false><<<sms, BIG_THREADS, smem_big, st>>>(a, 2);
+    DCR_LAUNCH_CHECK();
+    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * 4, MID_THREADS, smem_mid, st>>>(a, 1);
+    DCR_LAUNCH_CHECK();
+    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem_warp, st>>>(a, 0);
+    DCR_LAUNCH_CHECK();
+    paper_value_kernel<<<tb, 256, 0, st>>>(a);
+    DCR_LAUNCH_CHECK();
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
     return 0;
 }
