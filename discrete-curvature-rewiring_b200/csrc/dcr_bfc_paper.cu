@@ -39,23 +39,28 @@ constexpr uint32_t KEYMASK = 0x3fffffffu;
 //   class 2  d_a <= 16384  512-thread CTA team,  32768-slot table         (load factor <= 1/2), 1 CTA per SM
 //   class 3  larger        512-thread CTA team,  table in global memory (L2)
 constexpr int N_CLASSES = 4;
-constexpr int CLASS_DA[3] = {128, 1024, 16384};
+constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
 constexpr int WARP_SLOTS = 1024;
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
 constexpr int MID_SLOTS = 8192, MID_THREADS = 128;
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 512;
 constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
 constexpr int BUCKETS_PER_CLASS = 48;
-constexpr int N_BUCKETS = N_CLASSES * BUCKETS_PER_CLASS;
 constexpr int UNROLL = 4;
 
+// Ordering of the work.  Class 0 (warp teams): bucketed by log2(work), heavy first.  Classes 1-3 (CTA teams):
+// grouped by the tested endpoint va (counting sort over vertex ids), so that a CTA meets runs of edges with the
+// same va and re-uses the hash table of N(va) instead of rebuilding it per edge.
+constexpr int BUCKET_TRIVIAL = 255, BUCKET_GROUPED = 200, BUCKET_EXCEPTION = 204;
 struct PaperPlan {           // lives at the head of the scratch buffer
-    unsigned int hist[N_BUCKETS];
-    unsigned int cursor[N_BUCKETS];
-    unsigned int bucket_off[N_BUCKETS + 1];
+    unsigned int hist[BUCKETS_PER_CLASS];        // class-0 buckets
+    unsigned int cursor[BUCKETS_PER_CLASS];
+    unsigned int bucket_off[BUCKETS_PER_CLASS + 1];
+    unsigned int grouped[N_CLASSES + 1];         // [c] = #edges of class c (1..3) grouped by va, [4] = exceptions
+    unsigned int exc_cursor;
     unsigned int class_begin[N_CLASSES + 1];
-    unsigned int next[N_CLASSES];      // work-stealing counters
-    unsigned int pad[3];
+    unsigned int next[N_CLASSES];                // work-stealing counters
+    unsigned int pad[2];
 };
 
 struct PaperArgs {
@@ -72,7 +77,10 @@ struct PaperArgs {
     PaperPlan* plan;
     const int64_t* node_s;
     uint8_t* bucket;       // [count]
-    uint32_t* order;       // [count] local indices t grouped by bucket
+    uint32_t* order;       // [count] local indices t: class 0 by bucket, classes 1-3 by tested endpoint
+    uint32_t* va_cnt;      // [n] #grouped edges whose tested endpoint is v; after the scan: first position in `order`
+    uint32_t* va_cur;      // [n] fill cursors
+    int n;
     uint32_t* gtables;     // class-2 tables in global memory, gslots per CTA
     uint32_t gslots;
 };
@@ -147,54 +155,131 @@ __global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t*
     if (lane == 0) node_s[v] = s;
 }
 
-__global__ void classify_kernel(PaperArgs a) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const int64_t e = a.e_first + t * a.e_stride;
-    const int i = a.esrc[e], j = a.edst[e];
-    const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
-    if (min(di, dj) <= 1) {  // bfc_naive.py:18-19: deg_min == 1 -> 0 (no triangle is possible either)
-        a.out_tri[t] = 0; a.out_sq_i[t] = 0; a.out_sq_j[t] = 0; a.out_gamma[t] = 0; a.out_bfc[t] = 0.0;
-        a.bucket[t] = 255;
-        return;
-    }
-    const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
-    const long long work = min(ca, cb) + 4LL * (di + dj);
-    const int da = cb < ca ? dj : di;                                  // degree of the tested endpoint (see kernel)
-    const int db = cb < ca ? di : dj;                                  // degree of the streamed endpoint
-    int cls = da <= CLASS_DA[0] ? 0 : (da <= CLASS_DA[1] ? 1 : (da <= CLASS_DA[2] ? 2 : 3));
-    if (db > 65535) cls = 3;     // the 16-bit slot counters of the shared-memory tables count up to d_b lists
-    const int lg = 63 - __clzll(work | 1);
-    const int b = cls * BUCKETS_PER_CLASS + (BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1));  // heavy first
-    a.bucket[t] = (uint8_t)b;
-    atomicAdd(&a.plan->hist[b], 1u);
+__device__ __forceinline__ int class_of_degree(int da) {
+    return da <= CLASS_DA0 ? 0 : (da <= CLASS_DA1 ? 1 : (da <= CLASS_DA2 ? 2 : 3));
 }
 
-__global__ void bucket_scan_kernel(PaperPlan* plan) {
-    if (threadIdx.x == 0) {
-        unsigned int acc = 0;
-        for (int b = 0; b < N_BUCKETS; ++b) {
-            if (b % BUCKETS_PER_CLASS == 0) plan->class_begin[b / BUCKETS_PER_CLASS] = acc;
-            plan->bucket_off[b] = acc;
-            acc += plan->hist[b];
+__global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
+    __shared__ unsigned int s_hist[BUCKETS_PER_CLASS];
+    __shared__ unsigned int s_grp[N_CLASSES + 1];
+    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x) s_hist[b] = 0;
+    if (threadIdx.x <= N_CLASSES) s_grp[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.count) {
+        const int64_t e = a.e_first + t * a.e_stride;
+        const int i = a.esrc[e], j = a.edst[e];
+        const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+        if (min(di, dj) <= 1) {  // bfc_naive.py:18-19: deg_min == 1 -> 0 (no triangle is possible either)
+            a.out_tri[t] = 0; a.out_sq_i[t] = 0; a.out_sq_j[t] = 0; a.out_gamma[t] = 0; a.out_bfc[t] = 0.0;
+            a.bucket[t] = BUCKET_TRIVIAL;
+        } else {
+            const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
+            const bool swapped = cb < ca;
+            const int va = swapped ? j : i;                                    // tested endpoint (see the edge kernel)
+            const int da = swapped ? dj : di, db = swapped ? di : dj;
+            const int cls = class_of_degree(da);
+            if (db > 65535) {            // the 16-bit slot counters of the shared-memory tables count up to d_b lists
+                a.bucket[t] = BUCKET_EXCEPTION;
+                atomicAdd(&s_grp[N_CLASSES], 1u);
+            } else if (cls == 0) {
+                const long long work = min(ca, cb) + 4LL * (di + dj);
+                const int lg = 63 - __clzll(work | 1);
+                const int b = BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1);   // heavy first
+                a.bucket[t] = (uint8_t)b;
+                atomicAdd(&s_hist[b], 1u);
+            } else {
+                a.bucket[t] = (uint8_t)(BUCKET_GROUPED + cls);
+                atomicAdd(&s_grp[cls], 1u);
+                atomicAdd(&a.va_cnt[va], 1u);
+            }
         }
-        plan->bucket_off[N_BUCKETS] = acc;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&a.plan->hist[b], s_hist[b]);
+    if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
+}
+
+// One CTA: bucket offsets of class 0, class ranges, and for classes 1-3 the exclusive scan of va_cnt over the
+// vertices of that class (class is a function of the vertex degree), which turns va_cnt into first positions.
+constexpr int PLAN_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(PLAN_SCAN_THREADS) plan_scan_kernel(PaperArgs a) {
+    __shared__ unsigned int s_part[PLAN_SCAN_THREADS / 32];
+    __shared__ unsigned int s_total;
+    PaperPlan* plan = a.plan;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        unsigned int acc = 0;
+        plan->class_begin[0] = 0;
+        for (int b = 0; b < BUCKETS_PER_CLASS; ++b) { plan->bucket_off[b] = acc; acc += plan->hist[b]; }
+        plan->bucket_off[BUCKETS_PER_CLASS] = acc;
+        for (int c = 1; c < N_CLASSES; ++c) { plan->class_begin[c] = acc; acc += plan->grouped[c]; }
+        acc += plan->grouped[N_CLASSES];               // exceptions close class 3
         plan->class_begin[N_CLASSES] = acc;
     }
+    __syncthreads();
+    const int n = a.n;
+    const int per = (n + PLAN_SCAN_THREADS - 1) / PLAN_SCAN_THREADS;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    for (int c = 1; c < N_CLASSES; ++c) {
+        if (plan->grouped[c] == 0) continue;           // block-uniform
+        unsigned int sum = 0;
+        for (int v = lo; v < hi; ++v)
+            if (class_of_degree(a.rowptr[v + 1] - a.rowptr[v]) == c) sum += a.va_cnt[v];
+        unsigned int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        unsigned int off = plan->class_begin[c] + inc - sum;
+        for (int w = 0; w < warp; ++w) off += s_part[w];
+        for (int v = lo; v < hi; ++v)
+            if (class_of_degree(a.rowptr[v + 1] - a.rowptr[v]) == c) {
+                const unsigned int cnt = a.va_cnt[v];
+                a.va_cnt[v] = off;
+                off += cnt;
+            }
+        __syncthreads();
+    }
+    (void)s_total;
 }
 
-__global__ void order_kernel(PaperArgs a) {
+__global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
+    // class 0, block-aggregated: one global atomic per (block, bucket) reserves a range, ranks come from shared memory
+    __shared__ unsigned int s_cnt[BUCKETS_PER_CLASS];
+    __shared__ unsigned int s_base[BUCKETS_PER_CLASS];
+    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x) s_cnt[b] = 0;
+    __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const int b = a.bucket[t];
-    if (b == 255) return;
-    const unsigned int pos = a.plan->bucket_off[b] + atomicAdd(&a.plan->cursor[b], 1u);
-    a.order[pos] = (uint32_t)t;
+    int b = BUCKET_TRIVIAL;
+    unsigned int r = 0;
+    if (t < a.count) {
+        b = a.bucket[t];
+        if (b < BUCKETS_PER_CLASS) {
+            r = atomicAdd(&s_cnt[b], 1u);
+        } else if (b == BUCKET_EXCEPTION) {
+            const unsigned int pos = a.plan->class_begin[N_CLASSES] - a.plan->grouped[N_CLASSES] +
+                                     atomicAdd(&a.plan->exc_cursor, 1u);
+            a.order[pos] = (uint32_t)t;
+        } else if (b != BUCKET_TRIVIAL) {          // grouped by tested endpoint
+            const int64_t e = a.e_first + t * a.e_stride;
+            const int i = a.esrc[e], j = a.edst[e];
+            const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+            const int va = (a.node_s[i] - dj) < (a.node_s[j] - di) ? j : i;
+            a.order[a.va_cnt[va] + atomicAdd(&a.va_cur[va], 1u)] = (uint32_t)t;
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < BUCKETS_PER_CLASS; q += blockDim.x)
+        if (s_cnt[q]) s_base[q] = a.plan->bucket_off[q] + atomicAdd(&a.plan->cursor[q], s_cnt[q]);
+    __syncthreads();
+    if (b < BUCKETS_PER_CLASS) a.order[s_base[b] + r] = (uint32_t)t;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// the edge kernel.  CTA_TEAM = false: each warp is a team with a private table slice; true: the CTA is the team.
-// ------------------------------------------------------------------------------------------------------------
 template <bool CTA_TEAM>
 __device__ __forceinline__ void team_sync() {
     if (CTA_TEAM) __syncthreads(); else __syncwarp();
@@ -217,11 +302,12 @@ __device__ __forceinline__ uint32_t slot_count_get(const uint32_t* cnt, uint32_t
 // The flat stream: `pre` = exclusive prefix sums of the list lengths (pre[l+1]-pre[l] = length of list l), `beg` =
 // first CSR slot of each list, `lcnt` = per-list match counters, all in shared memory.  This warp handles the flat
 // elements [f_begin, f_end); lane f%32 takes element f.  `l` = a list index with pre[l] <= f_begin.
-// A match (key present with tag 1) bumps the list's counter and the matched key's slot counter.
+// A match (key present with tag 1, and not vb itself — the table holds all of N(va)) bumps the list's counter and
+// the matched key's slot counter.
 template <bool GLOBAL>
 __device__ __forceinline__ void flat_scan(const int32_t* __restrict__ colidx, const uint32_t* tab, uint32_t* cnt,
                                           uint32_t mask, int shift, const int* pre, const int* beg, int* lcnt, int l,
-                                          int f_begin, int f_end, int lane) {
+                                          int f_begin, int f_end, int lane, int vb) {
     for (int f0 = f_begin + lane; f0 < f_end; f0 += 32 * UNROLL) {
         int k[UNROLL], lu[UNROLL];
 #pragma unroll
@@ -240,7 +326,7 @@ __device__ __forceinline__ void flat_scan(const int32_t* __restrict__ colidx, co
             if (k[u] >= 0) {
                 uint32_t v;
                 const int h = probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)k[u], v);
-                if (h >= 0 && (v >> 30) == 1u) {
+                if (h >= 0 && (v >> 30) == 1u && k[u] != vb) {
                     atomicAdd(&lcnt[lu[u]], 1);
                     slot_count_add<GLOBAL>(cnt, h);
                 }
@@ -266,8 +352,8 @@ __device__ __forceinline__ void pure_head(const PaperArgs& a, const uint32_t* ta
 // state.  Accumulates (#lists with a match, largest per-list count) per lane.
 template <bool GLOBAL>
 __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
-                                           int shift, int list_begin, int list_len, int c0, int va, int* st, int lane,
-                                           int& sq, int& gmax) {
+                                           int shift, int list_begin, int list_len, int c0, int va, int vb, int* st,
+                                           int lane, int& sq, int& gmax) {
     int* pre = st;            // [33]
     int* beg = st + 33;       // [32]
     int* lcnt = st + 65;      // [32]
@@ -287,7 +373,7 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
     beg[lane] = mb;
     lcnt[lane] = 0;
     __syncwarp();
-    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, 0, 0, total, lane);
+    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, 0, 0, total, lane, vb);
     __syncwarp();
     const int c = lcnt[lane];
     sq += c > 0;
@@ -300,8 +386,8 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
 // list next to twenty short ones does not serialise).  `cs` = pre[HEADS+1] | beg[HEADS] | cnt[HEADS].
 template <int THREADS, bool GLOBAL>
 __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask, int shift,
-                                         int list_begin, int list_len, int va, int* cs, int* s_warp_tot, int& sq,
-                                         int& gmax) {
+                                         int list_begin, int list_len, int va, int vb, int* cs, int* s_warp_tot,
+                                         int& sq, int& gmax) {
     constexpr int HPT = 4;                        // heads per thread
     constexpr int HEADS = HPT * THREADS;
     constexpr int NW = THREADS / 32;
@@ -349,7 +435,7 @@ __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab
                     const int mid = (lo + hi) >> 1;
                     if (pre[mid + 1] <= f_begin) lo = mid + 1; else hi = mid;
                 }
-                flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, lo, f_begin, f_end, lane);
+                flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, lo, f_begin, f_end, lane, vb);
             }
             __syncthreads();
             for (int t = tid; t < nh; t += THREADS) {
@@ -396,107 +482,135 @@ paper_edge_kernel(PaperArgs a, int cls) {
     const unsigned int cbeg = a.plan->class_begin[cls];
     const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
     const uint32_t max_slots = GLOBAL_TABLE ? a.gslots : (uint32_t)MAX_SLOTS;
+    constexpr unsigned int GRAB = CTA_TEAM ? 16u : 1u;   // edges per work-stealing step (a run of one va, usually)
 
+    int cur_va = -1;                 // vertex whose neighbour set is in the table (CTA teams re-use it across edges)
+    uint32_t slots = 0, mask = 0;
+    int shift = 0;
     while (true) {
-        unsigned int idx;
+        unsigned int idx0;
         if (CTA_TEAM) {
-            if (threadIdx.x == 0) {
-                s_idx = atomicAdd(&a.plan->next[cls], 1u);
-                s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
-            }
+            if (threadIdx.x == 0) s_idx = atomicAdd(&a.plan->next[cls], GRAB);
             __syncthreads();
-            idx = s_idx;
+            idx0 = s_idx;
         } else {
-            idx = 0;
-            if (lane == 0) idx = atomicAdd(&a.plan->next[cls], 1u);
-            idx = __shfl_sync(FULL, idx, 0);
+            idx0 = 0;
+            if (lane == 0) idx0 = atomicAdd(&a.plan->next[cls], GRAB);
+            idx0 = __shfl_sync(FULL, idx0, 0);
         }
-        if (idx >= cnum) break;
-        const uint32_t t = a.order[cbeg + idx];
-        const int64_t e = a.e_first + (int64_t)t * a.e_stride;
-        const int i = a.esrc[e], j = a.edst[e];
-        const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
-        // (va, vb): vb = endpoint whose 2-hop lists are streamed (the cheaper side), va = the tested side
-        const bool swapped = (a.node_s[i] - dj) < (a.node_s[j] - di);
-        const int va = swapped ? j : i, vb = swapped ? i : j;
-        const int sa = a.rowptr[va], da = swapped ? dj : di;
-        const int sb = a.rowptr[vb], db = swapped ? di : dj;
-
-        // table of N(va) \ {vb}: power of two >= 8*d_a (load factor <= 1/8 keeps probe chains short and uniform
-        // across the lanes of a warp), capped by the class's table
-        const int lg = min(32 - __clz(max(8 * da, 64) - 1), 31 - __clz(max_slots));
-        const uint32_t slots = 1u << lg;
-        const uint32_t mask = slots - 1;
-        const int shift = 32 - lg;
-
-        for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
-        for (uint32_t s = team_tid; s < (GLOBAL_TABLE ? slots : slots / 2); s += team_threads) cnt[s] = 0u;
-        team_sync<CTA_TEAM>();
-        for (int p = team_tid; p < da; p += team_threads) {
-            const int k = a.colidx[sa + p];
-            if (k != vb) insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, 1u);
-        }
-        team_sync<CTA_TEAM>();
-        // common neighbours: heads of N(vb) found in the table become tag 3 (never a match, never a pure head)
-        int tri = 0;
-        for (int p = team_tid; p < db; p += team_threads) {
-            const int m = a.colidx[sb + p];
-            uint32_t v;
-            const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
-            if (h >= 0) {
-                atomicOr(&tab[h], 2u << 30);
-                ++tri;
+        if (idx0 >= cnum) break;
+        for (unsigned int q = 0; q < GRAB && idx0 + q < cnum; ++q) {
+            if (CTA_TEAM) {
+                if (threadIdx.x == 0) s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
+                __syncthreads();
             }
-        }
-        tri = warp_sum(tri);
-        if (CTA_TEAM) {
-            if (lane == 0 && tri) atomicAdd(&s_red[0], tri);
-        }
-        team_sync<CTA_TEAM>();
+            const uint32_t t = a.order[cbeg + idx0 + q];
+            const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+            const int i = a.esrc[e], j = a.edst[e];
+            const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+            // (va, vb): vb = endpoint whose 2-hop lists are streamed (the cheaper side), va = the tested side
+            const bool swapped = (a.node_s[i] - dj) < (a.node_s[j] - di);
+            const int va = swapped ? j : i, vb = swapped ? i : j;
+            const int sa = a.rowptr[va], da = swapped ? dj : di;
+            const int sb = a.rowptr[vb], db = swapped ? di : dj;
 
-        // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
-        int sqL = 0, gL = 0, sqS = 0, gS = 0;
-        if (CTA_TEAM) {
-            scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, va, st, s_warp_tot, sqL, gL);
-            sqL = warp_sum(sqL);
-            gL = warp_max(gL);
-            if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
-            __syncthreads();
-            sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
-        } else {
-            for (int c0 = 0; c0 < db; c0 += 32)
-                scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, va, st, lane, sqL, gL);
-            sqL = warp_sum(sqL);
-            gL = warp_max(gL);
-            __syncwarp();
-        }
-        // the sweep: slot counters of the tag-1 keys -> squares at va (empty iff the scan found nothing)
-        if (sqL > 0) {
-            for (uint32_t s = team_tid; s < slots; s += team_threads) {
-                const uint32_t v = GLOBAL_TABLE ? __ldcg(tab + s) : tab[s];
-                if ((v >> 30) == 1u) {
-                    const int c = (int)slot_count_get<GLOBAL_TABLE>(cnt, s);
-                    sqS += c > 0;
-                    gS = max(gS, c);
+            if (!CTA_TEAM || va != cur_va) {
+                // table of N(va), every key with tag 1: power of two >= 8*d_a (load factor <= 1/8 keeps probe
+                // chains short and uniform across the lanes of a warp), capped by the class's table
+                const int lg = min(32 - __clz(max(8 * da, 64) - 1), 31 - __clz(max_slots));
+                slots = 1u << lg;
+                mask = slots - 1;
+                shift = 32 - lg;
+                for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
+                for (uint32_t s = team_tid; s < (GLOBAL_TABLE ? slots : slots / 2); s += team_threads) cnt[s] = 0u;
+                team_sync<CTA_TEAM>();
+                for (int p = team_tid; p < da; p += team_threads)
+                    insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)a.colidx[sa + p], 1u);
+                team_sync<CTA_TEAM>();
+                cur_va = va;
+            }
+            // common neighbours: heads of N(vb) found in the table get bit 31 (tag 3: never a match, never a head)
+            int tri = 0;
+            for (int p = team_tid; p < db; p += team_threads) {
+                const int m = a.colidx[sb + p];
+                uint32_t v;
+                const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
+                if (h >= 0) {
+                    atomicOr(&tab[h], 2u << 30);
+                    ++tri;
                 }
             }
-            sqS = warp_sum(sqS);
-            gS = warp_max(gS);
+            tri = warp_sum(tri);
             if (CTA_TEAM) {
-                if (lane == 0 && sqS) { atomicAdd(&s_red[3], sqS); atomicMax(&s_red[4], gS); }
-                __syncthreads();
-                sqS = s_red[3]; gS = s_red[4];
+                if (lane == 0 && tri) atomicAdd(&s_red[0], tri);
             }
+            team_sync<CTA_TEAM>();
+
+            // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
+            int sqL = 0, gL = 0, sqS = 0, gS = 0;
+            if (CTA_TEAM) {
+                scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, va, vb, st, s_warp_tot, sqL, gL);
+                sqL = warp_sum(sqL);
+                gL = warp_max(gL);
+                if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
+                __syncthreads();
+                sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
+            } else {
+                for (int c0 = 0; c0 < db; c0 += 32)
+                    scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, va, vb, st, lane, sqL, gL);
+                sqL = warp_sum(sqL);
+                gL = warp_max(gL);
+                __syncwarp();
+            }
+            // the collect: slot counters of the pure neighbours of va -> squares at va (empty iff the scan found
+            // nothing).  Walks N(va) (d_a probes) instead of sweeping the table; CTA teams zero the counters they
+            // read so the table is clean for the next edge of the same va.
+            if (sqL > 0) {
+                for (int p = team_tid; p < da; p += team_threads) {
+                    const int k = a.colidx[sa + p];
+                    uint32_t v;
+                    const int h = probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)k, v);
+                    if (h >= 0 && (v >> 30) == 1u) {
+                        const int c = (int)slot_count_get<GLOBAL_TABLE>(cnt, (uint32_t)h);
+                        if (c > 0) {
+                            ++sqS;
+                            gS = max(gS, c);
+                            if (CTA_TEAM) {
+                                if (GLOBAL_TABLE) cnt[h] = 0u;
+                                else atomicAnd(&cnt[h >> 1], (h & 1) ? 0x0000ffffu : 0xffff0000u);
+                            }
+                        }
+                    }
+                }
+                sqS = warp_sum(sqS);
+                gS = warp_max(gS);
+                if (CTA_TEAM) {
+                    if (lane == 0 && sqS) { atomicAdd(&s_red[3], sqS); atomicMax(&s_red[4], gS); }
+                    __syncthreads();
+                    sqS = s_red[3]; gS = s_red[4];
+                }
+            }
+            if (team_tid == 0) {
+                const int sq_i = swapped ? sqL : sqS, sq_j = swapped ? sqS : sqL;
+                const int gamma = (sqL > 0 && sqS > 0) ? max(gL, gS) : 0;
+                a.out_tri[t] = tri;
+                a.out_sq_i[t] = sq_i;
+                a.out_sq_j[t] = sq_j;
+                a.out_gamma[t] = gamma;      // the fp64 value is computed by paper_value_kernel (one thread per edge)
+            }
+            if (CTA_TEAM) {
+                // undo the common-neighbour marks so the table is N(va) with tag 1 again
+                if (tri > 0) {
+                    for (int p = team_tid; p < db; p += team_threads) {
+                        const int m = a.colidx[sb + p];
+                        uint32_t v;
+                        const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
+                        if (h >= 0) atomicAnd(&tab[h], 0x7fffffffu);
+                    }
+                }
+            }
+            team_sync<CTA_TEAM>();  // table / s_red reuse
         }
-        if (team_tid == 0) {
-            const int sq_i = swapped ? sqL : sqS, sq_j = swapped ? sqS : sqL;
-            const int gamma = (sqL > 0 && sqS > 0) ? max(gL, gS) : 0;
-            a.out_tri[t] = tri;
-            a.out_sq_i[t] = sq_i;
-            a.out_sq_j[t] = sq_j;
-            a.out_gamma[t] = gamma;      // the fp64 value is computed by paper_value_kernel (one thread per edge)
-        }
-        team_sync<CTA_TEAM>();  // table / s_red reuse
     }
 }
 
@@ -525,7 +639,7 @@ static inline uint32_t next_pow2_u32(uint64_t v) {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct ScratchLayout {
-    size_t plan, node_s, bucket, order, gtables, total;
+    size_t plan, node_s, bucket, order, va_cnt, va_cur, gtables, total;
     uint32_t gslots;
     int g_ctas;
 };
@@ -537,10 +651,12 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.node_s = off; off = align_up(off + (size_t)n * sizeof(int64_t), 256);
     L.bucket = off; off = align_up(off + (size_t)count, 256);
     L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
+    L.va_cnt = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
+    L.va_cur = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
     L.gslots = 0;
     L.g_ctas = 0;
     L.gtables = off;
-    if (max_degree > CLASS_DA[2]) {  // some edge may need a table beyond shared memory (or 32-bit slot counters)
+    if (max_degree > CLASS_DA2) {  // some edge may need a table beyond shared memory (or 32-bit slot counters)
         L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
         L.g_ctas = sm_count();
         off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
@@ -576,16 +692,20 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.node_s = node_s;
     a.bucket = (uint8_t*)(base + L.bucket);
     a.order = (uint32_t*)(base + L.order);
+    a.va_cnt = (uint32_t*)(base + L.va_cnt);
+    a.va_cur = (uint32_t*)(base + L.va_cur);
+    a.n = n;
     a.gtables = (uint32_t*)(base + L.gtables);
     a.gslots = L.gslots;
 
     DCR_CUDA(cudaMemsetAsync(a.plan, 0, sizeof(PaperPlan), st));
+    DCR_CUDA(cudaMemsetAsync(a.va_cnt, 0, (L.va_cur - L.va_cnt) + (size_t)n * sizeof(uint32_t), st));   // va_cnt + va_cur
     node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s);
     DCR_LAUNCH_CHECK();
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
-    bucket_scan_kernel<<<1, 32, 0, st>>>(a.plan);
+    plan_scan_kernel<<<1, PLAN_SCAN_THREADS, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     order_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();

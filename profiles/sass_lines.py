@@ -73,11 +73,16 @@ def main():
     table = {demangle(k): v for k, v in line_table(so).items()}
     def norm(s):
         s = s.replace("(bool)1", "true").replace("(bool)0", "false")
+        s = re.sub(r"\((?:int|unsigned int|long|unsigned long)\)", "", s)
         s = re.sub(r"^void\s+", "", s.strip())
         return re.sub(r"\s|dcr::", "", s)
 
     src_cache = {}
+    seen = set()
     for b in ncu_source(report):
+        if (b["name"], len(b["rows"])) in seen:      # ncu lists every launch; identical code -> print once
+            continue
+        seen.add((b["name"], len(b["rows"])))
         if want and want not in b["name"]:
             continue
         key = [k for k in table if norm(k).startswith(norm(b["name"]).split("(")[0]) and
