@@ -35,15 +35,16 @@ constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
 // Edge classes by the degree d_a of the TESTED endpoint (the one whose neighbour set goes into the hash table):
 //   class 0  d_a <= 128    warp team,            1024-slot table per warp (load factor <= 1/8)
-//   class 1  d_a <= 1024   128-thread CTA team,  8192-slot table          (load factor <= 1/8), 4 CTAs per SM
-//   class 2  d_a <= 16384  512-thread CTA team,  32768-slot table         (load factor <= 1/2), 1 CTA per SM
-//   class 3  larger        512-thread CTA team,  table in global memory (L2)
+//   class 1  d_a <= 1024   128-thread CTA team,  4096-slot table          (load factor <= 1/4), 7 CTAs per SM
+//   class 2  d_a <= 16384  1024-thread CTA team, 32768-slot table         (load factor <= 1/2), 1 CTA per SM
+//   class 3  larger        1024-thread CTA team, table in global memory (L2)
 constexpr int N_CLASSES = 4;
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
 constexpr int WARP_SLOTS = 1024;
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int MID_SLOTS = 8192, MID_THREADS = 128;
-constexpr int BIG_SLOTS = 32768, BIG_THREADS = 512;
+constexpr int MID_SLOTS = 4096, MID_THREADS = 128, MID_CTAS_PER_SM = 7;
+constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
+__host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 2 : 4; }   // CTA stream state must fit beside the table
 constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
 constexpr int BUCKETS_PER_CLASS = 48;
 constexpr int UNROLL = 4;
@@ -381,14 +382,14 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
     __syncwarp();
 }
 
-// CTA team: up to HEADS = 4*THREADS heads per round; the CTA-wide flat stream is cut into equal contiguous ranges,
+// CTA team: up to HEADS = heads_per_thread*THREADS heads per round; the CTA-wide flat stream is cut into equal contiguous ranges,
 // one per warp, so every warp streams the same number of elements whatever the list-length distribution (a hub's
 // list next to twenty short ones does not serialise).  `cs` = pre[HEADS+1] | beg[HEADS] | cnt[HEADS].
 template <int THREADS, bool GLOBAL>
 __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask, int shift,
                                          int list_begin, int list_len, int va, int vb, int* cs, int* s_warp_tot,
                                          int& sq, int& gmax) {
-    constexpr int HPT = 4;                        // heads per thread
+    constexpr int HPT = heads_per_thread(THREADS);   // heads per thread
     constexpr int HEADS = HPT * THREADS;
     constexpr int NW = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -450,11 +451,12 @@ __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab
 
 // TEAM = threads per team (32 = warp team, several teams per CTA; otherwise the CTA is the team).
 template <int TEAM, int MAX_SLOTS, bool GLOBAL_TABLE>
-__global__ void __launch_bounds__(TEAM > 32 ? TEAM : WARP_TEAM_WARPS * 32, TEAM == BIG_THREADS ? 1 : 4)
+__global__ void __launch_bounds__(TEAM > 32 ? TEAM : WARP_TEAM_WARPS * 32,
+                                  TEAM == BIG_THREADS ? 1 : (TEAM == MID_THREADS ? MID_CTAS_PER_SM : 4))
 paper_edge_kernel(PaperArgs a, int cls) {
     constexpr bool CTA_TEAM = TEAM > 32;
     constexpr int NWARPS = CTA_TEAM ? TEAM / 32 : WARP_TEAM_WARPS;
-    constexpr int CTA_STREAM = 3 * 4 * TEAM + 8;
+    constexpr int CTA_STREAM = 3 * heads_per_thread(TEAM) * TEAM + 8;
     extern __shared__ uint32_t smem_dyn[];
     __shared__ unsigned int s_idx;
     __shared__ int s_warp_tot[NWARPS];
@@ -714,7 +716,8 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
     // heavy classes first: they own the long tail.  Persistent grids = SM count x resident CTAs per SM.
     static bool attr_done = false;
-    constexpr int big_stream = 3 * 4 * BIG_THREADS + 8, mid_stream = 3 * 4 * MID_THREADS + 8;
+    constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
+    constexpr int mid_stream = 3 * heads_per_thread(MID_THREADS) * MID_THREADS + 8;
     const int smem_x = big_stream * (int)sizeof(int);
     const int smem_big = (big_stream + BIG_SLOTS + BIG_SLOTS / 2) * (int)sizeof(uint32_t);
     const int smem_mid = (mid_stream + MID_SLOTS + MID_SLOTS / 2) * (int)sizeof(uint32_t);
@@ -734,7 +737,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     }
     paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false><<<sms, BIG_THREADS, smem_big, st>>>(a, 2);
     DCR_LAUNCH_CHECK();
-    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * 4, MID_THREADS, smem_mid, st>>>(a, 1);
+    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * MID_CTAS_PER_SM, MID_THREADS, smem_mid, st>>>(a, 1);
     DCR_LAUNCH_CHECK();
     paper_edge_kernel<32, WARP_SLOTS, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem_warp, st>>>(a, 0);
     DCR_LAUNCH_CHECK();

@@ -250,3 +250,25 @@ def test_full_size_properties_squirrel_shape():
         f = bfc_edge_fields(adj, int(es[e]), int(ed[e]))
         assert (tri[e], sq_i[e], sq_j[e], gamma[e]) == f[2:6], e
         assert bfcv[e] == float(f[6])
+
+
+def test_sharded_path_single_process_matches_full():
+    """The N>1 code path (shared result block, gather buffer, unshard kernel) run as W emulated ranks on one GPU."""
+    import torch
+    from dcr import bfc
+    from dcr.dist import chunk_size
+    from dcr.synth import named_graph
+    ei, n = named_graph("cora")
+    csr = _csr(ei, n)
+    full = bfc.paper_flavour(csr)
+    E = full["count"]
+    for world in (2, 8):
+        chunk = chunk_size(E, world)
+        gathered = torch.zeros(world * chunk * 24, dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            ws = bfc.PaperWorkspace(csr, bfc.shard_count(E, r, world), chunk=chunk)
+            bfc.paper_flavour(csr, rank=r, world=world, ws=ws)
+            gathered[r * chunk * 24:(r + 1) * chunk * 24] = ws.block
+        out = bfc.unshard(gathered, world, chunk, E)
+        for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+            assert torch.equal(out[k], full[k]), (world, k)
