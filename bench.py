@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -256,6 +256,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on stdout; stdout carries one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     from dcr import bfc
@@ -369,7 +371,7 @@ def run_ours(args):
         ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
         checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
 
-    launches_per_step = 4 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + 1   # plan, edge classes, value, unshard
+    launches_per_step = 5 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + 1   # plan(5), edge classes, value, unshard
     line = {
         "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -404,13 +406,33 @@ def run_ours(args):
     if rank == 0 and not args.no_sdrf:
         line["sdrf"] = sdrf_bench(args, torch)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line: anything libraries print to fd 1 (e.g. NCCL's version banner) goes to
+    stderr instead; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

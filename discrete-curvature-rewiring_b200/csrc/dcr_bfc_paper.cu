@@ -59,6 +59,7 @@ struct PaperPlan {           // lives at the head of the scratch buffer
     unsigned int bucket_off[BUCKETS_PER_CLASS + 1];
     unsigned int grouped[N_CLASSES + 1];         // [c] = #edges of class c (1..3) grouped by va, [4] = exceptions
     unsigned int exc_cursor;
+    unsigned int group_cursor[N_CLASSES];        // range reservation inside classes 1-3
     unsigned int class_begin[N_CLASSES + 1];
     unsigned int next[N_CLASSES];                // work-stealing counters
     unsigned int pad[2];
@@ -202,15 +203,10 @@ __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
     if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
 }
 
-// One CTA: bucket offsets of class 0, class ranges, and for classes 1-3 the exclusive scan of va_cnt over the
-// vertices of that class (class is a function of the vertex degree), which turns va_cnt into first positions.
-constexpr int PLAN_SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(PLAN_SCAN_THREADS) plan_scan_kernel(PaperArgs a) {
-    __shared__ unsigned int s_part[PLAN_SCAN_THREADS / 32];
-    __shared__ unsigned int s_total;
+// Bucket offsets of class 0 and the class ranges (one thread: 48 + 4 values).
+__global__ void plan_ranges_kernel(PaperArgs a) {
     PaperPlan* plan = a.plan;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         unsigned int acc = 0;
         plan->class_begin[0] = 0;
         for (int b = 0; b < BUCKETS_PER_CLASS; ++b) { plan->bucket_off[b] = acc; acc += plan->hist[b]; }
@@ -219,34 +215,18 @@ __global__ void __launch_bounds__(PLAN_SCAN_THREADS) plan_scan_kernel(PaperArgs 
         acc += plan->grouped[N_CLASSES];               // exceptions close class 3
         plan->class_begin[N_CLASSES] = acc;
     }
-    __syncthreads();
-    const int n = a.n;
-    const int per = (n + PLAN_SCAN_THREADS - 1) / PLAN_SCAN_THREADS;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    for (int c = 1; c < N_CLASSES; ++c) {
-        if (plan->grouped[c] == 0) continue;           // block-uniform
-        unsigned int sum = 0;
-        for (int v = lo; v < hi; ++v)
-            if (class_of_degree(a.rowptr[v + 1] - a.rowptr[v]) == c) sum += a.va_cnt[v];
-        unsigned int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int up = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += up;
-        }
-        if (lane == 31) s_part[warp] = inc;
-        __syncthreads();
-        unsigned int off = plan->class_begin[c] + inc - sum;
-        for (int w = 0; w < warp; ++w) off += s_part[w];
-        for (int v = lo; v < hi; ++v)
-            if (class_of_degree(a.rowptr[v + 1] - a.rowptr[v]) == c) {
-                const unsigned int cnt = a.va_cnt[v];
-                a.va_cnt[v] = off;
-                off += cnt;
-            }
-        __syncthreads();
-    }
-    (void)s_total;
+}
+
+// Every vertex that is the tested endpoint of grouped edges reserves a contiguous range of `order` inside its
+// class (the class is a function of the vertex degree).  The order of the ranges is irrelevant — only contiguity
+// matters for the table reuse — so one atomicAdd per such vertex replaces a scan over all vertices.
+__global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.n) return;
+    const unsigned int c = a.va_cnt[v];
+    if (c == 0) return;
+    const int cls = class_of_degree(a.rowptr[v + 1] - a.rowptr[v]);
+    a.va_cnt[v] = a.plan->class_begin[cls] + atomicAdd(&a.plan->group_cursor[cls], c);
 }
 
 __global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
@@ -484,7 +464,8 @@ paper_edge_kernel(PaperArgs a, int cls) {
     const unsigned int cbeg = a.plan->class_begin[cls];
     const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
     const uint32_t max_slots = GLOBAL_TABLE ? a.gslots : (uint32_t)MAX_SLOTS;
-    constexpr unsigned int GRAB = CTA_TEAM ? 16u : 1u;   // edges per work-stealing step (a run of one va, usually)
+    // edges per work-stealing step: a run of one va, usually — but never so long that the CTAs run out of steps
+    const unsigned int GRAB = CTA_TEAM ? min(16u, max(1u, cnum / (gridDim.x * 8u))) : 1u;
 
     int cur_va = -1;                 // vertex whose neighbour set is in the table (CTA teams re-use it across edges)
     uint32_t slots = 0, mask = 0;
@@ -707,7 +688,9 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
-    plan_scan_kernel<<<1, PLAN_SCAN_THREADS, 0, st>>>(a);
+    plan_ranges_kernel<<<1, 32, 0, st>>>(a);
+    DCR_LAUNCH_CHECK();
+    plan_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     order_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
