@@ -1,0 +1,270 @@
+// dcr_tc.cu — dense-regime supports on the 5th-generation tensor cores: A2 = A·A with tcgen05 kind::i8.
+//
+// Takes over the `A2 = torch.matmul(A, A)` of the reference (curvature/bfc_cuda.py:53, :146) for graphs small and
+// dense enough that the product really is a dense contraction (N <= 32768: A as int8 is <= 1 GiB).  For a 0/1
+// symmetric adjacency A2[i,j] = |N(i) ∩ N(j)| is exact in int32.  The N x N product is NEVER materialised: the
+// epilogue of every 128x128 tile keeps only the entries that sit on an edge and writes them straight into the
+// CSR-ordered support array that dcr_bfc_cuda_flavour / dcr_post_delta / the SDRF state consume (same output as
+// dcr_bfc_support, which is the sparse route for the same numbers).
+//
+// Structure (one 128x128 output tile per CTA, K swept in 128-byte blocks):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d of the A-rows tile (128 x 128 B) and the "B" tile — by symmetry
+//                           also 128 rows of A, K-major — into a 4-stage 128B-swizzled shared-memory ring,
+//                           mbarrier complete_tx
+//   warp 1   MMA issuer     one elected thread: 4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32) per stage,
+//                           accumulators in TMEM (128 lanes x 128 columns of int32); tcgen05.commit frees the stage
+//   warps 2-5 epilogue      tcgen05.ld 32x32b.x32 (each warp its 32-lane quarter), then per row: walk the 128-byte
+//                           row segment of A and store acc[c] for every non-zero A[i, j] at its CSR position
+// Roofline: tensor-bound, 2·N_pad³ int8 ops.  Evidence: UTCIMMA / UTMALDG / LDTM in the SASS (cuobjdump), and
+// sm__pipe_tensor_cycles_active under ncu.
+#include <cuda.h>
+
+#include "dcr_common.cuh"
+
+namespace dcr {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 128;      // tile (int8 elements; BK bytes = one 128B swizzle row)
+constexpr int TC_STAGES = 4;
+constexpr int TC_UMMA_K = 32;                             // int8: 32 elements = 32 bytes per MMA
+constexpr int TC_THREADS = 192;                           // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_STAGE_BYTES = TC_BM * TC_BK;             // 16 KB per operand per stage
+constexpr int TC_SMEM_BYTES = 2 * TC_STAGES * TC_STAGE_BYTES + 1024;   // + alignment slack
+
+// ---- thin PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc), "r"(zero) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte offset = 8 rows x 128 B = 1024
+// >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @[4,6), a/b format INT8 = 1 @[7,10)/[10,13),
+// a/b K-major = 0 @15/@16, N>>3 @[17,23), M>>4 @[24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- set-up kernels ----------------------------------------------------------------------------------------
+// int8 image of the adjacency (zero-padded to n_pad) from the CSR, and per (row, 128-column block) the number of
+// the row's entries before that block (so an epilogue thread knows where its block's entries start in the CSR).
+__global__ void tc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n, int n_pad,
+                               int8_t* __restrict__ A8, int32_t* __restrict__ blkpre) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n) return;
+    const int b = rowptr[row], e = rowptr[row + 1];
+    for (int p = b + lane; p < e; p += 32) A8[(size_t)row * n_pad + colidx[p]] = 1;
+    const int nblk = n_pad / TC_BN;
+    for (int t = lane; t < nblk; t += 32) blkpre[(size_t)row * nblk + t] = lower_bound(colidx, b, e - b, t * TC_BN);
+}
+
+// ---- the GEMM + fused edge-extraction kernel ---------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_support_kernel(const __grid_constant__ CUtensorMap tmap, const int8_t* __restrict__ A8,
+                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ blkpre, int n, int n_pad,
+                  int32_t* __restrict__ tri) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // 128B swizzle: 1024-byte aligned
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + TC_STAGES * TC_STAGE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.y, nt = blockIdx.x;
+    const int num_kb = n_pad / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation is a warp-wide instruction; the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t phase = (kb / TC_STAGES) & 1;
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                mbar_expect_tx(&full_bar[s], 2 * TC_STAGE_BYTES);
+                tma_load_2d(smem_a + s * TC_STAGE_BYTES, &tmap, &full_bar[s], kb * TC_BK, mt * TC_BM);
+                tma_load_2d(smem_b + s * TC_STAGE_BYTES, &tmap, &full_bar[s], kb * TC_BK, nt * TC_BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(TC_BM, TC_BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t phase = (kb / TC_STAGES) & 1;
+                mbar_wait(&full_bar[s], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem_a + s * TC_STAGE_BYTES);
+                const uint32_t b_addr = smem_u32(smem_b + s * TC_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    umma_i8(tmem_base, umma_desc_k_sw128(a_addr + k * TC_UMMA_K), umma_desc_k_sw128(b_addr + k * TC_UMMA_K),
+                            idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);          // frees the stage once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);             // accumulators complete
+        }
+    } else {
+        // epilogue: warp w owns TMEM lanes 32*(w % 4) .. +31 = rows of the tile
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int i = mt * TC_BM + r;
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int nblk = n_pad / TC_BN;
+        int pos = (i < n) ? rowptr[i] + blkpre[(size_t)i * nblk + nt] : 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t acc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+                  "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+                  "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]),
+                  "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]),
+                  "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (i < n) {
+                const uint4* seg = (const uint4*)(A8 + (size_t)i * n_pad + (size_t)nt * TC_BN + c0);   // 32 bytes
+                const uint4 lo = seg[0], hi = seg[1];
+                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if ((w[c >> 2] >> ((c & 3) * 8)) & 0xffu) tri[pos++] = (int32_t)acc[c];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+}  // namespace dcr
+
+using namespace dcr;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static inline int tc_pad(int n) { return (n + TC_BM - 1) / TC_BM * TC_BM; }
+
+extern "C" int64_t dcr_bfc_support_tc_workspace_bytes(int n) {
+    const int64_t np = tc_pad(n);
+    return np * np + (int64_t)n * (np / TC_BN) * (int64_t)sizeof(int32_t) + 512;
+}
+
+extern "C" int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    if (n <= 0) return 0;
+    if (n > 32768) { set_error("dcr_bfc_support_tc: dense tensor-core path is for n <= 32768 (got %d)", n); return 1; }
+    if (workspace_bytes < dcr_bfc_support_tc_workspace_bytes(n)) { set_error("dcr_bfc_support_tc: workspace too small"); return 1; }
+    PFN_encodeTiled encode = get_encode_tiled();
+    if (!encode) { set_error("dcr_bfc_support_tc: cuTensorMapEncodeTiled unavailable"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = tc_pad(n);
+    int8_t* A8 = (int8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int32_t* blkpre = (int32_t*)(A8 + (size_t)np * np);
+    DCR_CUDA(cudaMemsetAsync(A8, 0, (size_t)np * np, st));
+    tc_fill_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, np, A8, blkpre);
+    DCR_LAUNCH_CHECK();
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)np, (cuuint64_t)np};           // inner (columns, bytes), outer (rows)
+    const cuuint64_t gstride[1] = {(cuuint64_t)np};                        // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)A8, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("dcr_bfc_support_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        DCR_CUDA(cudaFuncSetAttribute(tc_support_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_done = true;
+    }
+    const dim3 grid((unsigned)(np / TC_BN), (unsigned)(np / TC_BM));
+    tc_support_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, A8, rowptr, blkpre, n, np, tri);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}

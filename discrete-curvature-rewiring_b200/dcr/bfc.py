@@ -78,6 +78,20 @@ def support(csr: DeviceCSR, out: torch.Tensor | None = None) -> torch.Tensor:
     return tri
 
 
+def support_tc(csr: DeviceCSR, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """Same numbers as :func:`support`, computed as the dense product ``A·A`` on the tensor cores (tcgen05 int8,
+    TMA, TMEM) with the edge extraction fused into the epilogue.  Dense regime only (``n <= 32768``)."""
+    lib = L.load()
+    dev = csr.colidx.device
+    tri = out if out is not None else torch.empty(max(csr.nnz, 1), dtype=torch.int32, device=dev)[:csr.nnz]
+    nbytes = int(lib.dcr_bfc_support_tc_workspace_bytes(csr.n))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(lib.dcr_bfc_support_tc(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(),
+                                   workspace.data_ptr(), nbytes, L.current_stream()), "dcr_bfc_support_tc")
+    return tri
+
+
 def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None, want_fields: bool = True,
                  tri: torch.Tensor | None = None) -> dict:
     """cuda-flavour BFC per directed entry: ``tri, sharp, lam`` (int32), ``c64`` (fp64), ``c32`` (fp32)."""

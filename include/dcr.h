@@ -73,6 +73,14 @@ int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx, int n, co
                          int32_t* sharp, int32_t* lam, double* c64, float* c32, int64_t entry_lo,
                          int64_t entry_hi, void* stream);
 
+/* Dense-regime alternative to dcr_bfc_support (n <= 32768): A2 = A·A on the tensor cores (tcgen05 kind::i8, TMA,
+ * TMEM), replacing `torch.matmul(A, A)` of curvature/bfc_cuda.py:53,146; the fused epilogue writes only the entries
+ * that sit on an edge, in CSR order — tri[0..nnz) is identical to dcr_bfc_support's.
+ * workspace: dcr_bfc_support_tc_workspace_bytes(n) bytes of device memory (int8 image of A + per-block offsets). */
+int64_t dcr_bfc_support_tc_workspace_bytes(int n);
+int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * paper-flavour BFC over CSR.  Replaces bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).
  * Undirected edges are given explicitly: edge e = (esrc[e], edst[e]).  One call handles the strided subset

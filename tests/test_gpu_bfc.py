@@ -272,3 +272,22 @@ def test_sharded_path_single_process_matches_full():
         out = bfc.unshard(gathered, world, chunk, E)
         for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
             assert torch.equal(out[k], full[k]), (world, k)
+
+
+def test_tensor_core_support_matches_sparse_support():
+    """Dense-regime A·A on tcgen05 (int8, TMA, TMEM) with the fused edge-extraction epilogue == sorted-list supports."""
+    import torch
+    from dcr import bfc
+    from dcr.synth import chung_lu_graph
+    for n, e, seed in ((100, 600, 1), (257, 3000, 2), (1000, 30000, 3), (5201, 198000, 5201)):
+        ei = chung_lu_graph(n, e, 0.7, 0.3, seed)
+        csr = _csr(ei, n)
+        want = bfc.support(csr)
+        got = bfc.support_tc(csr)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (n, int((got != want).sum()))
+    # edge cases: empty rows / isolated nodes, a clique (every tile entry on an edge)
+    csr = _csr(sym_edge_index([(0, i) for i in range(1, 40)], 300), 300)
+    assert torch.equal(bfc.support_tc(csr), bfc.support(csr))
+    csr = _csr(sym_edge_index([(i, j) for i in range(140) for j in range(i + 1, 140)], 140), 140)
+    assert torch.equal(bfc.support_tc(csr), bfc.support(csr))
