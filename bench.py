@@ -27,6 +27,10 @@ for _p in (PKG, REPO):
 
 import numpy as np  # noqa: E402
 
+DENSE_WORKLOAD = ("squirrel-shaped synthetic graph (N=5201, E=198000): full-graph cuda-flavour BFC in the dense regime — "
+                  "supports A2[i,j] on the edges via tcgen05 int8 A·A (TMA, TMEM, fused epilogue), then the per-entry "
+                  "closing pass; the sparse sorted-list support kernel is timed beside it")
+
 WORKLOADS = {
     "arxiv": "arxiv-shaped synthetic graph (N=169343, E=1166243, Chung-Lu alpha=0.6, p_tri=0.1, seed 169343): "
              "full-graph paper-flavour BFC (deg, #tri, #sq_i, #sq_j, gamma_max, fp64 value per undirected edge)",
@@ -431,6 +435,71 @@ def emit(line: dict):
     out.flush()
 
 
+def run_dense(args):
+    """Config 4: the dense-regime tensor path (1 GPU).  value = undirected edges/s of the full cuda-flavour pass."""
+    import torch
+
+    import __graft_entry__
+    __graft_entry__.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(0)
+    from dcr import bfc
+    ei, n, rowptr, col, esrc, edst = build_graph("squirrel")
+    E = int(esrc.size)
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    n_pad = (n + 127) // 128 * 128
+    ws = torch.empty(int(bfc.L.load().dcr_bfc_support_tc_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    tri = torch.empty(csr.nnz, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        out = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return float(np.mean(out))
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_tc = timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), args.steps, args.warmup)
+    ws2 = torch.empty(int(bfc.L.load().dcr_bfc_cuda_flavour_tc_workspace_bytes(n, csr.nnz)), dtype=torch.uint8,
+                      device="cuda")
+    ms_full = timed(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2), args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_sparse = timed(lambda: bfc.support(csr, out=tri), args.steps, args.warmup)
+    ms_full_sparse = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr, out=tri)),
+                           args.steps, args.warmup)
+    same = bool(torch.equal(bfc.support_tc(csr), bfc.support(csr)))
+    c_tc = bfc.cuda_flavour_tc(csr, want_fields=False)["c32"]
+    c_sp = bfc.cuda_flavour(csr, want_fields=False)["c32"]
+    same = same and bool(torch.equal(c_tc.view(torch.int32), c_sp.view(torch.int32)))
+    ops = 2.0 * n_pad ** 3
+    line = {
+        "metric": "bfc_edges_per_sec", "value": E / (ms_full * 1e-3), "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), f64 closing formula",
+        "data": "synthetic", "config": {"workload": DENSE_WORKLOAD, "nodes": n, "undirected_edges": E, "n_pad": n_pad,
+                                        "l2": "256 MiB memset between steps", "outputs_bit_identical_to_sparse_path": same},
+        "clocks": clocks, "gpu_launches": 5 * args.steps,   # fill, GEMM, fill_q, GEMM, closing (+ one memset)
+        "roofline": {"bound": "tensor", "kernel": "tc_support_kernel (+ memset and tc_fill_kernel of the same call)",
+                     "achieved": ops / (ms_tc * 1e-3) / 1e12, "peak": 4500.0, "unit": "TOP/s (int8)",
+                     "frac": ops / (ms_tc * 1e-3) / 1e12 / 4500.0,
+                     "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
+                     "traffic": None, "support_tc_ms": ms_tc, "ops": ops},
+        "sparse_path": {"support_ms": ms_sparse, "full_ms": ms_full_sparse,
+                        "note": "sorted-list intersection kernels on the same CSR (dcr_bfc_support + dcr_bfc_cuda_flavour)"},
+    }
+    emit(line)
+
+
 def main():
     guard_stdout()
     ap = argparse.ArgumentParser()
@@ -438,7 +507,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS) + ["squirrel-dense"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--sdrf-loops", type=int, default=1000)
     ap.add_argument("--sdrf-cpu-iters", type=int, default=3)
@@ -446,7 +515,13 @@ def main():
     ap.add_argument("--no-sdrf", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "squirrel-dense":
+        if args.impl == "reference":
+            args.workload = "squirrel"
+            run_reference(args)
+        else:
+            run_dense(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -9,7 +9,7 @@
 //
 // Structure (one 128x128 output tile per CTA, K swept in 128-byte blocks):
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d of the A-rows tile (128 x 128 B) and the "B" tile — by symmetry
-//                           also 128 rows of A, K-major — into a 4-stage 128B-swizzled shared-memory ring,
+//                           also 128 rows of A, K-major — into a 3-stage 128B-swizzled shared-memory ring,
 //                           mbarrier complete_tx
 //   warp 1   MMA issuer     one elected thread: 4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32) per stage,
 //                           accumulators in TMEM (128 lanes x 128 columns of int32); tcgen05.commit frees the stage
@@ -24,7 +24,7 @@
 namespace dcr {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 128;      // tile (int8 elements; BK bytes = one 128B swizzle row)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;                              // 3 x 32 KB: two CTAs per SM, one's epilogue under the other's MMAs
 constexpr int TC_UMMA_K = 32;                             // int8: 32 elements = 32 bytes per MMA
 constexpr int TC_THREADS = 192;                           // 6 warps: TMA, MMA, 4 x epilogue
 constexpr int TC_TMEM_COLS = 128;
@@ -100,8 +100,9 @@ __global__ void tc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t
 }
 
 // ---- the GEMM + fused edge-extraction kernel ---------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_support_kernel(const __grid_constant__ CUtensorMap tmap, const int8_t* __restrict__ A8,
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_support_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const int8_t* __restrict__ A8,
                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ blkpre, int n, int n_pad,
                   int32_t* __restrict__ tri) {
     extern __shared__ uint8_t smem_raw[];
@@ -117,7 +118,8 @@ tc_support_kernel(const __grid_constant__ CUtensorMap tmap, const int8_t* __rest
     const int num_kb = n_pad / TC_BK;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,8 +141,8 @@ tc_support_kernel(const __grid_constant__ CUtensorMap tmap, const int8_t* __rest
                 const uint32_t phase = (kb / TC_STAGES) & 1;
                 mbar_wait(&empty_bar[s], phase ^ 1);
                 mbar_expect_tx(&full_bar[s], 2 * TC_STAGE_BYTES);
-                tma_load_2d(smem_a + s * TC_STAGE_BYTES, &tmap, &full_bar[s], kb * TC_BK, mt * TC_BM);
-                tma_load_2d(smem_b + s * TC_STAGE_BYTES, &tmap, &full_bar[s], kb * TC_BK, nt * TC_BN);
+                tma_load_2d(smem_a + s * TC_STAGE_BYTES, &tmap_a, &full_bar[s], kb * TC_BK, mt * TC_BM);
+                tma_load_2d(smem_b + s * TC_STAGE_BYTES, &tmap_b, &full_bar[s], kb * TC_BK, nt * TC_BN);
             }
         }
     } else if (warp == 1) {
@@ -228,43 +230,143 @@ static PFN_encodeTiled get_encode_tiled() {
 
 static inline int tc_pad(int n) { return (n + TC_BM - 1) / TC_BM * TC_BM; }
 
-extern "C" int64_t dcr_bfc_support_tc_workspace_bytes(int n) {
-    const int64_t np = tc_pad(n);
-    return np * np + (int64_t)n * (np / TC_BN) * (int64_t)sizeof(int32_t) + 512;
-}
-
-extern "C" int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
-    if (n <= 0) return 0;
-    if (n > 32768) { set_error("dcr_bfc_support_tc: dense tensor-core path is for n <= 32768 (got %d)", n); return 1; }
-    if (workspace_bytes < dcr_bfc_support_tc_workspace_bytes(n)) { set_error("dcr_bfc_support_tc: workspace too small"); return 1; }
+static int make_tmap(CUtensorMap* tmap, const int8_t* base, int np) {
     PFN_encodeTiled encode = get_encode_tiled();
-    if (!encode) { set_error("dcr_bfc_support_tc: cuTensorMapEncodeTiled unavailable"); return 1; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int np = tc_pad(n);
-    int8_t* A8 = (int8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    int32_t* blkpre = (int32_t*)(A8 + (size_t)np * np);
-    DCR_CUDA(cudaMemsetAsync(A8, 0, (size_t)np * np, st));
-    tc_fill_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, np, A8, blkpre);
-    DCR_LAUNCH_CHECK();
-
-    CUtensorMap tmap;
+    if (!encode) { set_error("tensor path: cuTensorMapEncodeTiled unavailable"); return 1; }
     const cuuint64_t gdim[2] = {(cuuint64_t)np, (cuuint64_t)np};           // inner (columns, bytes), outer (rows)
     const cuuint64_t gstride[1] = {(cuuint64_t)np};                        // bytes between rows
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)A8, gdim, gstride, box, estr,
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("dcr_bfc_support_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+    if (r != CUDA_SUCCESS) { set_error("tensor path: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+    return 0;
+}
 
+static int launch_edge_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const int8_t* A8, const int32_t* rowptr,
+                            const int32_t* blkpre, int n, int np, int32_t* out, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         DCR_CUDA(cudaFuncSetAttribute(tc_support_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_done = true;
     }
     const dim3 grid((unsigned)(np / TC_BN), (unsigned)(np / TC_BM));
-    tc_support_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmap, A8, rowptr, blkpre, n, np, tri);
+    tc_support_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, A8, rowptr, blkpre, n, np, out);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+struct TcWorkspace {
+    int8_t* A8;
+    int8_t* Q8;
+    int32_t* blkpre;
+    int32_t* t1;
+    size_t total;
+};
+static TcWorkspace tc_layout(void* workspace, int n, int64_t nnz, bool with_q) {
+    TcWorkspace w;
+    const size_t np = (size_t)tc_pad(n);
+    char* p = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    char* p0 = p;
+    w.A8 = (int8_t*)p; p += np * np;
+    w.Q8 = (int8_t*)p; if (with_q) p += np * np;
+    w.blkpre = (int32_t*)p; p += ((size_t)n * (np / TC_BN) * sizeof(int32_t) + 255) / 256 * 256;
+    w.t1 = (int32_t*)p; if (with_q) p += ((size_t)nnz * sizeof(int32_t) + 255) / 256 * 256;
+    w.total = (size_t)(p - p0) + 256;
+    return w;
+}
+
+extern "C" int64_t dcr_bfc_support_tc_workspace_bytes(int n) { return (int64_t)tc_layout(nullptr, n, 0, false).total; }
+
+extern "C" int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    if (n <= 0) return 0;
+    if (n > 32768) { set_error("dcr_bfc_support_tc: dense tensor-core path is for n <= 32768 (got %d)", n); return 1; }
+    if (workspace_bytes < dcr_bfc_support_tc_workspace_bytes(n)) { set_error("dcr_bfc_support_tc: workspace too small"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = tc_pad(n);
+    const TcWorkspace w = tc_layout(workspace, n, 0, false);
+    DCR_CUDA(cudaMemsetAsync(w.A8, 0, (size_t)np * np, st));
+    tc_fill_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, np, w.A8, w.blkpre);
+    DCR_LAUNCH_CHECK();
+    CUtensorMap tmap;
+    if (make_tmap(&tmap, w.A8, np)) return 1;
+    return launch_edge_gemm(tmap, tmap, w.A8, rowptr, w.blkpre, n, np, tri, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The whole cuda flavour in the dense regime: two tensor-core products and an elementwise closing pass.
+//   A2 = A·A          -> tri[p] = A2[i,j] on the edges                               (bfc_cuda.py:53)
+//   T1 = Q·A, Q = A ∧ [A2 == 1]  -> t1[p] = #{k in N(i)∩N(j) : support(i,k) == 1}   (the zero terms of :34-44)
+//   sharp = d_i + d_j - t1[i,j] - t1[j,i],  lambda = d_max                            
+// ------------------------------------------------------------------------------------------------------------
+namespace dcr {
+__global__ void tc_fill_q_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 const int32_t* __restrict__ tri, int n, int n_pad, int8_t* __restrict__ Q8) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n) return;
+    const int b = rowptr[row], e = rowptr[row + 1];
+    for (int p = b + lane; p < e; p += 32)
+        if (tri[p] == 1) Q8[(size_t)row * n_pad + colidx[p]] = 1;
+}
+
+__global__ void __launch_bounds__(256) tc_closing_kernel(const int32_t* __restrict__ rowptr,
+                                                         const int32_t* __restrict__ colidx, int n, int64_t nnz,
+                                                         const int32_t* __restrict__ tri, const int32_t* __restrict__ t1,
+                                                         int32_t* __restrict__ sharp_out, int32_t* __restrict__ lam_out,
+                                                         double* __restrict__ c64_out, float* __restrict__ c32_out) {
+    // one thread per directed entry (hub rows would serialise a warp-per-row mapping)
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int a = 0, b = n;                       // row of entry p: rowptr[a] <= p < rowptr[b]
+    while (b - a > 1) {
+        const int m = (a + b) >> 1;
+        if ((int64_t)rowptr[m] <= p) a = m; else b = m;
+    }
+    const int i = a, j = colidx[p];
+    const int di = rowptr[i + 1] - rowptr[i];
+    const int sj = rowptr[j], dj = rowptr[j + 1] - sj;
+    const int q = find_sorted(colidx, sj, dj, i);                // the mirrored entry (j -> i)
+    const int dmax = max(di, dj), dmin = min(di, dj);
+    const int sharp = di + dj - t1[p] - t1[q];
+    const Closing c = closing_value(dmax, dmin, tri[p], 1, sharp, dmax);
+    if (sharp_out) sharp_out[p] = sharp;
+    if (lam_out) lam_out[p] = dmax;
+    if (c64_out) c64_out[p] = c.c64;
+    c32_out[p] = c.c32;
+}
+}  // namespace dcr
+
+extern "C" int64_t dcr_bfc_cuda_flavour_tc_workspace_bytes(int n, int64_t nnz) {
+    return (int64_t)tc_layout(nullptr, n, nnz, true).total;
+}
+
+extern "C" int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri,
+                                       int32_t* sharp, int32_t* lam, double* c64, float* c32, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+    if (n <= 0 || nnz <= 0) return 0;
+    if (n > 32768) { set_error("dcr_bfc_cuda_flavour_tc: dense tensor-core path is for n <= 32768 (got %d)", n); return 1; }
+    if (!tri || !c32) { set_error("dcr_bfc_cuda_flavour_tc: tri and c32 must not be NULL"); return 1; }
+    if (workspace_bytes < dcr_bfc_cuda_flavour_tc_workspace_bytes(n, nnz)) {
+        set_error("dcr_bfc_cuda_flavour_tc: workspace too small");
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = tc_pad(n);
+    const TcWorkspace w = tc_layout(workspace, n, nnz, true);
+    const unsigned row_grid = (unsigned)(((int64_t)n * 32 + 255) / 256);
+    DCR_CUDA(cudaMemsetAsync(w.A8, 0, 2 * (size_t)np * np, st));     // A8 and Q8 are adjacent
+    tc_fill_kernel<<<row_grid, 256, 0, st>>>(rowptr, colidx, n, np, w.A8, w.blkpre);
+    DCR_LAUNCH_CHECK();
+    CUtensorMap map_a, map_q;
+    if (make_tmap(&map_a, w.A8, np) || make_tmap(&map_q, w.Q8, np)) return 1;
+    if (launch_edge_gemm(map_a, map_a, w.A8, rowptr, w.blkpre, n, np, tri, st)) return 1;
+    tc_fill_q_kernel<<<row_grid, 256, 0, st>>>(rowptr, colidx, tri, n, np, w.Q8);
+    DCR_LAUNCH_CHECK();
+    if (launch_edge_gemm(map_q, map_a, w.A8, rowptr, w.blkpre, n, np, w.t1, st)) return 1;
+    tc_closing_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, nnz, tri, w.t1, sharp, lam, c64, c32);
     DCR_LAUNCH_CHECK();
     return 0;
 }

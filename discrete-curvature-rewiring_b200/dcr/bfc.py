@@ -92,6 +92,26 @@ def support_tc(csr: DeviceCSR, out: torch.Tensor | None = None, workspace: torch
     return tri
 
 
+def cuda_flavour_tc(csr: DeviceCSR, want_fields: bool = True, workspace: torch.Tensor | None = None) -> dict:
+    """cuda-flavour BFC per directed entry through the dense tensor-core route (``n <= 32768``): same outputs as
+    :func:`cuda_flavour`."""
+    lib = L.load()
+    dev = csr.colidx.device
+    nnz = csr.nnz
+    alloc = lambda dt: torch.zeros(max(nnz, 1), dtype=dt, device=dev)[:nnz]
+    tri, c32 = alloc(torch.int32), alloc(torch.float32)
+    sharp = alloc(torch.int32) if want_fields else None
+    lam = alloc(torch.int32) if want_fields else None
+    c64 = alloc(torch.float64) if want_fields else None
+    nbytes = int(lib.dcr_bfc_cuda_flavour_tc_workspace_bytes(csr.n, nnz))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(lib.dcr_bfc_cuda_flavour_tc(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, nnz, tri.data_ptr(),
+                                        L.ptr(sharp), L.ptr(lam), L.ptr(c64), c32.data_ptr(), workspace.data_ptr(),
+                                        nbytes, L.current_stream()), "dcr_bfc_cuda_flavour_tc")
+    return {"tri": tri, "sharp": sharp, "lam": lam, "c64": c64, "c32": c32, "workspace": workspace}
+
+
 def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None, want_fields: bool = True,
                  tri: torch.Tensor | None = None) -> dict:
     """cuda-flavour BFC per directed entry: ``tri, sharp, lam`` (int32), ``c64`` (fp64), ``c32`` (fp32)."""

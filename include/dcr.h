@@ -80,6 +80,12 @@ int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx, int n, co
 int64_t dcr_bfc_support_tc_workspace_bytes(int n);
 int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
                        int64_t workspace_bytes, void* stream);
+/* The whole cuda flavour in the dense regime (same outputs as dcr_bfc_support + dcr_bfc_cuda_flavour over all
+ * entries): A2 = A·A and T1 = (A ∧ [A2 == 1])·A on the tensor cores, then an elementwise closing pass. */
+int64_t dcr_bfc_cuda_flavour_tc_workspace_bytes(int n, int64_t nnz);
+int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri,
+                            int32_t* sharp, int32_t* lam, double* c64, float* c32, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * paper-flavour BFC over CSR.  Replaces bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).

@@ -291,3 +291,25 @@ def test_tensor_core_support_matches_sparse_support():
     assert torch.equal(bfc.support_tc(csr), bfc.support(csr))
     csr = _csr(sym_edge_index([(i, j) for i in range(140) for j in range(i + 1, 140)], 140), 140)
     assert torch.equal(bfc.support_tc(csr), bfc.support(csr))
+
+
+def test_tensor_core_cuda_flavour_matches_sparse_route_and_oracle():
+    import torch
+    from dcr import bfc
+    from dcr.synth import chung_lu_graph
+    from oracle.cuda_flavour import bfc_cuda_dense
+    for n, e, seed in ((60, 300, 7), (300, 4000, 8), (5201, 198000, 5201)):
+        ei = chung_lu_graph(n, e, 0.7, 0.3, seed)
+        csr = _csr(ei, n)
+        a = bfc.cuda_flavour(csr)
+        b = bfc.cuda_flavour_tc(csr)
+        torch.cuda.synchronize()
+        for k in ("tri", "sharp", "lam"):
+            assert torch.equal(a[k], b[k]), (n, k)
+        assert torch.equal(a["c32"].view(torch.int32), b["c32"].view(torch.int32)), n     # fp32 bit patterns
+        assert torch.equal(a["c64"], b["c64"]), n
+        if n <= 300:
+            ref = bfc_cuda_dense(dense_of(ei, n), "compiled")
+            C = torch.zeros(n, n, device="cuda")
+            bfc.scatter_dense(csr, b["c32"], C)
+            assert np.array_equal(C.cpu().numpy().view(np.uint32), ref["C"].view(np.uint32))

@@ -76,3 +76,18 @@ def test_rewire_dropin_returns_edge_index_and_consumes_numpy_stream():
     draws = sum(r["n_candidates"] > 0 for r in wlog)
     assert after == uni[draws]        # the global generator advanced by exactly the reference's number of draws
     assert rewire(data, None, loops, 1.64, 22) is data.edge_index
+
+
+def test_balanced_forman_curvature_dense_regime_uses_tensor_path_and_matches_oracle():
+    import torch
+    from curvature import bfc_cuda
+    from dcr.synth import chung_lu_graph
+    from oracle.cuda_flavour import bfc_cuda_dense
+    n = 220
+    ei = chung_lu_graph(n, 5000, 0.5, 0.3, 4)          # average degree 45: dense regime
+    An = dense_of(ei, n)
+    from dcr import bfc
+    assert bfc_cuda._dense_regime(bfc.DeviceCSR.from_dense(torch.from_numpy(An).cuda()))
+    C = bfc_cuda.balanced_forman_curvature(torch.from_numpy(An).cuda())
+    ref = bfc_cuda_dense(An)["C"]
+    assert np.array_equal(C.cpu().numpy().view(np.uint32), ref.view(np.uint32))
