@@ -6,6 +6,6 @@ This package provides exactly the names those files use, with the semantics of t
 (SURVEY.md App. E.1).  It is only put on ``sys.path`` when the real package is absent
 (``dcr.compat.ensure_torch_geometric()``); a real installation always wins.
 """
-from . import data, utils  # noqa: F401
+from . import data, nn, utils  # noqa: F401
 
 __version__ = "2.0.3+dcr.standin"

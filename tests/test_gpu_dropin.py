@@ -91,3 +91,40 @@ def test_balanced_forman_curvature_dense_regime_uses_tensor_path_and_matches_ora
     C = bfc_cuda.balanced_forman_curvature(torch.from_numpy(An).cuda())
     ref = bfc_cuda_dense(An)["C"]
     assert np.array_equal(C.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_config2_rewire_then_gcn_on_gpu():
+    """Config 2: SDRF (greedy and softmax tau) on the wisconsin-shaped graph, then a GCN trained on the B200 on the
+    rewired edge_index (GCNConv stand-in; the reference's models/gcn.py runs unchanged on it — CPU test)."""
+    import torch
+    from dcr import compat
+    from dcr.synth import SDRF_PARAMS, named_graph
+    from rewiring.rewire import rewire
+    compat.ensure_torch_geometric()
+    from torch_geometric.data import Data
+    from torch_geometric.nn import GCNConv
+    ei, n = named_graph("wisconsin")
+    loops, tau, bound = SDRF_PARAMS["wisconsin"]
+    for t in (tau, float("inf")):
+        data = Data(edge_index=torch.from_numpy(ei))
+        data.num_nodes = n
+        np.random.seed(5)
+        new_ei = rewire(data, "bfc", loops, bound, t).cuda()
+        assert new_ei.shape[0] == 2 and int(new_ei.max()) < n
+        g = torch.Generator().manual_seed(0)
+        y = torch.randint(0, 3, (n,), generator=g)
+        x = (torch.randn(n, 16, generator=g)
+             + 2.0 * torch.nn.functional.one_hot(y, 3).float() @ torch.randn(3, 16, generator=g)).cuda()
+        y = y.cuda()
+        torch.manual_seed(0)
+        c1, c2 = GCNConv(16, 32).cuda(), GCNConv(32, 3).cuda()
+        opt = torch.optim.Adam(list(c1.parameters()) + list(c2.parameters()), lr=0.05)
+        first = None
+        for _ in range(60):
+            opt.zero_grad()
+            logits = c2(torch.relu(c1(x, new_ei)), new_ei)
+            loss = torch.nn.functional.cross_entropy(logits, y)
+            loss.backward()
+            opt.step()
+            first = loss.item() if first is None else first
+        assert loss.item() < 0.5 * first

@@ -133,3 +133,16 @@ def test_softmax_overflow_raises_like_numpy():
     assert np.isnan(p).any()
     with pytest.raises(ValueError, match="NaN"):
         choice_index(p, 0.5)
+
+
+def test_c_oracle_agrees_with_python_oracle():
+    from dcr import graph
+    from dcr.synth import named_graph
+    from oracle.c_port import bfc_paper_c
+    from oracle.paper_flavour import bfc_paper
+    ei, n = named_graph("wisconsin")
+    rowptr, col = graph.undirected_csr(ei, n)
+    ref = bfc_paper(ei, n)
+    c = bfc_paper_c(rowptr, col, ref["edges"][:, 0], ref["edges"][:, 1], threads=2)
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        assert np.array_equal(c[k], ref[k]), k
