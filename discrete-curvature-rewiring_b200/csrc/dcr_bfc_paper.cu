@@ -42,9 +42,16 @@ constexpr int N_CLASSES = 4;
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
 constexpr int WARP_SLOTS = 1024;
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int MID_SLOTS = 4096, MID_THREADS = 128, MID_CTAS_PER_SM = 7;
+constexpr int MID_SLOTS = 4096, MID_THREADS = 128, MID_CTAS_PER_SM = 6;
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
-__host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 2 : 4; }   // CTA stream state must fit beside the table
+__host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 1 : 4; }   // CTA stream state must fit beside the table
+// Membership pre-filter: a hashed bitmap of N(va) (bit index = node id mod B).  Almost every streamed element is NOT
+// a neighbour of va, and the bitmap says so with one shared-memory load and no loop; only the few elements whose bit
+// is set (true members + d_a/B false positives) go on to the exact hash probe.
+constexpr int WARP_BITS = 4096, MID_BITS = 32768, BIG_BITS = 131072, GLOBAL_BITS = 1048576;
+__host__ __device__ constexpr int filter_bits(int team, bool global_table) {
+    return global_table ? GLOBAL_BITS : (team == 32 ? WARP_BITS : (team >= 1024 ? BIG_BITS : MID_BITS));
+}
 constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
 constexpr int BUCKETS_PER_CLASS = 48;
 constexpr int UNROLL = 4;
@@ -282,32 +289,50 @@ __device__ __forceinline__ uint32_t slot_count_get(const uint32_t* cnt, uint32_t
 
 // The flat stream: `pre` = exclusive prefix sums of the list lengths (pre[l+1]-pre[l] = length of list l), `beg` =
 // first CSR slot of each list, `lcnt` = per-list match counters, all in shared memory.  This warp handles the flat
-// elements [f_begin, f_end); lane f%32 takes element f.  `l` = a list index with pre[l] <= f_begin.
-// A match (key present with tag 1, and not vb itself — the table holds all of N(va)) bumps the list's counter and
-// the matched key's slot counter.
+// elements [f_begin, f_end) in windows of 32*UNROLL; lane f%32 takes element f.  `lw` = a list index with
+// pre[lw] <= f_begin.  Windows that lie inside one list (most elements belong to long lists) take a fast path with
+// no per-element owner search.  An element first meets the bitmap filter `bm`; only if its bit is set the exact
+// probe runs.  A match (key present with tag 1, and not vb itself — the table holds all of N(va)) bumps the list's
+// counter and the matched key's slot counter.
 template <bool GLOBAL>
 __device__ __forceinline__ void flat_scan(const int32_t* __restrict__ colidx, const uint32_t* tab, uint32_t* cnt,
-                                          uint32_t mask, int shift, const int* pre, const int* beg, int* lcnt, int l,
-                                          int f_begin, int f_end, int lane, int vb) {
-    for (int f0 = f_begin + lane; f0 < f_end; f0 += 32 * UNROLL) {
+                                          uint32_t mask, int shift, const uint32_t* bm, uint32_t bmask, const int* pre,
+                                          const int* beg, int* lcnt, int lw, int f_begin, int f_end, int lane, int vb) {
+    for (int F = f_begin; F < f_end; F += 32 * UNROLL) {
+        while (pre[lw + 1] <= F) ++lw;                       // warp-uniform
+        const int win = min(32 * UNROLL, f_end - F);
         int k[UNROLL], lu[UNROLL];
+        if (pre[lw + 1] - F >= win) {                        // the whole window lies inside list lw
+            const int32_t* src = colidx + beg[lw] + (F - pre[lw]);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int f = f0 + 32 * u;
-            k[u] = -1;
-            lu[u] = 0;
-            if (f < f_end) {
-                while (pre[l + 1] <= f) ++l;         // monotone in f: amortised O(1)
-                lu[u] = l;
-                k[u] = colidx[beg[l] + (f - pre[l])];
+            for (int u = 0; u < UNROLL; ++u) {
+                const int idx = 32 * u + lane;
+                k[u] = idx < win ? src[idx] : -1;
+                lu[u] = lw;
+            }
+        } else {
+            int l = lw;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int f = F + 32 * u + lane;
+                k[u] = -1;
+                lu[u] = 0;
+                if (f < f_end) {
+                    while (pre[l + 1] <= f) ++l;             // monotone in f: amortised O(1)
+                    lu[u] = l;
+                    k[u] = colidx[beg[l] + (f - pre[l])];
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if (k[u] >= 0) {
+            // vb itself sits in every streamed list (m in N(vb)) and in the table (vb in N(va)): dropping it BEFORE the
+            // filter keeps the exact probe off the common path
+            const uint32_t kk = (uint32_t)k[u];
+            if (k[u] >= 0 && k[u] != vb && ((bm[(kk & bmask) >> 5] >> (kk & 31u)) & 1u)) {
                 uint32_t v;
-                const int h = probe_slot<GLOBAL>(tab, mask, shift, (uint32_t)k[u], v);
-                if (h >= 0 && (v >> 30) == 1u && k[u] != vb) {
+                const int h = probe_slot<GLOBAL>(tab, mask, shift, kk, v);
+                if (h >= 0 && (v >> 30) == 1u) {
                     atomicAdd(&lcnt[lu[u]], 1);
                     slot_count_add<GLOBAL>(cnt, h);
                 }
@@ -333,8 +358,8 @@ __device__ __forceinline__ void pure_head(const PaperArgs& a, const uint32_t* ta
 // state.  Accumulates (#lists with a match, largest per-list count) per lane.
 template <bool GLOBAL>
 __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
-                                           int shift, int list_begin, int list_len, int c0, int va, int vb, int* st,
-                                           int lane, int& sq, int& gmax) {
+                                           int shift, const uint32_t* bm, uint32_t bmask, int list_begin, int list_len,
+                                           int c0, int va, int vb, int* st, int lane, int& sq, int& gmax) {
     int* pre = st;            // [33]
     int* beg = st + 33;       // [32]
     int* lcnt = st + 65;      // [32]
@@ -354,7 +379,7 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
     beg[lane] = mb;
     lcnt[lane] = 0;
     __syncwarp();
-    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, 0, 0, total, lane, vb);
+    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, bm, bmask, pre, beg, lcnt, 0, 0, total, lane, vb);
     __syncwarp();
     const int c = lcnt[lane];
     sq += c > 0;
@@ -367,8 +392,8 @@ __device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* t
 // list next to twenty short ones does not serialise).  `cs` = pre[HEADS+1] | beg[HEADS] | cnt[HEADS].
 template <int THREADS, bool GLOBAL>
 __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask, int shift,
-                                         int list_begin, int list_len, int va, int vb, int* cs, int* s_warp_tot,
-                                         int& sq, int& gmax) {
+                                         const uint32_t* bm, uint32_t bmask, int list_begin, int list_len, int va,
+                                         int vb, int* cs, int* s_warp_tot, int& sq, int& gmax) {
     constexpr int HPT = heads_per_thread(THREADS);   // heads per thread
     constexpr int HEADS = HPT * THREADS;
     constexpr int NW = THREADS / 32;
@@ -416,7 +441,7 @@ __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab
                     const int mid = (lo + hi) >> 1;
                     if (pre[mid + 1] <= f_begin) lo = mid + 1; else hi = mid;
                 }
-                flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, pre, beg, lcnt, lo, f_begin, f_end, lane, vb);
+                flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, bm, bmask, pre, beg, lcnt, lo, f_begin, f_end, lane, vb);
             }
             __syncthreads();
             for (int t = tid; t < nh; t += THREADS) {
@@ -446,9 +471,12 @@ paper_edge_kernel(PaperArgs a, int cls) {
     const int warp = threadIdx.x >> 5;
     constexpr int team_threads = CTA_TEAM ? TEAM : 32;
     const int team_tid = CTA_TEAM ? (int)threadIdx.x : lane;
-    // shared-memory carve-up: [stream state (per warp | per CTA)][table keys][slot counters]
+    // shared-memory carve-up: [stream state (per warp | per CTA)][bitmap filter(s)][table keys][slot counters]
+    constexpr int FBITS = filter_bits(TEAM, GLOBAL_TABLE);
+    constexpr uint32_t bmask = (uint32_t)FBITS - 1u;
     int* st = (int*)smem_dyn + (CTA_TEAM ? 0 : warp * STREAM_INTS);
-    uint32_t* sm_tab = smem_dyn + (CTA_TEAM ? CTA_STREAM : NWARPS * STREAM_INTS);
+    uint32_t* bm = smem_dyn + (CTA_TEAM ? CTA_STREAM : NWARPS * STREAM_INTS + warp * (FBITS / 32));
+    uint32_t* sm_tab = smem_dyn + (CTA_TEAM ? CTA_STREAM + FBITS / 32 : NWARPS * (STREAM_INTS + FBITS / 32));
     uint32_t* tab;
     uint32_t* cnt;
     if (GLOBAL_TABLE) {
@@ -506,9 +534,13 @@ paper_edge_kernel(PaperArgs a, int cls) {
                 shift = 32 - lg;
                 for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
                 for (uint32_t s = team_tid; s < (GLOBAL_TABLE ? slots : slots / 2); s += team_threads) cnt[s] = 0u;
+                for (uint32_t s = team_tid; s < (uint32_t)FBITS / 32; s += team_threads) bm[s] = 0u;
                 team_sync<CTA_TEAM>();
-                for (int p = team_tid; p < da; p += team_threads)
-                    insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)a.colidx[sa + p], 1u);
+                for (int p = team_tid; p < da; p += team_threads) {
+                    const uint32_t k = (uint32_t)a.colidx[sa + p];
+                    insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, k, 1u);
+                    atomicOr(&bm[(k & bmask) >> 5], 1u << (k & 31u));
+                }
                 team_sync<CTA_TEAM>();
                 cur_va = va;
             }
@@ -532,7 +564,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
             // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
             int sqL = 0, gL = 0, sqS = 0, gS = 0;
             if (CTA_TEAM) {
-                scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, va, vb, st, s_warp_tot, sqL, gL);
+                scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, bm, bmask, sb, db, va, vb, st, s_warp_tot, sqL, gL);
                 sqL = warp_sum(sqL);
                 gL = warp_max(gL);
                 if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
@@ -540,7 +572,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
                 sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
             } else {
                 for (int c0 = 0; c0 < db; c0 += 32)
-                    scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, sb, db, c0, va, vb, st, lane, sqL, gL);
+                    scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, bm, bmask, sb, db, c0, va, vb, st, lane, sqL, gL);
                 sqL = warp_sum(sqL);
                 gL = warp_max(gL);
                 __syncwarp();
@@ -701,10 +733,10 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     static bool attr_done = false;
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
     constexpr int mid_stream = 3 * heads_per_thread(MID_THREADS) * MID_THREADS + 8;
-    const int smem_x = big_stream * (int)sizeof(int);
-    const int smem_big = (big_stream + BIG_SLOTS + BIG_SLOTS / 2) * (int)sizeof(uint32_t);
-    const int smem_mid = (mid_stream + MID_SLOTS + MID_SLOTS / 2) * (int)sizeof(uint32_t);
-    const int smem_warp = WARP_TEAM_WARPS * (STREAM_INTS + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
+    const int smem_big = (big_stream + BIG_BITS / 32 + BIG_SLOTS + BIG_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_mid = (mid_stream + MID_BITS / 32 + MID_SLOTS + MID_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_warp = WARP_TEAM_WARPS * (STREAM_INTS + WARP_BITS / 32 + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);
     if (!attr_done) {
         DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big));
@@ -712,18 +744,39 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid));
         DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<32, WARP_SLOTS, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
         attr_done = true;
     }
+    // The class kernels are independent (disjoint edges, disjoint outputs).  They are launched on three streams
+    // forked from `st` — heaviest class first — so that, as the persistent CTAs of one class run out of work, CTAs
+    // of the next class take over the freed SMs instead of waiting for the slowest CTA (tail filling).
+    static cudaStream_t aux[2] = {nullptr, nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    if (!aux[0]) {
+        for (int q = 0; q < 2; ++q) {
+            DCR_CUDA(cudaStreamCreateWithFlags(&aux[q], cudaStreamNonBlocking));
+            DCR_CUDA(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
+        }
+        DCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    }
+    DCR_CUDA(cudaEventRecord(ev_fork, st));
+    DCR_CUDA(cudaStreamWaitEvent(aux[0], ev_fork, 0));
+    DCR_CUDA(cudaStreamWaitEvent(aux[1], ev_fork, 0));
     if (L.gslots) {
         paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, st>>>(a, 3);
         DCR_LAUNCH_CHECK();
     }
     paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false><<<sms, BIG_THREADS, smem_big, st>>>(a, 2);
     DCR_LAUNCH_CHECK();
-    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * MID_CTAS_PER_SM, MID_THREADS, smem_mid, st>>>(a, 1);
+    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * MID_CTAS_PER_SM, MID_THREADS, smem_mid, aux[0]>>>(a, 1);
     DCR_LAUNCH_CHECK();
-    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem_warp, st>>>(a, 0);
+    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem_warp, aux[1]>>>(a, 0);
     DCR_LAUNCH_CHECK();
+    for (int q = 0; q < 2; ++q) {
+        DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));
+        DCR_CUDA(cudaStreamWaitEvent(st, ev_join[q], 0));
+    }
     paper_value_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
