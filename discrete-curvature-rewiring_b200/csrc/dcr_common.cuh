@@ -112,4 +112,29 @@ __device__ __forceinline__ Closing closing_value(int d_max, int d_min, int a2, i
     return out;
 }
 
+// The same formula split in two: the part that depends only on (d_max, d_min, A2[x,y], A[x,y]) — the first fp32
+// store — and the part that adds sharp/(d_max*lambda) — the second.  closing_finish(closing_first(...), sharp, lam)
+// is bit-identical to closing_value(...).c32; candidate scoring computes the first part once per (x,y).
+struct ClosingFirst {
+    float c32;     // value after the first store
+    double dmax;
+};
+__device__ __forceinline__ ClosingFirst closing_first(int d_max, int d_min, int a2, int a_xy) {
+    const double dmax = (double)d_max, dmin = (double)d_min;
+    const double r = __ddiv_rn(2.0, dmax);
+    const double s = __ddiv_rn(2.0, dmin);
+    const double b = __dadd_rn(__dadd_rn(s, r), -2.0);
+    const double q = __dadd_rn(__ddiv_rn(1.0, dmin), r);
+    const double t = __dmul_rn(q, (double)a2);
+    ClosingFirst f;
+    f.c32 = __double2float_rn(__fma_rn(t, (double)a_xy, b));
+    f.dmax = dmax;
+    return f;
+}
+__device__ __forceinline__ float closing_finish(const ClosingFirst& f, long long sharp, int lam) {
+    if (lam <= 0) return f.c32;
+    const double w = __ddiv_rn((double)sharp, __dmul_rn((double)lam, f.dmax));
+    return __double2float_rn(__dadd_rn(w, (double)f.c32));
+}
+
 }  // namespace dcr

@@ -29,6 +29,7 @@ struct ScoreScratch {
 
 struct ScoreShared {   // block-shared state of one scoring call
     int axy, dx, dy, sx, sy, a2xy, sharp0, lam0;
+    ClosingFirst first;      // closing formula up to the first fp32 store, for the unchanged degrees (d_x, d_y)
 };
 
 __device__ __forceinline__ int edge_slot(const GraphView& g, int a, int b) {
@@ -61,6 +62,10 @@ __device__ void score_prepare(const GraphView& g, const int32_t* supp, int x, in
         sh->a2xy = s >= 0 ? supp[s] : 0;   // only used multiplied by A[x,y]
         sh->sharp0 = 0;
         sh->lam0 = 0;
+        sh->first.c32 = 0.0f;
+        sh->first.dmax = 1.0;
+        if (sh->dx > 0 && sh->dy > 0)
+            sh->first = closing_first(max(sh->dx, sh->dy), min(sh->dx, sh->dy), sh->a2xy, sh->axy);
     }
     __syncthreads();
     const int dx = sh->dx, dy = sh->dy, sx = sh->sx, sy = sh->sy;
@@ -93,7 +98,8 @@ __device__ __forceinline__ float score_cell_simple(const GraphView& g, const Sco
     if (j == x) din += 1; else if (i == y) dout += 1;                 // :82-85
     if (din == 0 || dout == 0) return 0.0f;                           // :87-89
     const int dmax = max(din, dout), dmin = min(din, dout);           // :91-96
-    if (!sh->axy) return closing_value(dmax, dmin, 0, 0, 0, 0).c32;
+    const bool bumped = (j == x) || (i == y);                         // never true for an unmasked cell of SDRF
+    if (!sh->axy) return bumped ? closing_value(dmax, dmin, 0, 0, 0, 0).c32 : sh->first.c32;
     const int pI = sc.posI[I], pJ = sc.posJ[J];
     int sharp = sh->sharp0, lam = sh->lam0;
     if (pJ >= 0 && pI >= 0) {          // z == j: A2_x_z += A[x,i]   (:123-124)
@@ -106,7 +112,9 @@ __device__ __forceinline__ float score_cell_simple(const GraphView& g, const Sco
         sharp += (b <= 0);
         lam = max(lam, b + 1);
     }
-    return closing_value(dmax, dmin, sh->a2xy, 1, sharp, lam).c32;    // :139-141 (no triangle patch: x!=i, y!=j)
+    // :139-141 (no triangle patch: x != i, y != j); the first store is shared by all such cells
+    if (bumped) return closing_value(dmax, dmin, sh->a2xy, 1, sharp, lam).c32;
+    return closing_finish(sh->first, sharp, lam);
 }
 
 // One cell with x == i or y == j (warp-level; all lanes pass identical arguments).  Returns D[I,J].

@@ -23,7 +23,10 @@
 
 namespace dcr {
 
-constexpr int SDRF_THREADS = 512;
+#ifndef DCR_SDRF_THREADS
+#define DCR_SDRF_THREADS 1024
+#endif
+constexpr int SDRF_THREADS = DCR_SDRF_THREADS;
 constexpr int SDRF_WARPS = SDRF_THREADS / 32;
 constexpr uint32_t IMP_MASKED = 0xffffffffu;   // bit pattern marking a masked cell in the improvement matrix
 constexpr int STATUS_TOO_MANY_CANDIDATES = DCR_SDRF_TOO_MANY_CANDIDATES;

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdcr.so")
+LIB_PATH = os.environ.get("DCR_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libdcr.so")   # override: experiments
 
 
 class DcrError(RuntimeError):
