@@ -70,6 +70,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
+        self.first = 0
         self.proc = None
         self.thread = None
 
@@ -88,6 +89,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Samples taken from now on belong to the timed region (the process is started earlier, during warm-up, so
+        that nvidia-smi's own start-up does not perturb the timed steps)."""
+        self.first = len(self.rows)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -99,7 +105,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows[-1:]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -299,13 +306,15 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident throughput -------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)             # let nvidia-smi finish its own start-up before anything is timed
     for _ in range(args.warmup):
         flush.zero_()
         sh.run()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     step_ms, edge_ms = [], []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -375,7 +384,7 @@ def run_ours(args):
         ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
         checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
 
-    launches_per_step = 5 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + 1   # plan(5), edge classes, value, unshard
+    launches_per_step = 6 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + 1   # plan(6), edge classes, value, unshard
     line = {
         "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -469,6 +478,9 @@ def run_dense(args):
 
     sampler = ClockSampler(0)
     sampler.start()
+    time.sleep(0.5)
+    timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), 1, args.warmup)
+    sampler.mark()
     ms_tc = timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), args.steps, args.warmup)
     ws2 = torch.empty(int(bfc.L.load().dcr_bfc_cuda_flavour_tc_workspace_bytes(n, csr.nnz)), dtype=torch.uint8,
                       device="cuda")
