@@ -61,65 +61,107 @@ def algorithmic_bytes(rowptr: np.ndarray, col: np.ndarray, esrc: np.ndarray, eds
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons for the clocks record of the JSON line.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    * SM clock DURING the timed steps: an in-band probe (`dcr_sm_clock_probe`: one thread, clock64 / globaltimer)
+      enqueued on a side stream between the timed steps, so it runs while their kernels run.
+    * Throttle reasons: NVML, in-process — but NOT while the timed steps execute.  On these shared hosts every form of
+      NVML / nvidia-smi polling tried (nvidia-smi -lms, nvmlDeviceGetClockInfo, nvmlDeviceGetCurrentClocksEventReasons)
+      sporadically stalled GPU work for 20-200 ms, turning one 7 ms step into a 170 ms one (step_ms lists in
+      profiles/r01_clock_sampling_perturbation.txt; without polling every step is within 0.02 ms of the others).
+      The reasons are therefore sampled every 20 ms over an UNTIMED batch of the same steps run back to back right
+      after the timed region (`under_load`), i.e. under the identical load."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
-        self.first = 0
-        self.proc = None
-        self.thread = None
+        self.masks = []
+        self.stop_flag = False
+        self.handle = None
+        self.nvml = None
+        self.max_mhz = None
+        self.probe_out = None
+        self.probe_stream = None
+        self.n_probes = 0
 
     def start(self):
+        import torch
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
-        self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+        self.probe_out = torch.zeros(64, dtype=torch.float32, device=f"cuda:{self.gpu}")
+        self.probe_stream = torch.cuda.Stream(device=self.gpu)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def mark(self):
-        """Samples taken from now on belong to the timed region (the process is started earlier, during warm-up, so
-        that nvidia-smi's own start-up does not perturb the timed steps)."""
-        self.first = len(self.rows)
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = self.rows[self.first:] or self.rows[-1:]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
+    def _poll(self):
+        while not self.stop_flag:
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                try:
+                    m = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    m = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.masks.append(int(m))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def probe(self):
+        """Enqueue one SM-clock probe on the side stream (call between the enqueues of the timed steps)."""
+        if self.probe_out is None or self.n_probes >= self.probe_out.numel():
+            return
+        from dcr import lib as L
+        L.check(L.load().dcr_sm_clock_probe(self.probe_out[self.n_probes:].data_ptr(), self.probe_stream.cuda_stream),
+                "dcr_sm_clock_probe")
+        self.n_probes += 1
+
+    def under_load(self, step_fn, steps: int, exact: bool = False):
+        """Poll the throttle reasons while untimed repetitions of the timed step execute (`exact`: exactly `steps`
+        of them — needed when the step contains collectives and every rank must run the same count)."""
+        import torch
+        if self.nvml is None:
+            for _ in range(steps if exact else 0):
+                step_fn()
+            return
+        self.stop_flag = False
+        th = threading.Thread(target=self._poll, daemon=True)
+        th.start()
+        t_end = time.perf_counter() + (0.0 if exact else 0.25)
+        done = 0
+        while done < steps or time.perf_counter() < t_end:       # single GPU: at least a quarter of a second of load
+            step_fn()
+            done += 1
+            if done % 4 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        self.stop_flag = True
+        th.join(timeout=3)
+
+    def result(self) -> dict:
+        import torch
+        torch.cuda.synchronize()
+        mhz = [float(v) for v in self.probe_out[: self.n_probes].cpu().tolist() if v > 0] if self.n_probes else []
+        mask = 0
+        for m in self.masks:
+            mask |= m
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for name, bit in self.REASONS if mask & bit],
+                "samples": len(mhz), "reason_samples": len(self.masks),
+                "source": "sm_mhz: in-band clock64/globaltimer probes on a side stream during the timed steps; reasons: NVML "
+                          "every 20 ms over an untimed batch of the same steps run right after the timed region (NVML polling "
+                          "inside the region stalls GPU work on these hosts, see profiles/)"}
 
 
 def host_threads() -> int:
@@ -288,10 +330,6 @@ def run_ours(args):
     csr._edges = (torch.from_numpy(esrc).to(dev), torch.from_numpy(edst).to(dev), None)
     sh = ShardedPaperBFC(csr)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ev_edge = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    for e in ev_edge:
-        e.record()      # materialise the cudaEvent handles
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -305,30 +343,56 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def new_events(k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        for a, b in evs:
+            a.record()
+            b.record()      # materialise the cudaEvent handles (the edge-kernel pair is recorded by the library)
+        return evs
+
     # ---- device-resident throughput -------------------------------------------------------------------------
+    # All K steps are ENQUEUED without a host sync in between (per-step CUDA events on the stream, L2 flush between
+    # steps outside the events): the GPU never waits for the host, so host-side hiccups (e.g. the NVML sampler
+    # thread) cannot leak into the device times.
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
-        time.sleep(0.5)             # let nvidia-smi finish its own start-up before anything is timed
     for _ in range(args.warmup):
         flush.zero_()
         sh.run()
+    step_ev, edge_ev = new_events(args.steps), new_events(args.steps)
     barrier()
-    sampler.mark()
-    step_ms, edge_ms = [], []
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    res = None
+    for k in range(args.steps):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = sh.run(events=ev_edge)
-        e1.record()
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        edge_ms.append(ev_edge[0].elapsed_time(ev_edge[1]))
+        step_ev[k][0].record()
+        res = sh.run(events=edge_ev[k])
+        step_ev[k][1].record()
+        if rank == 0 and not args.no_clocks and k % max(1, args.steps // 8) == 0:
+            sampler.probe()         # runs on a side stream while this step's kernels execute
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in step_ev]
+    edge_ms = [a.elapsed_time(b) for a, b in edge_ev]
+    def untimed_step():
+        flush.zero_()
+        sh.run()
+
+    if world > 1:
+        n_untimed = max(args.steps, 16)              # every rank runs the same untimed batch (collectives inside)
+        if rank == 0 and not args.no_clocks:
+            sampler.under_load(untimed_step, n_untimed, exact=True)
+        else:
+            for _ in range(n_untimed):
+                untimed_step()
+        barrier()
+        clocks = sampler.result() if (rank == 0 and not args.no_clocks) else None
+    else:
+        clocks = None
+        if not args.no_clocks:
+            sampler.under_load(untimed_step, args.steps)
+            clocks = sampler.result()
     total_ms = max_over_ranks(float(np.sum(step_ms)))
     ms_per_step = total_ms / args.steps
     value = E / (ms_per_step * 1e-3)
@@ -362,18 +426,15 @@ def run_ours(args):
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
+    e2e_ev = new_events(args.steps)
     barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
+    for k in range(args.steps):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e2e_ev[k][0].record()
         e2e_step()
-        e1.record()
-        e1.synchronize()
-        e2e_ms.append(e0.elapsed_time(e1))
+        e2e_ev[k][1].record()
     barrier()
-    e2e_total = max_over_ranks(float(np.sum(e2e_ms)))
+    e2e_total = max_over_ranks(float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])))
     e2e_value = E / (e2e_total / args.steps * 1e-3)
 
     # parity spot check of what was just timed (full check lives in tests/): first 2000 edges vs the C oracle
@@ -392,8 +453,8 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[args.workload], "nodes": n, "undirected_edges": E,
                    "sharding": f"edge e -> rank e % {world}, graph replicated, one all-gather" if world > 1 else "single GPU",
                    "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
-                   "timing": "sum of per-step CUDA-event times, max over ranks", "wall_s_timed_region": wall,
-                   "parity_spot_check_vs_c_oracle": checked},
+                   "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks", "wall_s_timed_region": wall,
+                   "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / args.steps,
@@ -478,14 +539,16 @@ def run_dense(args):
 
     sampler = ClockSampler(0)
     sampler.start()
-    time.sleep(0.5)
     timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), 1, args.warmup)
-    sampler.mark()
+    for _ in range(4):
+        sampler.probe()
+        bfc.support_tc(csr, out=tri, workspace=ws)
     ms_tc = timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), args.steps, args.warmup)
     ws2 = torch.empty(int(bfc.L.load().dcr_bfc_cuda_flavour_tc_workspace_bytes(n, csr.nnz)), dtype=torch.uint8,
                       device="cuda")
     ms_full = timed(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2), args.steps, args.warmup)
-    clocks = sampler.stop()
+    sampler.under_load(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2), args.steps)
+    clocks = sampler.result()
     ms_sparse = timed(lambda: bfc.support(csr, out=tri), args.steps, args.warmup)
     ms_full_sparse = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr, out=tri)),
                            args.steps, args.warmup)
@@ -525,6 +588,7 @@ def main():
     ap.add_argument("--sdrf-cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sdrf", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "squirrel-dense":

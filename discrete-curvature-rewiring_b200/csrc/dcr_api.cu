@@ -33,5 +33,26 @@ int sm_count() {
 
 }  // namespace dcr
 
+// In-band SM clock probe: one thread spins for ~100 us and reports cycles / nanosecond = the SM clock it ran at.
+// bench.py launches it on a side stream while the timed kernels run; NVML's clock query was observed to stall GPU
+// work for up to 200 ms on the shared hosts, which a measurement taken under load cannot afford.
+__global__ void sm_clock_probe_kernel(float* out) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < 100000ull);
+    const long long c1 = clock64();
+    *out = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));   // MHz
+}
+
+extern "C" int dcr_sm_clock_probe(float* out_mhz, void* stream) {
+    if (!out_mhz) { dcr::set_error("dcr_sm_clock_probe: out_mhz is NULL"); return 1; }
+    sm_clock_probe_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out_mhz);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" const char* dcr_last_error(void) { return dcr::g_err; }
 extern "C" int dcr_version(void) { return DCR_VERSION; }

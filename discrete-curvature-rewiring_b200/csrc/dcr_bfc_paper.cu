@@ -34,15 +34,27 @@ namespace dcr {
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
 // Edge classes by the degree d_a of the TESTED endpoint (the one whose neighbour set goes into the hash table):
-//   class 0  d_a <= 128    warp team,            1024-slot table per warp (load factor <= 1/8)
-//   class 1  d_a <= 1024   128-thread CTA team,  4096-slot table          (load factor <= 1/4), 7 CTAs per SM
+//   class 0  d_a <= 128    warp team,            512-slot table per warp  (load factor <= 1/4), 48 warps per SM
+//   class 1  d_a <= 1024   128-thread CTA team,  2048-slot table          (load factor <= 1/2), 8 CTAs per SM
 //   class 2  d_a <= 16384  1024-thread CTA team, 32768-slot table         (load factor <= 1/2), 1 CTA per SM
 //   class 3  larger        1024-thread CTA team, table in global memory (L2)
 constexpr int N_CLASSES = 4;
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
-constexpr int WARP_SLOTS = 1024;
+#ifndef DCR_WARP_SLOTS
+#define DCR_WARP_SLOTS 512
+#endif
+#ifndef DCR_WARP_CTAS
+#define DCR_WARP_CTAS 6
+#endif
+#ifndef DCR_MID_SLOTS
+#define DCR_MID_SLOTS 2048
+#endif
+#ifndef DCR_MID_CTAS
+#define DCR_MID_CTAS 8
+#endif
+constexpr int WARP_SLOTS = DCR_WARP_SLOTS, WARP_CTAS_PER_SM = DCR_WARP_CTAS;
 constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int MID_SLOTS = 4096, MID_THREADS = 128, MID_CTAS_PER_SM = 6;
+constexpr int MID_SLOTS = DCR_MID_SLOTS, MID_THREADS = 128, MID_CTAS_PER_SM = DCR_MID_CTAS;
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
 __host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 1 : 4; }   // CTA stream state must fit beside the table
 // Membership pre-filter: a hashed bitmap of N(va) (bit index = node id mod B).  Almost every streamed element is NOT
@@ -460,7 +472,7 @@ __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab
 // TEAM = threads per team (32 = warp team, several teams per CTA; otherwise the CTA is the team).
 template <int TEAM, int MAX_SLOTS, bool GLOBAL_TABLE>
 __global__ void __launch_bounds__(TEAM > 32 ? TEAM : WARP_TEAM_WARPS * 32,
-                                  TEAM == BIG_THREADS ? 1 : (TEAM == MID_THREADS ? MID_CTAS_PER_SM : 4))
+                                  TEAM == BIG_THREADS ? 1 : (TEAM == MID_THREADS ? MID_CTAS_PER_SM : WARP_CTAS_PER_SM))
 paper_edge_kernel(PaperArgs a, int cls) {
     constexpr bool CTA_TEAM = TEAM > 32;
     constexpr int NWARPS = CTA_TEAM ? TEAM / 32 : WARP_TEAM_WARPS;
@@ -778,7 +790,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     DCR_LAUNCH_CHECK();
     paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * MID_CTAS_PER_SM, MID_THREADS, smem_mid, aux[0]>>>(a, 1);
     DCR_LAUNCH_CHECK();
-    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * 4, WARP_TEAM_WARPS * 32, smem_warp, aux[1]>>>(a, 0);
+    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * WARP_CTAS_PER_SM, WARP_TEAM_WARPS * 32, smem_warp, aux[1]>>>(a, 0);
     DCR_LAUNCH_CHECK();
     for (int q = 0; q < 2; ++q) {
         DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));

@@ -32,6 +32,7 @@ _D = C.c_double
 SIGNATURES = {
     "dcr_last_error": (C.c_char_p, []),
     "dcr_version": (_I, []),
+    "dcr_sm_clock_probe": (_I, [_P, _P]),
     "dcr_dense_count": (_I, [_P, _I, _P, _P, _P]),
     "dcr_dense_fill": (_I, [_P, _I, _P, _P, _P]),
     "dcr_scatter_dense": (_I, [_P, _P, _I, _P, _P, _P]),

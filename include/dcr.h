@@ -39,6 +39,9 @@ extern "C" {
 
 const char* dcr_last_error(void);
 int dcr_version(void);
+/* Measurement aid (no reference counterpart): a one-thread kernel that spins ~100 us on `stream` and writes the SM
+ * clock it observed (clock64 / globaltimer, MHz) to *out_mhz (device memory). */
+int dcr_sm_clock_probe(float* out_mhz, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense <-> CSR for the legacy dense-matrix signatures.
