@@ -39,6 +39,12 @@ WORKLOADS = {
 }
 
 
+# DRAM traffic of the edge kernels of ONE pass over the arxiv-shaped graph, from the committed ncu capture
+# (17.64 + 22.60 + 26.82 MB read, 0.23 + 1.58 + 3.26 MB written): the CSR is L2-resident, so this is ~1000x below the
+# algorithmic gather bytes.
+NCU_DRAM_BYTES_PER_PASS = 72.13e6
+
+
 def load_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -464,7 +470,10 @@ def run_ours(args):
             "bound": "hbm", "kernel": "paper_edge_kernel (CTA-team + warp-team launches of one step)",
             "achieved": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-            "traffic": None, "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
+            "traffic": NCU_DRAM_BYTES_PER_PASS if (world == 1 and args.workload == "arxiv") else None,
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the three class "
+                              "launches of one pass (profiles/r01_v10_ncu_full_paper_edge_kernel.csv)",
+            "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
             "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
             "note": "algorithmic bytes = SURVEY.md §8d B_gather of this rank's edges (every 2-hop list once per edge, "
                     "no cross-edge reuse charged); the CSR is L2-resident so DRAM traffic is far below it — see "
