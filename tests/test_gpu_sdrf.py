@@ -158,3 +158,60 @@ def test_sdrf_cora_shape_long_run_properties():
     fresh = bfc.cuda_flavour(csr)
     assert np.array_equal(fresh["c32"].cpu().numpy().view(np.uint32), c32.view(np.uint32))
     assert np.array_equal(fresh["tri"].cpu().numpy(), tri)
+
+
+def test_sdrf_row_relocation_star_like_growth():
+    # a hub keeps receiving edges: its arena row outgrows its slack several times and is relocated; a double star
+    # keeps the curvature of the bridge the minimum so that candidates always exist
+    pairs = [(0, 1)] + [(0, i) for i in range(2, 12)] + [(1, i) for i in range(12, 40)]
+    ei = sym_edge_index(pairs, 40)
+    _run_both(ei, 40, 60, 5.0, float("inf"), 3)
+    _run_both(ei, 40, 60, 0.2, 8, 3)
+
+
+def test_sdrf_zero_loops_and_edgeless_graph():
+    from dcr import sdrf
+    ei = gnp(12, 0.3, 1)
+    out, log = sdrf.sdrf(ei, 12, 0, True, 0.5, 3, uniforms=np.zeros(0), return_log=True)
+    assert len(log) == 0 and set(map(tuple, out.T.tolist())) == set(map(tuple, ei.T.tolist()))
+    # isolated nodes beyond the largest index are kept as nodes, not edges
+    out = sdrf.sdrf(ei, 20, 3, True, 0.5, float("inf"), uniforms=np.array([0.1, 0.2, 0.3]))
+    assert int(out.max()) < 12
+
+
+def test_sdrf_squirrel_shape_stress_incremental_state():
+    """Config-4-sized graph (hubs of degree ~3400: candidate matrices of millions of cells, CTA-wide edits of long
+    rows): 60 greedy iterations, then the incrementally maintained supports / curvatures against fresh kernels."""
+    from dcr import bfc, sdrf
+    from dcr.synth import named_graph
+    ei, n = named_graph("squirrel")
+    loops = 60
+    uni = np.random.RandomState(0).random_sample(loops)
+    keep = []
+    got, log = sdrf.sdrf(ei, n, loops, True, 5.88, float("inf"), uniforms=uni, return_log=True, state_out=keep)
+    assert len(log) == loops
+    rowptr, order, col, c32, tri = keep[0].export(with_curvature=True)
+    keep[0].close()
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    fresh = bfc.cuda_flavour(csr)
+    assert np.array_equal(fresh["tri"].cpu().numpy(), tri)
+    assert np.array_equal(fresh["c32"].cpu().numpy().view(np.uint32), c32.view(np.uint32))
+    edges = set(map(tuple, ei.T.tolist()))
+    for r in log:
+        if r[3] >= 0:
+            edges |= {(int(r[3]), int(r[4])), (int(r[4]), int(r[3]))}
+        if r[6] >= 0:
+            edges -= {(int(r[6]), int(r[7])), (int(r[7]), int(r[6]))}
+    assert set(map(tuple, got.T.tolist())) == edges
+
+
+def test_sdrf_negative_bound_removes_nonedge_raises_like_networkx():
+    nx = pytest.importorskip("networkx")
+    from dcr import sdrf
+    from oracle.cuda_flavour import bfc_cuda_dense
+    # K3,3: every edge has curvature -1.99e-8 (compiled dataflow), so the argmax falls back to (0,0) with C = 0 > -1
+    # and the reference's G.remove_edge(0, 0) raises NetworkXError
+    ei, n = toy_graphs()["k33"]
+    assert bfc_cuda_dense(dense_of(ei, n))["C"].max() <= 0
+    with pytest.raises(nx.NetworkXError):
+        sdrf.sdrf(ei, n, 2, True, -1.0, float("inf"), uniforms=np.array([0.5, 0.5]))
