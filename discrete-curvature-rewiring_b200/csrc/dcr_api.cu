@@ -20,15 +20,21 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return 100 + (int)e;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;  // B200
+    static int cache[MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+        cache[dev] = n;
     }
-    return n;
+    return cache[dev];
 }
 
 }  // namespace dcr

@@ -706,6 +706,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
                              void* ev_edge_begin, void* ev_edge_end, void* stream) {
     if (count <= 0 || n <= 0) return 0;
     if (count > 0xfffffff0LL) { set_error("dcr_bfc_paper: more than 2^32 edges per call"); return 1; }
+    if (n >= (1 << 30) - 1) { set_error("dcr_bfc_paper: node ids must fit 30 bits (table keys carry 2 tag bits)"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     const ScratchLayout L = scratch_layout(n, max_degree, count);
     if ((int64_t)L.total > scratch_bytes) {
@@ -749,7 +750,9 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     const int sms = sm_count();
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
     // heavy classes first: they own the long tail.  Persistent grids = SM count x resident CTAs per SM.
-    static bool attr_done = false;
+    static bool attr_done_dev[MAX_DEVICES] = {false};
+    const int dev = current_device();
+    bool& attr_done = attr_done_dev[dev];
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
     constexpr int mid_stream = 3 * heads_per_thread(MID_THREADS) * MID_THREADS + 8;
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
@@ -770,8 +773,11 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     // The class kernels are independent (disjoint edges, disjoint outputs).  They are launched on three streams
     // forked from `st` — heaviest class first — so that, as the persistent CTAs of one class run out of work, CTAs
     // of the next class take over the freed SMs instead of waiting for the slowest CTA (tail filling).
-    static cudaStream_t aux[2] = {nullptr, nullptr};
-    static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    static cudaStream_t aux_dev[MAX_DEVICES][2] = {};
+    static cudaEvent_t fork_dev[MAX_DEVICES] = {}, join_dev[MAX_DEVICES][2] = {};
+    cudaStream_t* aux = aux_dev[dev];
+    cudaEvent_t& ev_fork = fork_dev[dev];
+    cudaEvent_t* ev_join = join_dev[dev];
     if (!aux[0]) {
         for (int q = 0; q < 2; ++q) {
             DCR_CUDA(cudaStreamCreateWithFlags(&aux[q], cudaStreamNonBlocking));

@@ -23,6 +23,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define DCR_LAUNCH_CHECK() DCR_CUDA(cudaGetLastError())
 
+constexpr int MAX_DEVICES = 64;   // per-device host-side state (streams, function attributes) is indexed by ordinal
+int current_device();
 int sm_count();
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -246,7 +246,8 @@ static int make_tmap(CUtensorMap* tmap, const int8_t* base, int np) {
 
 static int launch_edge_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const int8_t* A8, const int32_t* rowptr,
                             const int32_t* blkpre, int n, int np, int32_t* out, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done_dev[MAX_DEVICES] = {false};
+    bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         DCR_CUDA(cudaFuncSetAttribute(tc_support_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_done = true;
