@@ -30,7 +30,29 @@ struct ScoreScratch {
 struct ScoreShared {   // block-shared state of one scoring call
     int axy, dx, dy, sx, sy, a2xy, sharp0, lam0;
     ClosingFirst first;      // closing formula up to the first fp32 store, for the unchanged degrees (d_x, d_y)
+    // aggregates of the base terms, so that a cell which patches only a few terms never re-walks all of them:
+    int cnt1, cnt2;          // #{base1 > 0}, #{base2 > 0}
+    int m1, i1, m1x;         // max base1, an index attaining it, max over the OTHER indices (-1 = none)
+    int m2, i2, m2x;         // same for base2
 };
+
+// (max, an index attaining it, max over the other indices, #positive) of arr[0..n) — warp-cooperative, every lane
+// returns the same values
+__device__ __forceinline__ void warp_top2(const int32_t* arr, int n, int lane, int& m, int& idx, int& mx, int& pos) {
+    m = -1; idx = -1; mx = -1; pos = 0;
+    for (int q = lane; q < n; q += 32) {
+        const int v = arr[q];
+        pos += v > 0;
+        if (v > m) { mx = m; m = v; idx = q; } else mx = max(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int om = __shfl_xor_sync(FULL, m, o), oi = __shfl_xor_sync(FULL, idx, o), ox = __shfl_xor_sync(FULL, mx, o);
+        if (om > m) { mx = max(m, ox); m = om; idx = oi; } else mx = max(mx, om);
+    }
+    pos = warp_sum(pos);
+    m = __shfl_sync(FULL, m, 0); idx = __shfl_sync(FULL, idx, 0); mx = __shfl_sync(FULL, mx, 0);
+}
 
 __device__ __forceinline__ int edge_slot(const GraphView& g, int a, int b) {
     return find_sorted(g.col, g.begin(a), g.degree(a), b);
@@ -42,6 +64,14 @@ __device__ __forceinline__ int warp_a2(const GraphView& g, const int32_t* supp, 
     if (a == b) return g.degree(a);
     const int s = edge_slot(g, a, b);
     if (s >= 0) return supp[s];
+    return warp_intersect_count(g, a, b, lane);
+}
+
+// A2[a,b] - A[a,b] with one adjacency search (the base term of bfc_cuda.py:127 / :133)
+__device__ __forceinline__ int warp_a2_minus_a(const GraphView& g, const int32_t* supp, int a, int b, int lane) {
+    if (a == b) return g.degree(a);
+    const int s = edge_slot(g, a, b);
+    if (s >= 0) return supp[s] - 1;
     return warp_intersect_count(g, a, b, lane);
 }
 
@@ -62,6 +92,9 @@ __device__ void score_prepare(const GraphView& g, const int32_t* supp, int x, in
         sh->a2xy = s >= 0 ? supp[s] : 0;   // only used multiplied by A[x,y]
         sh->sharp0 = 0;
         sh->lam0 = 0;
+        sh->cnt1 = sh->cnt2 = 0;
+        sh->m1 = sh->m1x = sh->m2 = sh->m2x = -1;
+        sh->i1 = sh->i2 = -1;
         sh->first.c32 = 0.0f;
         sh->first.dmax = 1.0;
         if (sh->dx > 0 && sh->dy > 0)
@@ -75,17 +108,30 @@ __device__ void score_prepare(const GraphView& g, const int32_t* supp, int x, in
     int cnt = 0, mx = 0;
     for (int q = warp; q < dy; q += nwarps) {    // T1 terms: z in N(y)
         const int z = g.col[sy + q];
-        const int b = warp_a2(g, supp, x, z, lane) - (z != x && edge_slot(g, x, z) >= 0 ? 1 : 0);
+        const int b = warp_a2_minus_a(g, supp, x, z, lane);
         if (lane == 0) { sc.base1[q] = b; cnt += b > 0; mx = max(mx, b); }
     }
     for (int p = warp; p < dx; p += nwarps) {    // T2 terms: z in N(x)
         const int z = g.col[sx + p];
-        const int b = warp_a2(g, supp, z, y, lane) - (z != y && edge_slot(g, z, y) >= 0 ? 1 : 0);
+        const int b = warp_a2_minus_a(g, supp, z, y, lane);
         if (lane == 0) { sc.base2[p] = b; cnt += b > 0; mx = max(mx, b); }
     }
-    if (lane == 0) {
-        if (cnt) atomicAdd(&sh->sharp0, cnt);
-        if (mx) atomicMax(&sh->lam0, mx);
+    (void)cnt; (void)mx;
+    __syncthreads();
+    if (warp < 2) {          // warp 0: aggregates of base1, warp 1 (or warp 0 again): aggregates of base2
+        for (int which = warp; which < 2; which += nwarps >= 2 ? 2 : 1) {
+            int m, idx, mxo, pos;
+            warp_top2(which == 0 ? sc.base1 : sc.base2, which == 0 ? dy : dx, lane, m, idx, mxo, pos);
+            if (lane == 0) {
+                if (which == 0) { sh->cnt1 = pos; sh->m1 = m; sh->i1 = idx; sh->m1x = mxo; }
+                else            { sh->cnt2 = pos; sh->m2 = m; sh->i2 = idx; sh->m2x = mxo; }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sh->sharp0 = sh->cnt1 + sh->cnt2;
+        sh->lam0 = max(0, max(sh->m1, sh->m2));
     }
     __syncthreads();
 }
@@ -118,6 +164,13 @@ __device__ __forceinline__ float score_cell_simple(const GraphView& g, const Sco
 }
 
 // One cell with x == i or y == j (warp-level; all lanes pass identical arguments).  Returns D[I,J].
+// With x == i the patches of bfc_cuda.py:113-124 read, for every z in N(y):  v(z) = base1(z) + A[j,z] - [z == j];
+// the T2 terms over N(x) are unchanged, and one extra T2 term appears at z = j.  So instead of re-walking all of
+// N(y) with a membership test per element, only the COMMON neighbours of j and y matter:
+//     #positive = cnt1 + #{w in N(j)∩N(y) : base1(w) = 0} - [j in N(y) and base1(j) = 1]
+//     max       = max( max base1 over z != j,  max over common w of base1(w) + 1,  base1(j) - 1 )
+// (base terms are >= 0 whenever A[x,y] = 1, and base1(j) >= 1 for j in N(y)).  y == j is the mirror image with
+// N(x), base2 and the extra T1 term at z = i.  All integer and exact.
 __device__ __forceinline__ float score_cell_warp(const GraphView& g, const int32_t* supp, const ScoreScratch& sc,
                                                  const ScoreShared* sh, int x, int y, int i, int j, int lane) {
     if (i == j || edge_slot(g, i, j) >= 0) return MASKED_D;
@@ -126,50 +179,60 @@ __device__ __forceinline__ float score_cell_warp(const GraphView& g, const int32
     if (din == 0 || dout == 0) return 0.0f;
     const int dmax = max(din, dout), dmin = min(din, dout);
     if (!sh->axy) return closing_value(dmax, dmin, 0, 0, 0, 0).c32;
-    const int dx = sh->dx, dy = sh->dy, sx = sh->sx, sy = sh->sy;
-    const int axi = (x == i) ? 0 : (edge_slot(g, x, i) >= 0);   // A[x,i]
-    const int ajy = (j == y) ? 0 : (edge_slot(g, j, y) >= 0);   // A[j,y]
-    int a2 = sh->a2xy;                                          // :99-103
-    if (x == i && ajy) a2 += 1; else if (y == j && axi) a2 += 1;
-    int cnt = 0, mx = 0;
-    for (int q = lane; q < dy; q += 32) {                       // z in N(y): A_z_y = 1
-        const int z = g.col[sy + q];
-        int v = sc.base1[q];
-        if (x == i) v += (z != j && edge_slot(g, j, z) >= 0);   // :119-120  A2_x_z += A[j,z]
-        if (z == j) v += axi;                                   // :123-124
-        if (x == i && z == j) v -= 1;                           // :115-116  A_x_z += 1
-        cnt += v > 0;
-        mx = max(mx, v);
+    // orient: `r` = the endpoint of (x,y) whose row is patched (y when i == x, x when j == y), `o` = the new
+    // neighbour on the other side (j resp. i); base/aggregates of that side in (base, cntP, mP, iP, mPx)
+    const bool rowA = (x == i);                    // class A: i == x, patch the N(y) terms with N(j)
+    const int r = rowA ? y : x, o = rowA ? j : i;
+    const int sr = rowA ? sh->sy : sh->sx, dr = rowA ? sh->dy : sh->dx;
+    const int32_t* base = rowA ? sc.base1 : sc.base2;
+    const int cntP = rowA ? sh->cnt1 : sh->cnt2, cntQ = rowA ? sh->cnt2 : sh->cnt1;
+    const int mP = rowA ? sh->m1 : sh->m2, iP = rowA ? sh->i1 : sh->i2, mPx = rowA ? sh->m1x : sh->m2x;
+    const int mQ = rowA ? sh->m2 : sh->m1;
+    const int so = g.begin(o), d_o = g.degree(o);
+    // common neighbours of o and r, located in r's row
+    int czero = 0, mmark = -1, ncommon = 0;
+    if (d_o <= dr) {
+        for (int t = lane; t < d_o; t += 32) {
+            const int q = find_sorted(g.col, sr, dr, g.col[so + t]);
+            if (q >= 0) { const int b = base[q - sr]; ++ncommon; czero += (b == 0); mmark = max(mmark, b + 1); }
+        }
+    } else {
+        for (int q = lane; q < dr; q += 32) {
+            if (find_sorted(g.col, so, d_o, g.col[sr + q]) >= 0) {
+                const int b = base[q]; ++ncommon; czero += (b == 0); mmark = max(mmark, b + 1);
+            }
+        }
     }
-    for (int p = lane; p < dx; p += 32) {                       // z in N(x): A_x_z = 1
-        const int z = g.col[sx + p];
-        int v = sc.base2[p];
-        if (z == i) v += ajy;                                   // :117-118
-        if (y == j) v += (z != i && edge_slot(g, z, i) >= 0);   // :121-122  A2_z_y += A[z,i]
-        if (z == i && y == j) v -= 1;                           // :113-114  A_z_y += 1
-        cnt += v > 0;
-        mx = max(mx, v);
+    czero = warp_sum(czero);
+    ncommon = warp_sum(ncommon);
+    mmark = warp_max(mmark);
+    const int po = find_sorted(g.col, sr, dr, o);            // is o itself a neighbour of r (A[j,y] resp. A[x,i])?
+    const int aor = po >= 0;
+    int cnt = cntP + czero, mx = max(mmark, mQ);
+    if (po >= 0) {
+        const int b = base[po - sr];                         // >= 1: r's partner endpoint is a common neighbour
+        cnt -= (b == 1);
+        mx = max(mx, b - 1);
+        mx = max(mx, (po - sr) == iP ? mPx : mP);
+    } else {
+        mx = max(mx, mP);
     }
-    cnt = warp_sum(cnt);
-    mx = warp_max(mx);
-    // the one z outside N(x) ∪ N(y) that the patched A makes non-zero
-    if (y == j && x != i) {          // z == i: A_z_y = 0 + 1 ; T1 = A2[x,i] (+0) - A[x,i]
-        const int v = warp_a2(g, supp, x, i, lane) - axi;
-        cnt += v > 0;
-        mx = max(mx, v);
-    }
-    if (x == i && y != j) {          // z == j: A_x_z = 0 + 1 ; T2 = A2[j,y] - A[j,y]
-        const int v = warp_a2(g, supp, j, y, lane) - ajy;
-        cnt += v > 0;
-        mx = max(mx, v);
-    }
-    return closing_value(dmax, dmin, a2, 1, cnt, mx).c32;
+    cnt += cntQ;
+    // the one z outside N(x) ∪ N(y) that the patched A makes non-zero: z = o, value A2[o,r] - A[o,r]
+    const int extra = (po >= 0 ? supp[po] : ncommon) - aor;
+    cnt += extra > 0;
+    mx = max(mx, extra);
+    const int a2 = sh->a2xy + aor;                           // bfc_cuda.py:99-103
+    return closing_value(dmax, dmin, a2, 1, cnt, max(mx, 0)).c32;
 }
 
 // Step 3 for the whole matrix.  `out(I, J, d)` receives every cell value.
+// `only_I` / `only_J` >= 0: the caller knows that x (resp. y) occurs exactly once in the list, at that position
+// (the SDRF loop appends it last, sdrf_cuda_bfc.py:45-46) — saves every thread a walk over the lists.
 template <class NbI, class NbJ, class Out>
 __device__ void score_cells(const GraphView& g, const int32_t* supp, int x, int y, NbI nbI, int n_i, NbJ nbJ,
-                            int n_j, const ScoreScratch& sc, const ScoreShared* sh, Out out) {
+                            int n_j, const ScoreScratch& sc, const ScoreShared* sh, Out out, int only_I = -1,
+                            int only_J = -1) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const long long cells = (long long)n_i * n_j;
@@ -180,14 +243,14 @@ __device__ void score_cells(const GraphView& g, const int32_t* supp, int x, int 
         out(I, J, score_cell_simple(g, sc, sh, x, y, i, j, I, J));
     }
     // rows with i == x and columns with j == y: one warp per cell
-    for (int I = 0; I < n_i; ++I) {
+    for (int I = (only_I >= 0 ? only_I : 0); I < (only_I >= 0 ? only_I + 1 : n_i); ++I) {
         if (nbI(I) != x) continue;
         for (int J = warp; J < n_j; J += nwarps) {
             const float d = score_cell_warp(g, supp, sc, sh, x, y, x, nbJ(J), lane);
             if (lane == 0) out(I, J, d);
         }
     }
-    for (int J = 0; J < n_j; ++J) {
+    for (int J = (only_J >= 0 ? only_J : 0); J < (only_J >= 0 ? only_J + 1 : n_j); ++J) {
         if (nbJ(J) != y) continue;
         for (int I = warp; I < n_i; I += nwarps) {
             if (nbI(I) == x) continue;   // done above

@@ -31,6 +31,22 @@ constexpr int SDRF_WARPS = SDRF_THREADS / 32;
 constexpr uint32_t IMP_MASKED = 0xffffffffu;   // bit pattern marking a masked cell in the improvement matrix
 constexpr int STATUS_TOO_MANY_CANDIDATES = DCR_SDRF_TOO_MANY_CANDIDATES;
 
+// Optional phase timers (build with -DDCR_SDRF_PROFILE): cycles per phase summed over the iterations of a launch,
+// written to a device array read back with dcr_sdrf_phase_cycles().  Compiled out of the product library.
+#ifdef DCR_SDRF_PROFILE
+__device__ unsigned long long g_sdrf_phase[16];
+#define SDRF_TICK(slot)                                                         \
+    do {                                                                        \
+        if (threadIdx.x == 0) {                                                 \
+            const long long now__ = clock64();                                  \
+            g_sdrf_phase[slot] += (unsigned long long)(now__ - tick__);         \
+            tick__ = now__;                                                     \
+        }                                                                       \
+    } while (0)
+#else
+#define SDRF_TICK(slot) do { } while (0)
+#endif
+
 struct SdrfDev {
     int n;
     int cap_total;        // arena slots
@@ -162,6 +178,36 @@ __device__ double block_exscan_d(double v, double* total, Reduce* r) {
     return __dadd_rn(off, excl);
 }
 
+// exclusive prefixes of a (count, fp64 sum) pair over the threads, plus both totals: one primitive, two barriers
+__device__ void block_exscan_pair(long long c, double d, long long* c_off, double* d_off, long long* c_tot,
+                                  double* d_tot, Reduce* r) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long ci = c;
+    double di = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long tc = __shfl_up_sync(FULL, ci, o);
+        const double td = __shfl_up_sync(FULL, di, o);
+        if (lane >= o) { ci += tc; di = __dadd_rn(di, td); }
+    }
+    double dex = __shfl_up_sync(FULL, di, 1);
+    if (lane == 0) dex = 0.0;
+    if (lane == 31) { r->l[warp] = ci; r->d[warp] = di; }
+    __syncthreads();
+    long long co = 0, ct = 0;
+    double dof = 0.0, dt = 0.0;
+    for (int w = 0; w < SDRF_WARPS; ++w) {
+        if (w < warp) { co += r->l[w]; dof = __dadd_rn(dof, r->d[w]); }
+        ct += r->l[w];
+        dt = __dadd_rn(dt, r->d[w]);
+    }
+    __syncthreads();
+    *c_off = co + ci - c;
+    *d_off = __dadd_rn(dof, dex);
+    *c_tot = ct;
+    *d_tot = dt;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // arena row edits (block-cooperative; arguments are block-uniform)
 // ------------------------------------------------------------------------------------------------------------
@@ -173,6 +219,7 @@ struct LoopShared {
     int n_i, n_j;
     long long n_cand;
     long long chosen_flat;
+    long long found_flat;     // first flat index whose CDF exceeds u (atomicMin over the threads)
     int choice, k, l;
     int status, stop, can_add, do_remove;
     double below, above;      // normalised CDF just below / at the chosen candidate
@@ -221,6 +268,7 @@ __device__ bool row_reserve(const SdrfDev& S, int v, LoopShared* sh) {
         S.c32[nstart + t] = S.c32[start + t];
         S.owner[nstart + t] = v;
         S.owner[start + t] = -1;
+        S.c32[start + t] = 0.0f;          // free slots hold 0: the argmin/argmax scan reads values only
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -269,6 +317,7 @@ __device__ void row_delete(const SdrfDev& S, int v, int key, LoopShared* sh) {
     shift_left(S.ord, opos + 1, start + len);
     if (threadIdx.x == 0) {
         S.owner[start + len - 1] = -1;
+        S.c32[start + len - 1] = 0.0f;    // free slots hold 0
         S.rlen[v] = len - 1;
     }
     __syncthreads();
@@ -381,20 +430,40 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
     if (tid == 0) { sh.status = DCR_SDRF_OK; sh.stop = 0; }
     __syncthreads();
 
+#ifdef DCR_SDRF_PROFILE
+    long long tick__ = clock64();
+#endif
     for (; it < loops; ++it) {
         // ---- 1. argmin / argmax of C_t (sdrf_cuda_bfc.py:40-42, :80-82) ---------------------------------
+        // Pass 1 reads only the curvatures (free slots hold 0, which is neither < 0 nor > 0) and reduces the two
+        // extreme VALUES; pass 2 visits the few slots that attain them and reduces the first row-major key.
         const int top = S.scalars[0];
-        Best bmin{0.0f, ~0ull}, bmax{0.0f, ~0ull};   // bmax holds the NEGATED value
+        float vmin = 0.0f, vmax = 0.0f;
         for (int s = tid; s < top; s += SDRF_THREADS) {
-            const int o = S.owner[s];
-            if (o < 0) continue;
             const float v = S.c32[s];
-            const unsigned long long key = ((unsigned long long)(unsigned)o << 32) | (unsigned)S.col[s];
-            if (v < 0.0f) bmin = best_of(bmin, Best{v, key});
-            if (v > 0.0f) bmax = best_of(bmax, Best{-v, key});
+            vmin = fminf(vmin, v);
+            vmax = fmaxf(vmax, v);
         }
-        bmin = block_best(bmin, &sh.red);
-        bmax = block_best(bmax, &sh.red);
+        {
+            Best a = block_best(Best{vmin, 0ull}, &sh.red);
+            Best b = block_best(Best{-vmax, 0ull}, &sh.red);
+            vmin = a.v;
+            vmax = -b.v;
+        }
+        Best bmin{0.0f, ~0ull}, bmax{0.0f, ~0ull};   // bmax holds the NEGATED value
+        if (vmin < 0.0f || vmax > 0.0f) {
+            unsigned long long kmin = ~0ull, kmax = ~0ull;
+            for (int s = tid; s < top; s += SDRF_THREADS) {
+                const float v = S.c32[s];
+                if ((v == vmin && vmin < 0.0f) || (v == vmax && vmax > 0.0f)) {
+                    const unsigned long long key = ((unsigned long long)(unsigned)S.owner[s] << 32) | (unsigned)S.col[s];
+                    if (v == vmin && vmin < 0.0f) kmin = min(kmin, key);
+                    if (v == vmax && vmax > 0.0f) kmax = min(kmax, key);
+                }
+            }
+            bmin = block_best(Best{vmin < 0.0f ? vmin : 0.0f, kmin}, &sh.red);
+            bmax = block_best(Best{vmax > 0.0f ? -vmax : 0.0f, kmax}, &sh.red);
+        }
         if (tid == 0) {
             sh.have_min = bmin.v < 0.0f;
             sh.x = sh.have_min ? (int)(bmin.key >> 32) : 0;
@@ -405,6 +474,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             sh.yr = sh.have_max ? (int)(bmax.key & 0xffffffffu) : 0;
             sh.cmax = sh.have_max ? -bmax.v : 0.0f;
             sh.can_add = 1; sh.do_remove = 0; sh.k = -1; sh.l = -1; sh.choice = -1; sh.chosen_flat = -1;
+            sh.found_flat = 0x7fffffffffffffffLL;
             sh.n_i = S.rlen[sh.x] + 1;
             sh.n_j = S.rlen[sh.y] + 1;
         }
@@ -417,6 +487,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             __syncthreads();
             break;
         }
+        SDRF_TICK(0);   // argmin/argmax
         // ---- 2. candidate matrix in networkx order (:45-54) and improvements (:57-62) ------------------
         const int ox = S.rstart[x], oy = S.rstart[y];
         auto nbI = [=](int I) { return I < n_i - 1 ? S.ord[ox + I] : x; };
@@ -427,17 +498,34 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             uint32_t* imp = S.imp;
             score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, [=](int I, int J, float d) {
                 imp[(long long)I * n_j + J] = (d == MASKED_D) ? IMP_MASKED : __float_as_uint(__fsub_rn(d, cxy));
-            });
+            }, n_i - 1, n_j - 1);
         }
         __syncthreads();
+        SDRF_TICK(1);   // scoring
         // ---- 3. selection ------------------------------------------------------------------------------
         // thread t owns the contiguous flat range [t*L, (t+1)*L): counts and prefix sums follow candidate order
         const long long L = (cells + SDRF_THREADS - 1) / SDRF_THREADS;
         const long long f_lo = min(cells, (long long)tid * L), f_hi = min(cells, f_lo + L);
+        // one pass: candidate count and (finite tau) the softmax weights exp(a*tau) of softmax.py:9
+        const bool forced = (it == 0 && forced_choice >= 0);
+        const bool weigh = !tau_inf;
         long long my_cnt = 0;
-        for (long long f = f_lo; f < f_hi; ++f) my_cnt += S.imp[f] != IMP_MASKED;
-        long long n_cand;
-        const long long my_off = block_exscan_ll(my_cnt, &n_cand, &sh.red);
+        double local = 0.0;
+        int bad = 0;
+        for (long long f = f_lo; f < f_hi; ++f) {
+            const uint32_t bits = S.imp[f];
+            if (bits == IMP_MASKED) continue;
+            ++my_cnt;
+            if (weigh) {
+                const double e = exp(__dmul_rn((double)__uint_as_float(bits), tau));
+                if (!(e <= 1.7976931348623157e308)) bad = 1;   // inf or NaN
+                local = __dadd_rn(local, e);
+            }
+        }
+        long long n_cand, my_off;
+        double total, carry;
+        block_exscan_pair(my_cnt, local, &my_off, &carry, &n_cand, &total, &sh.red);
+        const int nbad = __syncthreads_or(bad);
         if (tid == 0) sh.n_cand = n_cand;
         if (n_cand > 0) {
             if (draws >= n_uniforms) {
@@ -446,7 +534,6 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
                 break;
             }
             const double u = uniforms[draws];
-            const bool forced = (it == 0 && forced_choice >= 0);
             if (forced) {
                 if (forced_choice >= my_off && forced_choice < my_off + my_cnt) {
                     long long c = my_off;
@@ -481,22 +568,10 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
                 __syncthreads();
             } else {
                 // softmax.py:9-10 + np.random.choice: p = exp(a*tau)/sum; first index whose normalised CDF > u
-                double local = 0.0;
-                int bad = 0;
-                for (long long f = f_lo; f < f_hi; ++f) {
-                    const uint32_t bits = S.imp[f];
-                    if (bits == IMP_MASKED) continue;
-                    const double e = exp(__dmul_rn((double)__uint_as_float(bits), tau));
-                    if (!(e <= 1.7976931348623157e308)) bad = 1;   // inf or NaN
-                    local = __dadd_rn(local, e);
-                }
-                double total;
-                const double carry = block_exscan_d(local, &total, &sh.red);
-                const long long nbad = block_sum_ll(bad, &sh.red);
-                if (nbad > 0 || total == 0.0 || !(total <= 1.7976931348623157e308)) {
+                if (nbad != 0 || total == 0.0 || !(total <= 1.7976931348623157e308)) {
                     // exp overflow -> inf/inf = NaN, all-underflow -> 0/0 = NaN (numpy: "probabilities contain
                     // NaN"); a finite-term sum that overflows gives p = 0 everywhere ("do not sum to 1")
-                    if (tid == 0) sh.status = (nbad > 0 || total == 0.0) ? DCR_SDRF_PROB_NAN : DCR_SDRF_PROB_SUM;
+                    if (tid == 0) sh.status = (nbad != 0 || total == 0.0) ? DCR_SDRF_PROB_NAN : DCR_SDRF_PROB_SUM;
                     __syncthreads();
                     break;
                 }
@@ -518,9 +593,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
                     }
                     ++c;
                 }
-                Best b{found < cells ? 0.0f : 1.0f, (unsigned long long)found};
-                b = block_best(b, &sh.red);
-                if (b.v == 0.0f && (long long)b.key == found) {
+                if (found < cells) atomicMin(&sh.found_flat, found);
+                __syncthreads();
+                if (found < cells && sh.found_flat == found) {
                     sh.chosen_flat = found;
                     sh.choice = (int)found_c;
                     sh.below = below;
@@ -553,6 +628,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             if (tid == 0) { sh.can_add = 0; if (!remove_edges) sh.stop = 1; }   // :74-77
         }
         __syncthreads();
+        SDRF_TICK(2);   // selection
         // ---- removal decision on the SAME C_t (:79-91) --------------------------------------------------
         if (tid == 0 && remove_edges && !sh.stop) {
             if (sh.cmax > bound32) {                   // fp32 compare: torch casts the Python float (:83)
@@ -578,7 +654,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             }
             if (tid == 0) S.scalars[1] += 2;
             __syncthreads();
+            SDRF_TICK(3);   // insert rows
             toggle_supports(S, g, k, l, +1, &dirty_count, &sh);
+            SDRF_TICK(4);   // supports + dirty (add)
         }
         if (sh.do_remove) {                             // :84-88
             const int xr = sh.xr, yr = sh.yr;
@@ -588,6 +666,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             if (tid == 0) S.scalars[1] -= 2;
             __syncthreads();
         }
+        SDRF_TICK(5);   // removal: supports + delete rows
         // ---- 5. refresh the curvature of the dirty edges ----------------------------------------------
         const int nd = min(dirty_count, S.dirty_cap);
         if (dirty_count > S.dirty_cap) {
@@ -612,6 +691,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
                 S.flag[s] = 0;
             }
         }
+        SDRF_TICK(6);   // refresh
         // ---- 6. log ------------------------------------------------------------------------------------
         if (tid == 0) {
             int32_t* rec = log + (long long)it * DCR_SDRF_LOG_INTS;
@@ -829,3 +909,14 @@ extern "C" int dcr_sdrf_export(dcr_sdrf* s, int32_t* rowptr, int32_t* order_out,
     DCR_LAUNCH_CHECK();
     return 0;
 }
+
+#ifdef DCR_SDRF_PROFILE
+extern "C" int dcr_sdrf_phase_cycles(unsigned long long* out_host, int reset) {
+    if (cudaMemcpyFromSymbol(out_host, dcr::g_sdrf_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long zero[16] = {0};
+        if (cudaMemcpyToSymbol(dcr::g_sdrf_phase, zero, sizeof(zero)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
