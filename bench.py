@@ -451,7 +451,7 @@ def run_ours(args):
         ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
         checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
 
-    launches_per_step = 6 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + 1   # plan(6), edge classes, value, unshard
+    launches_per_step = 6 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + (1 if world > 1 else 0)   # plan(6), edge classes, value, unshard
     line = {
         "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -38,10 +38,11 @@ class ShardedPaperBFC:
         return bfc.paper_flavour(self.csr, rank=self.rank, world=self.world, ws=self.ws, events=events)
 
     def gather(self):
-        if self.world == 1:
-            self.gathered.copy_(self.ws.block)
-        else:
-            dist.all_gather_into_tensor(self.gathered, self.ws.block, group=self.group)
+        if self.world == 1:     # one rank: the compact shard IS the full result, already in edge order
+            ws, e = self.ws, self.n_edges
+            return {"tri": ws.tri[:e], "sq_i": ws.sq_i[:e], "sq_j": ws.sq_j[:e], "gamma": ws.gamma[:e],
+                    "bfc": ws.bfc[:e]}
+        dist.all_gather_into_tensor(self.gathered, self.ws.block, group=self.group)
         return bfc.unshard(self.gathered, self.world, self.chunk, self.n_edges)
 
     def run(self, events=None):
