@@ -182,7 +182,7 @@ __device__ __forceinline__ float score_cell_warp(const GraphView& g, const int32
     // orient: `r` = the endpoint of (x,y) whose row is patched (y when i == x, x when j == y), `o` = the new
     // neighbour on the other side (j resp. i); base/aggregates of that side in (base, cntP, mP, iP, mPx)
     const bool rowA = (x == i);                    // class A: i == x, patch the N(y) terms with N(j)
-    const int r = rowA ? y : x, o = rowA ? j : i;
+    const int o = rowA ? j : i;                    // (r = y when i == x, r = x when j == y)
     const int sr = rowA ? sh->sy : sh->sx, dr = rowA ? sh->dy : sh->dx;
     const int32_t* base = rowA ? sc.base1 : sc.base2;
     const int cntP = rowA ? sh->cnt1 : sh->cnt2, cntQ = rowA ? sh->cnt2 : sh->cnt1;
