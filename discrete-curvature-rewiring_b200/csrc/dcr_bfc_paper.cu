@@ -8,24 +8,29 @@
 //   gamma     = max over squares of |N(k) ∩ M_j| resp. |N(m) ∩ M_i|           (:36-37; the "-1" removes i / j)
 // i.e. everything is a function of cnt(m) = |N(m) ∩ M_i| for m in M_j and cnt(k) = |N(k) ∩ M_j| for k in M_i.
 //
-// Mapping to the GPU.  One TEAM per edge — a warp for edges with d_i + d_j <= 512, a whole CTA above that:
-//   1. the team builds ONE open-addressing hash table in shared memory holding N(a) ∪ N(b) \ {a,b}, each key
-//      tagged 1 (only in N(a)), 2 (only in N(b)) or 3 (both = triangle node); #tag-3 keys = #triangles.
-//      (a,b) = (i,j) or (j,i): b is the endpoint whose 2-hop lists are CHEAPER to stream (smaller S_b - d_a);
-//   2. ONE scan: for every m with tag 2 the neighbour list N(m) is streamed.  Every match (k in N(m) with tag 1)
-//      is an edge of the bipartite graph M_a–M_b, and it is counted TWICE: in a per-list counter (-> cnt(m)) and
-//      in a 16-bit counter attached to k's table slot (-> cnt(k)); so the expensive side is never streamed;
-//   3. a sweep over the table slots turns the slot counters into (#squares, max) of endpoint a, the per-list
-//      counters give those of endpoint b.
-// The lists of 32 heads at a time are processed as ONE flat stream (prefix sums of the list lengths in shared
-// memory, lane f handles flat element f): coalesced where lists are long, and no idle lanes where they are short
-// — half of the 2-hop lists of a power-law graph have fewer than 20 entries.
+// Mapping to the GPU (v11).  (a,b) = (i,j) or (j,i): b is the endpoint whose 2-hop lists are CHEAPER to stream
+// (smaller S_b - d_a); a is the TESTED endpoint.  Edges are grouped by their tested endpoint (device counting sort),
+// so that the membership structures of N(a) — an open-addressing hash table and, in front of it, a hashed bitmap —
+// are built once per group and READ-ONLY afterwards:
+//   * LIGHT edges (<= HEAVY_STREAM streamed entries; 98.8 % of the edges and 80 % of the stream of the arxiv-shaped
+//     graph): ONE WARP PER EDGE.  For d_a <= 128 the table is private to the warp and kept while consecutive edges
+//     share a; above that the CTA builds one table for a run of edges of the same a and its warps pull edges from
+//     a shared counter.  The warp streams the lists N(m), m a pure neighbour of b, as ONE flat stream: the (begin,
+//     prefix) of up to 32 lists live in the lanes' registers, the owner of flat element f is found with one
+//     warp-wide OR-reduction of the "a list starts here" bits plus a popc, and the list data come through shuffles —
+//     no per-element search loop, no shared-memory prefix arrays.  An element k is a bipartite edge (m,k) iff it is
+//     in N(a) (bitmap, then exact probe), is not b and is not a common neighbour (binary search in the sorted row
+//     of b — only the few elements that passed the table reach it).  Matches bump the list's counter (-> cnt(m))
+//     and a small per-warp hash keyed by the table slot (-> cnt(k)): #squares and gamma of BOTH endpoints from one
+//     scan.  A warp whose match hash fills up defers the edge to the CTA-team path (overflow list).
+//   * HEAVY edges (hub–hub, up to 2.5e5 streamed entries each) and every edge with d_a > 16384: one CTA per edge
+//     (the v10 CTA-team kernel below: slot counters in the table, CTA-wide flat stream cut into equal warp slices).
 // Global traffic is at most the algorithmic gather of SURVEY.md §8d (which charges BOTH sides' 2-hop lists): the
 // two endpoint lists once and the cheaper side's 2-hop lists once per edge.  The CSR of the benchmark graphs is
 // L2-resident, so the kernel is bound by instruction issue / L1 gathers / shared-memory probes, not by DRAM.
-// Edges are bucketed by class and by log2(work) on the device (heavy first) and teams pull edges from a global
-// counter, so power-law hubs do not serialise the tail.  Grids are persistent: a multiple of the SM count.
+// Grids are persistent (multiples of the SM count) and pull work from global counters.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "dcr_common.cuh"
 
@@ -33,55 +38,86 @@ namespace dcr {
 
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
-// Edge classes by the degree d_a of the TESTED endpoint (the one whose neighbour set goes into the hash table):
-//   class 0  d_a <= 128    warp team,            512-slot table per warp  (load factor <= 1/4), 48 warps per SM
-//   class 1  d_a <= 1024   128-thread CTA team,  2048-slot table          (load factor <= 1/2), 8 CTAs per SM
-//   class 2  d_a <= 16384  1024-thread CTA team, 32768-slot table         (load factor <= 1/2), 1 CTA per SM
-//   class 3  larger        1024-thread CTA team, table in global memory (L2)
-constexpr int N_CLASSES = 4;
+// Edge classes.  d_a = degree of the TESTED endpoint (the one whose neighbour set goes into the hash table).
+//   L0  d_a <= 128, stream <= COOP_G1    warp per edge, warp-private 256-slot table
+//   G1  d_a <= 1024                      CTA-shared 2048-slot table, 8 warps:  warp per edge; CTA per edge above COOP_G1
+//   G2  d_a <= 16384                     CTA-shared 32768-slot table, 16 warps: warp per edge; CTA per edge above COOP_G2
+//   X   d_a > 16384                      1024-thread CTA team, table and 32-bit counters in global memory (L2)
+//   dense mode (n <= DENSE_MAX_N): L0 as above, everything else in ONE group class (G1 id) whose membership
+//   structure is an exact bitmap over all node ids in shared memory — no table, no false positives, any degree
+//   (overflow list: light / cooperative edges whose match hash filled up -> the 1024-thread CTA-team kernel)
+enum { CL_L0 = 0, CL_G1, CL_G2, CL_X, N_CLASSES, CL_OVF = N_CLASSES };
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
-#ifndef DCR_WARP_SLOTS
-#define DCR_WARP_SLOTS 512
+#ifndef DCR_COOP_G1
+#define DCR_COOP_G1 24576
 #endif
-#ifndef DCR_WARP_CTAS
-#define DCR_WARP_CTAS 6
+#ifndef DCR_COOP_G2
+#define DCR_COOP_G2 24576
 #endif
-#ifndef DCR_MID_SLOTS
-#define DCR_MID_SLOTS 2048
+constexpr long long COOP_G1 = DCR_COOP_G1, COOP_G2 = DCR_COOP_G2;
+// Inside the range of one tested endpoint the edges are ordered by size bucket, heaviest first (cooperative edges,
+// then stream > 2048, > 512, the rest): warps that pull edges of a run from a shared counter then finish together.
+constexpr int N_SIZE_BUCKETS = 4, N_SLOTS = N_SIZE_BUCKETS + 1;   // slot 4: edges of an L0 vertex promoted to G1
+constexpr long long SIZE_B1 = 2048, SIZE_B2 = 512;
+// A group (all edges with the same tested endpoint) of a group class is cut into R = ceil(count / RUN_EDGES) runs;
+// the edge with rank s in the size order goes to run s mod R, so EVERY run holds the same mix — heaviest first,
+// lightest last — and the warps of a CTA that pull its edges from a shared counter finish together.
+constexpr int RUN_EDGES = 64;
+#ifndef DCR_COOP_SLICE
+#define DCR_COOP_SLICE 512
 #endif
-#ifndef DCR_MID_CTAS
-#define DCR_MID_CTAS 8
-#endif
-constexpr int WARP_SLOTS = DCR_WARP_SLOTS, WARP_CTAS_PER_SM = DCR_WARP_CTAS;
-constexpr int WARP_TEAM_WARPS = 8;           // warps (teams) per CTA in the warp-team kernel
-constexpr int MID_SLOTS = DCR_MID_SLOTS, MID_THREADS = 128, MID_CTAS_PER_SM = DCR_MID_CTAS;
+constexpr int COOP_SLICE = DCR_COOP_SLICE;        // cooperative edges: flat-stream elements per work item of a warp
+__host__ __device__ inline int run_table_of(int cls) { return cls == CL_G2 ? 1 : 0; }
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
 __host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 1 : 4; }   // CTA stream state must fit beside the table
 // Membership pre-filter: a hashed bitmap of N(va) (bit index = node id mod B).  Almost every streamed element is NOT
 // a neighbour of va, and the bitmap says so with one shared-memory load and no loop; only the few elements whose bit
 // is set (true members + d_a/B false positives) go on to the exact hash probe.
-constexpr int WARP_BITS = 4096, MID_BITS = 32768, BIG_BITS = 131072, GLOBAL_BITS = 1048576;
+constexpr int BIG_BITS = 131072, GLOBAL_BITS = 1048576;
 __host__ __device__ constexpr int filter_bits(int team, bool global_table) {
-    return global_table ? GLOBAL_BITS : (team == 32 ? WARP_BITS : (team >= 1024 ? BIG_BITS : MID_BITS));
+    return global_table ? GLOBAL_BITS : BIG_BITS;
 }
-constexpr int STREAM_INTS = 100;             // per-warp flat-stream state: pre[33] + beg[32] + cnt[32] (+pad)
-constexpr int BUCKETS_PER_CLASS = 48;
-constexpr int UNROLL = 4;
+#ifndef DCR_UNROLL
+#define DCR_UNROLL 4
+#endif
+constexpr int UNROLL = DCR_UNROLL;
+// light path geometry
+#ifndef DCR_L0_CTAS
+#define DCR_L0_CTAS 6
+#endif
+#ifndef DCR_G1_CTAS
+#define DCR_G1_CTAS 4
+#endif
+#ifndef DCR_L0_GRAB
+#define DCR_L0_GRAB 4
+#endif
+#ifndef DCR_FLAT_UNROLL
+#define DCR_FLAT_UNROLL 2
+#endif
+#ifndef DCR_LONG_LIST
+#define DCR_LONG_LIST 64
+#endif
+constexpr int LONG_LIST = DCR_LONG_LIST;     // lists at least this long are streamed one at a time by the whole warp
+constexpr int L0_SLOTS = 256, L0_BITS = 4096, L0_CAP = 256, L0_WARPS = 8, L0_CTAS_PER_SM = DCR_L0_CTAS;
+constexpr int G1_SLOTS = 2048, G1_BITS = 32768, G1_CAP = 512, G1_WARPS = 8, G1_CTAS_PER_SM = DCR_G1_CTAS;
+constexpr int G2_SLOTS = 32768, G2_BITS = 131072, G2_CAP = 256, G2_WARPS = 16;
+// dense mode: exact bitmap of N(va) over all node ids; 8 warps and >= 4 CTAs per SM while n <= DENSE_MAX_N
+#ifndef DCR_GD_CTAS
+#define DCR_GD_CTAS 4
+#endif
+constexpr int GD_CAP = 256, GD_WARPS = 8, GD_CTAS_PER_SM = DCR_GD_CTAS, DENSE_MAX_N = 262144;
+// per-warp scratch (ints): beg[32] | len[32] | lcnt[32] | n_distinct + pad
+constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 96, WSTATE_INTS = 100;
+constexpr int TB_WORDS = 32;                 // per-warp triangle bitmap: 1024 bits
 
-// Ordering of the work.  Class 0 (warp teams): bucketed by log2(work), heavy first.  Classes 1-3 (CTA teams):
-// grouped by the tested endpoint va (counting sort over vertex ids), so that a CTA meets runs of edges with the
-// same va and re-uses the hash table of N(va) instead of rebuilding it per edge.
-constexpr int BUCKET_TRIVIAL = 255, BUCKET_GROUPED = 200, BUCKET_EXCEPTION = 204;
 struct PaperPlan {           // lives at the head of the scratch buffer
-    unsigned int hist[BUCKETS_PER_CLASS];        // class-0 buckets
-    unsigned int cursor[BUCKETS_PER_CLASS];
-    unsigned int bucket_off[BUCKETS_PER_CLASS + 1];
-    unsigned int grouped[N_CLASSES + 1];         // [c] = #edges of class c (1..3) grouped by va, [4] = exceptions
-    unsigned int exc_cursor;
-    unsigned int group_cursor[N_CLASSES];        // range reservation inside classes 1-3
+    unsigned int grouped[N_CLASSES + 1];         // [c] = #edges of class c
+    unsigned int group_cursor[N_CLASSES];        // range reservation inside the classes
     unsigned int class_begin[N_CLASSES + 1];
-    unsigned int next[N_CLASSES];                // work-stealing counters
-    unsigned int pad[2];
+    unsigned int next[N_CLASSES + 1];            // work-stealing counters ([CL_OVF] = overflow list)
+    unsigned int n_runs[2];                      // run tables of the group classes (G1, G2)
+    unsigned int ovf_count;                      // edges deferred to the CTA-team path
+    unsigned int pad[3];
 };
 
 struct PaperArgs {
@@ -97,12 +133,18 @@ struct PaperArgs {
     double* out_bfc;
     PaperPlan* plan;
     const int64_t* node_s;
-    uint8_t* bucket;       // [count]
-    uint32_t* order;       // [count] local indices t: class 0 by bucket, classes 1-3 by tested endpoint
-    uint32_t* va_cnt;      // [n] #grouped edges whose tested endpoint is v; after the scan: first position in `order`
-    uint32_t* va_cur;      // [n] fill cursors
+    uint8_t* bucket;       // [count] class of local edge t (BUCKET_TRIVIAL: nothing to do)
+    uint32_t* order;       // [count] local indices t, class by class, grouped by tested endpoint inside a class
+    uint32_t* ova;         // [count] tested endpoint of order[pos]; bit 31: cooperative (CTA per edge)
+    uint32_t* ovf_order;   // [count] overflow list (local indices t)
+    uint32_t* va_cnt;      // [N_SLOTS][n] #edges per (size bucket | promoted, tested endpoint); then: rank offset inside the group
+    uint32_t* va_cur;      // [N_SLOTS][n] fill cursors
+    uint32_t* grp;         // [4][n] (start, count) of the vertex's own group and of its promoted group in `order`
+    uint2* runs;           // [2][max_runs] (first position, length) of the runs of the group classes
+    uint32_t max_runs;
     int n;
-    uint32_t* gtables;     // class-2 tables in global memory, gslots per CTA
+    int dense;             // 1: n is small enough for an exact bitmap of N(va) in shared memory (classes L0 + G1 only)
+    uint32_t* gtables;     // class-X tables in global memory, gslots per CTA
     uint32_t gslots;
 };
 
@@ -179,14 +221,41 @@ __global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t*
     if (lane == 0) node_s[v] = s;
 }
 
-__device__ __forceinline__ int class_of_degree(int da) {
-    return da <= CLASS_DA0 ? 0 : (da <= CLASS_DA1 ? 1 : (da <= CLASS_DA2 ? 2 : 3));
+constexpr int BUCKET_TRIVIAL = 255;
+
+__device__ __forceinline__ int degree_class(int da, int dense) {
+    if (dense) return da <= CLASS_DA0 ? CL_L0 : CL_G1;       // the dense group kernel takes any degree
+    return da <= CLASS_DA0 ? CL_L0 : (da <= CLASS_DA1 ? CL_G1 : (da <= CLASS_DA2 ? CL_G2 : CL_X));
+}
+
+// (tested endpoint, its degree, the other degree, stream size) of an edge, and where the plan puts it
+struct EdgeRole { int va, da, db, cls, slot; bool coop; long long stream; };
+__device__ __forceinline__ EdgeRole edge_role(const PaperArgs& a, int i, int j, int di, int dj) {
+    const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
+    const bool swapped = cb < ca;                                      // stream i's side, test j
+    EdgeRole r;
+    r.va = swapped ? j : i;
+    r.da = swapped ? dj : di;
+    r.db = swapped ? di : dj;
+    r.stream = swapped ? cb : ca;
+    r.cls = degree_class(r.da, a.dense);
+    r.coop = false;
+    r.slot = r.stream > SIZE_B1 ? 1 : (r.stream > SIZE_B2 ? 2 : 3);
+    if (r.cls == CL_L0 && r.stream > COOP_G1) {          // too long for one warp: promoted to the G1 kernel
+        r.cls = CL_G1;
+        r.coop = true;
+        r.slot = N_SIZE_BUCKETS;
+    } else if ((r.cls == CL_G1 && r.stream > COOP_G1) || (r.cls == CL_G2 && r.stream > COOP_G2)) {
+        r.coop = true;
+        r.slot = 0;
+    } else if (r.cls == CL_X) {
+        r.slot = 0;
+    }
+    return r;
 }
 
 __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
-    __shared__ unsigned int s_hist[BUCKETS_PER_CLASS];
     __shared__ unsigned int s_grp[N_CLASSES + 1];
-    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x) s_hist[b] = 0;
     if (threadIdx.x <= N_CLASSES) s_grp[threadIdx.x] = 0;
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,94 +267,104 @@ __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
             a.out_tri[t] = 0; a.out_sq_i[t] = 0; a.out_sq_j[t] = 0; a.out_gamma[t] = 0; a.out_bfc[t] = 0.0;
             a.bucket[t] = BUCKET_TRIVIAL;
         } else {
-            const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
-            const bool swapped = cb < ca;
-            const int va = swapped ? j : i;                                    // tested endpoint (see the edge kernel)
-            const int da = swapped ? dj : di, db = swapped ? di : dj;
-            const int cls = class_of_degree(da);
-            if (db > 65535) {            // the 16-bit slot counters of the shared-memory tables count up to d_b lists
-                a.bucket[t] = BUCKET_EXCEPTION;
-                atomicAdd(&s_grp[N_CLASSES], 1u);
-            } else if (cls == 0) {
-                const long long work = min(ca, cb) + 4LL * (di + dj);
-                const int lg = 63 - __clzll(work | 1);
-                const int b = BUCKETS_PER_CLASS - 1 - min(lg, BUCKETS_PER_CLASS - 1);   // heavy first
-                a.bucket[t] = (uint8_t)b;
-                atomicAdd(&s_hist[b], 1u);
-            } else {
-                a.bucket[t] = (uint8_t)(BUCKET_GROUPED + cls);
-                atomicAdd(&s_grp[cls], 1u);
-                atomicAdd(&a.va_cnt[va], 1u);
-            }
+            const EdgeRole r = edge_role(a, i, j, di, dj);
+            a.bucket[t] = (uint8_t)r.cls;
+            atomicAdd(&s_grp[r.cls], 1u);
+            atomicAdd(&a.va_cnt[(size_t)r.slot * a.n + r.va], 1u);
         }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x)
-        if (s_hist[b]) atomicAdd(&a.plan->hist[b], s_hist[b]);
     if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
 }
 
-// Bucket offsets of class 0 and the class ranges (one thread: 48 + 4 values).
+// Class ranges (one thread).
 __global__ void plan_ranges_kernel(PaperArgs a) {
     PaperPlan* plan = a.plan;
     if (threadIdx.x == 0) {
         unsigned int acc = 0;
-        plan->class_begin[0] = 0;
-        for (int b = 0; b < BUCKETS_PER_CLASS; ++b) { plan->bucket_off[b] = acc; acc += plan->hist[b]; }
-        plan->bucket_off[BUCKETS_PER_CLASS] = acc;
-        for (int c = 1; c < N_CLASSES; ++c) { plan->class_begin[c] = acc; acc += plan->grouped[c]; }
-        acc += plan->grouped[N_CLASSES];               // exceptions close class 3
+        for (int c = 0; c < N_CLASSES; ++c) { plan->class_begin[c] = acc; acc += plan->grouped[c]; }
         plan->class_begin[N_CLASSES] = acc;
     }
 }
 
-// Every vertex that is the tested endpoint of grouped edges reserves a contiguous range of `order` inside its
-// class (the class is a function of the vertex degree).  The order of the ranges is irrelevant — only contiguity
-// matters for the table reuse — so one atomicAdd per such vertex replaces a scan over all vertices.
+// position of rank s inside a group of `cnt` edges that starts at `gstart` (see RUN_EDGES)
+__device__ __forceinline__ unsigned int run_layout_pos(unsigned int gstart, unsigned int cnt, unsigned int s) {
+    const unsigned int R = (cnt + RUN_EDGES - 1) / RUN_EDGES, q = cnt / R, rem = cnt % R;
+    const unsigned int r = s % R;
+    return gstart + r * q + min(r, rem) + s / R;
+}
+__device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned int gstart, unsigned int cnt) {
+    const unsigned int R = (cnt + RUN_EDGES - 1) / RUN_EDGES, q = cnt / R, rem = cnt % R;
+    const int tbl = run_table_of(cls);
+    const unsigned int base = atomicAdd(&a.plan->n_runs[tbl], R);
+    for (unsigned int r = 0; r < R; ++r)
+        a.runs[(size_t)tbl * a.max_runs + base + r] = make_uint2(gstart + r * q + min(r, rem), q + (r < rem ? 1u : 0u));
+}
+
+// Every vertex that is the tested endpoint of edges reserves a contiguous range of `order` inside the class of its
+// degree, and L0 vertices a second one in G1 for their promoted edges.  The order of the ranges is irrelevant — only
+// contiguity matters for the table reuse — so one atomicAdd per such vertex replaces a scan over all vertices.
+// Inside a group the size buckets follow each other, heaviest first; group classes also get their run table.
 __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= a.n) return;
-    const unsigned int c = a.va_cnt[v];
-    if (c == 0) return;
-    const int cls = class_of_degree(a.rowptr[v + 1] - a.rowptr[v]);
-    a.va_cnt[v] = a.plan->class_begin[cls] + atomicAdd(&a.plan->group_cursor[cls], c);
+    unsigned int c[N_SLOTS], own = 0;
+#pragma unroll
+    for (int q = 0; q < N_SLOTS; ++q) {
+        c[q] = a.va_cnt[(size_t)q * a.n + v];
+        if (q < N_SIZE_BUCKETS) {
+            a.va_cnt[(size_t)q * a.n + v] = own;        // rank offset of the bucket inside the group
+            own += c[q];
+        }
+    }
+    a.va_cnt[(size_t)N_SIZE_BUCKETS * a.n + v] = 0;
+    if (own) {
+        const int cls = degree_class(a.rowptr[v + 1] - a.rowptr[v], a.dense);
+        const unsigned int gstart = a.plan->class_begin[cls] + atomicAdd(&a.plan->group_cursor[cls], own);
+        a.grp[v] = gstart;
+        a.grp[(size_t)a.n + v] = own;
+        if (cls == CL_G1 || cls == CL_G2) emit_runs(a, cls, gstart, own);
+    }
+    const unsigned int cp = c[N_SIZE_BUCKETS];
+    if (cp) {
+        const unsigned int gstart = a.plan->class_begin[CL_G1] + atomicAdd(&a.plan->group_cursor[CL_G1], cp);
+        a.grp[(size_t)2 * a.n + v] = gstart;
+        a.grp[(size_t)3 * a.n + v] = cp;
+        emit_runs(a, CL_G1, gstart, cp);
+    }
 }
 
 __global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
-    // class 0, block-aggregated: one global atomic per (block, bucket) reserves a range, ranks come from shared memory
-    __shared__ unsigned int s_cnt[BUCKETS_PER_CLASS];
-    __shared__ unsigned int s_base[BUCKETS_PER_CLASS];
-    for (int b = threadIdx.x; b < BUCKETS_PER_CLASS; b += blockDim.x) s_cnt[b] = 0;
-    __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int b = BUCKET_TRIVIAL;
-    unsigned int r = 0;
-    if (t < a.count) {
-        b = a.bucket[t];
-        if (b < BUCKETS_PER_CLASS) {
-            r = atomicAdd(&s_cnt[b], 1u);
-        } else if (b == BUCKET_EXCEPTION) {
-            const unsigned int pos = a.plan->class_begin[N_CLASSES] - a.plan->grouped[N_CLASSES] +
-                                     atomicAdd(&a.plan->exc_cursor, 1u);
-            a.order[pos] = (uint32_t)t;
-        } else if (b != BUCKET_TRIVIAL) {          // grouped by tested endpoint
-            const int64_t e = a.e_first + t * a.e_stride;
-            const int i = a.esrc[e], j = a.edst[e];
-            const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
-            const int va = (a.node_s[i] - dj) < (a.node_s[j] - di) ? j : i;
-            a.order[a.va_cnt[va] + atomicAdd(&a.va_cur[va], 1u)] = (uint32_t)t;
-        }
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < BUCKETS_PER_CLASS; q += blockDim.x)
-        if (s_cnt[q]) s_base[q] = a.plan->bucket_off[q] + atomicAdd(&a.plan->cursor[q], s_cnt[q]);
-    __syncthreads();
-    if (b < BUCKETS_PER_CLASS) a.order[s_base[b] + r] = (uint32_t)t;
+    if (t >= a.count) return;
+    const int b = a.bucket[t];
+    if (b == BUCKET_TRIVIAL) return;
+    const int64_t e = a.e_first + t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+    const EdgeRole r = edge_role(a, i, j, di, dj);
+    const size_t slot = (size_t)r.slot * a.n + r.va;
+    const unsigned int s = a.va_cnt[slot] + atomicAdd(&a.va_cur[slot], 1u);
+    const size_t g = (r.slot == N_SIZE_BUCKETS ? (size_t)2 * a.n : 0) + r.va;
+    const unsigned int gstart = a.grp[g], cnt = a.grp[g + a.n];
+    const unsigned int pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, s) : gstart + s;
+    a.order[pos] = (uint32_t)t;
+    a.ova[pos] = (uint32_t)r.va | (r.coop ? 0x80000000u : 0u);
 }
 
-template <bool CTA_TEAM>
-__device__ __forceinline__ void team_sync() {
-    if (CTA_TEAM) __syncthreads(); else __syncwarp();
+// where a class kernel finds its work: a range of `order` (classes) or the overflow list
+struct WorkSource { const uint32_t* order; unsigned int count; unsigned int* next; };
+__device__ __forceinline__ WorkSource work_source(const PaperArgs& a, int cls) {
+    WorkSource w;
+    if (cls == CL_OVF) {
+        w.order = a.ovf_order;
+        w.count = a.plan->ovf_count;
+    } else {
+        w.order = a.order + a.plan->class_begin[cls];
+        w.count = a.plan->class_begin[cls + 1] - a.plan->class_begin[cls];
+    }
+    w.next = &a.plan->next[cls];
+    return w;
 }
 
 // Slot counters: 16 bit per slot packed in 32-bit words for the shared-memory tables (a count is at most the number
@@ -369,39 +448,6 @@ __device__ __forceinline__ void pure_head(const PaperArgs& a, const uint32_t* ta
     }
 }
 
-// Warp team: the lists of the pure heads among list[c0 .. c0+32) as one flat stream.  `st` = this warp's stream
-// state.  Accumulates (#lists with a match, largest per-list count) per lane.
-template <bool GLOBAL>
-__device__ __forceinline__ void scan_chunk(const PaperArgs& a, const uint32_t* tab, uint32_t* cnt, uint32_t mask,
-                                           int shift, const uint32_t* bm, uint32_t bmask, int list_begin, int list_len,
-                                           int c0, int va, int vb, int* st, int lane, int& sq, int& gmax) {
-    int* pre = st;            // [33]
-    int* beg = st + 33;       // [32]
-    int* lcnt = st + 65;      // [32]
-    const int t = c0 + lane;
-    int mb = 0, md = 0;
-    if (t < list_len) pure_head<GLOBAL>(a, tab, mask, shift, a.colidx[list_begin + t], va, mb, md);
-    int inc = md;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += up;
-    }
-    const int total = __shfl_sync(FULL, inc, 31);
-    if (total == 0) return;
-    pre[lane + 1] = inc;
-    if (lane == 0) pre[0] = 0;
-    beg[lane] = mb;
-    lcnt[lane] = 0;
-    __syncwarp();
-    flat_scan<GLOBAL>(a.colidx, tab, cnt, mask, shift, bm, bmask, pre, beg, lcnt, 0, 0, total, lane, vb);
-    __syncwarp();
-    const int c = lcnt[lane];
-    sq += c > 0;
-    gmax = max(gmax, c);
-    __syncwarp();
-}
-
 // CTA team: up to HEADS = heads_per_thread*THREADS heads per round; the CTA-wide flat stream is cut into equal contiguous ranges,
 // one per warp, so every warp streams the same number of elements whatever the list-length distribution (a hub's
 // list next to twenty short ones does not serialise).  `cs` = pre[HEADS+1] | beg[HEADS] | cnt[HEADS].
@@ -469,13 +515,11 @@ __device__ __forceinline__ void scan_cta(const PaperArgs& a, const uint32_t* tab
     }
 }
 
-// TEAM = threads per team (32 = warp team, several teams per CTA; otherwise the CTA is the team).
+// CTA-team kernel (heavy edges, global-table edges, overflow list): the CTA is the team of one edge at a time.
 template <int TEAM, int MAX_SLOTS, bool GLOBAL_TABLE>
-__global__ void __launch_bounds__(TEAM > 32 ? TEAM : WARP_TEAM_WARPS * 32,
-                                  TEAM == BIG_THREADS ? 1 : (TEAM == MID_THREADS ? MID_CTAS_PER_SM : WARP_CTAS_PER_SM))
+__global__ void __launch_bounds__(TEAM, 1)
 paper_edge_kernel(PaperArgs a, int cls) {
-    constexpr bool CTA_TEAM = TEAM > 32;
-    constexpr int NWARPS = CTA_TEAM ? TEAM / 32 : WARP_TEAM_WARPS;
+    constexpr int NWARPS = TEAM / 32;
     constexpr int CTA_STREAM = 3 * heads_per_thread(TEAM) * TEAM + 8;
     extern __shared__ uint32_t smem_dyn[];
     __shared__ unsigned int s_idx;
@@ -483,54 +527,41 @@ paper_edge_kernel(PaperArgs a, int cls) {
     __shared__ int s_red[5];  // tri, sq(lists), g(lists), sq(slots), g(slots)
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    constexpr int team_threads = CTA_TEAM ? TEAM : 32;
-    const int team_tid = CTA_TEAM ? (int)threadIdx.x : lane;
-    // shared-memory carve-up: [stream state (per warp | per CTA)][bitmap filter(s)][table keys][slot counters]
+    constexpr int team_threads = TEAM;
+    const int team_tid = (int)threadIdx.x;
+    // shared-memory carve-up: [stream state][bitmap filter][table keys][slot counters]
     constexpr int FBITS = filter_bits(TEAM, GLOBAL_TABLE);
     constexpr uint32_t bmask = (uint32_t)FBITS - 1u;
-    int* st = (int*)smem_dyn + (CTA_TEAM ? 0 : warp * STREAM_INTS);
-    uint32_t* bm = smem_dyn + (CTA_TEAM ? CTA_STREAM : NWARPS * STREAM_INTS + warp * (FBITS / 32));
-    uint32_t* sm_tab = smem_dyn + (CTA_TEAM ? CTA_STREAM + FBITS / 32 : NWARPS * (STREAM_INTS + FBITS / 32));
+    int* st = (int*)smem_dyn;
+    uint32_t* bm = smem_dyn + CTA_STREAM;
+    uint32_t* sm_tab = smem_dyn + CTA_STREAM + FBITS / 32;
     uint32_t* tab;
     uint32_t* cnt;
     if (GLOBAL_TABLE) {
         tab = a.gtables + (size_t)blockIdx.x * a.gslots * 2;
         cnt = tab + a.gslots;
-    } else if (CTA_TEAM) {
+    } else {
         tab = sm_tab;
         cnt = sm_tab + MAX_SLOTS;
-    } else {
-        tab = sm_tab + warp * (MAX_SLOTS + MAX_SLOTS / 2);
-        cnt = tab + MAX_SLOTS;
     }
-    const unsigned int cbeg = a.plan->class_begin[cls];
-    const unsigned int cnum = a.plan->class_begin[cls + 1] - cbeg;
+    const WorkSource ws = work_source(a, cls);
+    const unsigned int cnum = ws.count;
     const uint32_t max_slots = GLOBAL_TABLE ? a.gslots : (uint32_t)MAX_SLOTS;
     // edges per work-stealing step: a run of one va, usually — but never so long that the CTAs run out of steps
-    const unsigned int GRAB = CTA_TEAM ? min(16u, max(1u, cnum / (gridDim.x * 8u))) : 1u;
+    const unsigned int GRAB = min(16u, max(1u, cnum / (gridDim.x * 8u)));
 
-    int cur_va = -1;                 // vertex whose neighbour set is in the table (CTA teams re-use it across edges)
+    int cur_va = -1;                 // vertex whose neighbour set is in the table (re-used across edges)
     uint32_t slots = 0, mask = 0;
     int shift = 0;
     while (true) {
-        unsigned int idx0;
-        if (CTA_TEAM) {
-            if (threadIdx.x == 0) s_idx = atomicAdd(&a.plan->next[cls], GRAB);
-            __syncthreads();
-            idx0 = s_idx;
-        } else {
-            idx0 = 0;
-            if (lane == 0) idx0 = atomicAdd(&a.plan->next[cls], GRAB);
-            idx0 = __shfl_sync(FULL, idx0, 0);
-        }
+        if (threadIdx.x == 0) s_idx = atomicAdd(ws.next, GRAB);
+        __syncthreads();
+        const unsigned int idx0 = s_idx;
         if (idx0 >= cnum) break;
         for (unsigned int q = 0; q < GRAB && idx0 + q < cnum; ++q) {
-            if (CTA_TEAM) {
-                if (threadIdx.x == 0) s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
-                __syncthreads();
-            }
-            const uint32_t t = a.order[cbeg + idx0 + q];
+            if (threadIdx.x == 0) s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = 0;
+            __syncthreads();
+            const uint32_t t = ws.order[idx0 + q];
             const int64_t e = a.e_first + (int64_t)t * a.e_stride;
             const int i = a.esrc[e], j = a.edst[e];
             const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
@@ -540,7 +571,7 @@ paper_edge_kernel(PaperArgs a, int cls) {
             const int sa = a.rowptr[va], da = swapped ? dj : di;
             const int sb = a.rowptr[vb], db = swapped ? di : dj;
 
-            if (!CTA_TEAM || va != cur_va) {
+            if (va != cur_va) {
                 // table of N(va), every key with tag 1: power of two >= 8*d_a (load factor <= 1/8 keeps probe
                 // chains short and uniform across the lanes of a warp), capped by the class's table
                 const int lg = min(32 - __clz(max(8 * da, 64) - 1), 31 - __clz(max_slots));
@@ -550,13 +581,13 @@ paper_edge_kernel(PaperArgs a, int cls) {
                 for (uint32_t s = team_tid; s < slots; s += team_threads) tab[s] = EMPTY;
                 for (uint32_t s = team_tid; s < (GLOBAL_TABLE ? slots : slots / 2); s += team_threads) cnt[s] = 0u;
                 for (uint32_t s = team_tid; s < (uint32_t)FBITS / 32; s += team_threads) bm[s] = 0u;
-                team_sync<CTA_TEAM>();
+                __syncthreads();
                 for (int p = team_tid; p < da; p += team_threads) {
                     const uint32_t k = (uint32_t)a.colidx[sa + p];
                     insert_or_tag<GLOBAL_TABLE>(tab, mask, shift, k, 1u);
                     atomicOr(&bm[(k & bmask) >> 5], 1u << (k & 31u));
                 }
-                team_sync<CTA_TEAM>();
+                __syncthreads();
                 cur_va = va;
             }
             // common neighbours: heads of N(vb) found in the table get bit 31 (tag 3: never a match, never a head)
@@ -571,30 +602,20 @@ paper_edge_kernel(PaperArgs a, int cls) {
                 }
             }
             tri = warp_sum(tri);
-            if (CTA_TEAM) {
-                if (lane == 0 && tri) atomicAdd(&s_red[0], tri);
-            }
-            team_sync<CTA_TEAM>();
+            if (lane == 0 && tri) atomicAdd(&s_red[0], tri);
+            __syncthreads();
 
             // the scan: lists of the pure neighbours of vb, matches against the pure neighbours of va
             int sqL = 0, gL = 0, sqS = 0, gS = 0;
-            if (CTA_TEAM) {
-                scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, bm, bmask, sb, db, va, vb, st, s_warp_tot, sqL, gL);
-                sqL = warp_sum(sqL);
-                gL = warp_max(gL);
-                if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
-                __syncthreads();
-                sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
-            } else {
-                for (int c0 = 0; c0 < db; c0 += 32)
-                    scan_chunk<GLOBAL_TABLE>(a, tab, cnt, mask, shift, bm, bmask, sb, db, c0, va, vb, st, lane, sqL, gL);
-                sqL = warp_sum(sqL);
-                gL = warp_max(gL);
-                __syncwarp();
-            }
+            scan_cta<TEAM, GLOBAL_TABLE>(a, tab, cnt, mask, shift, bm, bmask, sb, db, va, vb, st, s_warp_tot, sqL, gL);
+            sqL = warp_sum(sqL);
+            gL = warp_max(gL);
+            if (lane == 0 && sqL) { atomicAdd(&s_red[1], sqL); atomicMax(&s_red[2], gL); }
+            __syncthreads();
+            sqL = s_red[1]; gL = s_red[2]; tri = s_red[0];
             // the collect: slot counters of the pure neighbours of va -> squares at va (empty iff the scan found
-            // nothing).  Walks N(va) (d_a probes) instead of sweeping the table; CTA teams zero the counters they
-            // read so the table is clean for the next edge of the same va.
+            // nothing).  Walks N(va) (d_a probes) instead of sweeping the table and zeroes the counters it reads,
+            // so the table is clean for the next edge of the same va.
             if (sqL > 0) {
                 for (int p = team_tid; p < da; p += team_threads) {
                     const int k = a.colidx[sa + p];
@@ -605,20 +626,16 @@ paper_edge_kernel(PaperArgs a, int cls) {
                         if (c > 0) {
                             ++sqS;
                             gS = max(gS, c);
-                            if (CTA_TEAM) {
-                                if (GLOBAL_TABLE) cnt[h] = 0u;
-                                else atomicAnd(&cnt[h >> 1], (h & 1) ? 0x0000ffffu : 0xffff0000u);
-                            }
+                            if (GLOBAL_TABLE) cnt[h] = 0u;
+                            else atomicAnd(&cnt[h >> 1], (h & 1) ? 0x0000ffffu : 0xffff0000u);
                         }
                     }
                 }
                 sqS = warp_sum(sqS);
                 gS = warp_max(gS);
-                if (CTA_TEAM) {
-                    if (lane == 0 && sqS) { atomicAdd(&s_red[3], sqS); atomicMax(&s_red[4], gS); }
-                    __syncthreads();
-                    sqS = s_red[3]; gS = s_red[4];
-                }
+                if (lane == 0 && sqS) { atomicAdd(&s_red[3], sqS); atomicMax(&s_red[4], gS); }
+                __syncthreads();
+                sqS = s_red[3]; gS = s_red[4];
             }
             if (team_tid == 0) {
                 const int sq_i = swapped ? sqL : sqS, sq_j = swapped ? sqS : sqL;
@@ -628,19 +645,581 @@ paper_edge_kernel(PaperArgs a, int cls) {
                 a.out_sq_j[t] = sq_j;
                 a.out_gamma[t] = gamma;      // the fp64 value is computed by paper_value_kernel (one thread per edge)
             }
-            if (CTA_TEAM) {
-                // undo the common-neighbour marks so the table is N(va) with tag 1 again
-                if (tri > 0) {
-                    for (int p = team_tid; p < db; p += team_threads) {
-                        const int m = a.colidx[sb + p];
-                        uint32_t v;
-                        const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
-                        if (h >= 0) atomicAnd(&tab[h], 0x7fffffffu);
-                    }
+            // undo the common-neighbour marks so the table is N(va) with tag 1 again
+            if (tri > 0) {
+                for (int p = team_tid; p < db; p += team_threads) {
+                    const int m = a.colidx[sb + p];
+                    uint32_t v;
+                    const int h = (m == va) ? -1 : probe_slot<GLOBAL_TABLE>(tab, mask, shift, (uint32_t)m, v);
+                    if (h >= 0) atomicAnd(&tab[h], 0x7fffffffu);
                 }
             }
-            team_sync<CTA_TEAM>();  // table / s_red reuse
+            __syncthreads();  // table / s_red reuse
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// warp-granular edges over READ-ONLY membership structures of N(va)
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+
+// slot of `key` in a key-only table, or -1
+__device__ __forceinline__ int ro_probe(const uint32_t* tab, uint32_t mask, int shift, uint32_t key) {
+    uint32_t h = hash_slot(key, shift);
+    while (true) {
+        const uint32_t v = tab[h];
+        if (v == key) return (int)h;
+        if (v == EMPTY) return -1;
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ void ro_insert(uint32_t* tab, uint32_t mask, int shift, uint32_t key) {
+    uint32_t h = hash_slot(key, shift);
+    while (true) {
+        const uint32_t v = atomicCAS(&tab[h], EMPTY, key);
+        if (v == EMPTY || v == key) return;
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ bool bitmap_test(const uint32_t* bm, uint32_t bmask, uint32_t k) {
+    return (bm[(k & bmask) >> 5] >> (k & 31u)) & 1u;
+}
+
+// Table geometry for a tested endpoint of degree d_a: power of two >= FILL*d_a slots (>= 64), key-only.
+template <int MAX_SLOTS, int FILL>
+__device__ __forceinline__ void ro_geometry(int da, uint32_t& mask, int& shift) {
+    const int lg = min(32 - __clz(max(FILL * da, 64) - 1), ilog2_c(MAX_SLOTS));
+    mask = (1u << lg) - 1u;
+    shift = 32 - lg;
+}
+
+// Membership in N(va).  DENSE: an exact bitmap over all node ids in shared memory (one load, no probe) — used when
+// n bits fit beside the rest of the CTA state.  Otherwise: hashed bitmap pre-filter + key-only open-addressing table.
+template <bool DENSE>
+struct Member {
+    const uint32_t* tab;
+    const uint32_t* bm;
+    uint32_t mask, bmask;
+    int shift;
+    __device__ __forceinline__ bool maybe(uint32_t k) const {      // cheap necessary condition (exact when DENSE)
+        return DENSE ? ((bm[k >> 5] >> (k & 31u)) & 1u) : bitmap_test(bm, bmask, k);
+    }
+    __device__ __forceinline__ bool confirm(uint32_t k) const {    // after maybe(k)
+        return DENSE ? true : (ro_probe(tab, mask, shift, k) >= 0);
+    }
+    __device__ __forceinline__ bool has(uint32_t k) const { return maybe(k) && confirm(k); }
+};
+
+// Match hash: keys[CAP] (node id + 1) | counts[CAP].  Returns false when the hash is (nearly) full.
+template <int CAP>
+__device__ __forceinline__ bool match_add(uint32_t* mh, int* n_distinct, uint32_t k) {
+    const uint32_t key = k + 1u;
+    uint32_t p = (key * 0x9E3779B1u) >> (32 - ilog2_c(CAP));
+    for (int tries = 0; tries < CAP; ++tries) {
+        uint32_t v = *(volatile uint32_t*)(mh + p);
+        if (v == 0u) {
+            if (*(volatile int*)n_distinct >= CAP / 4 * 3) return false;
+            v = atomicCAS(&mh[p], 0u, key);
+            if (v == 0u) atomicAdd(n_distinct, 1);
+        }
+        if (v == 0u || v == key) {
+            atomicAdd(&mh[CAP + p], 1u);
+            return true;
+        }
+        p = (p + 1) & (CAP - 1);
+    }
+    return false;
+}
+// (#distinct keys, largest count) of this thread's share of the hash; clears what it reads
+template <int CAP>
+__device__ __forceinline__ void match_collect(uint32_t* mh, int first, int stride, int& sq_a, int& g_a) {
+    for (int p = first; p < CAP; p += stride) {
+        if (mh[p]) {
+            ++sq_a;
+            g_a = max(g_a, (int)mh[CAP + p]);
+            mh[p] = 0u;
+            mh[CAP + p] = 0u;
+        }
+    }
+}
+
+// Everything a warp needs to test streamed elements of one edge (va tested, vb streamed).
+template <int CAP, int TBW, bool DENSE>
+struct EdgeCtx {
+    const int32_t* __restrict__ colidx;
+    Member<DENSE> mem;
+    const uint32_t* tb;      // hashed bitmap of the common neighbours N(va) ∩ N(vb) (TBW words)
+    uint32_t* mh;            // match hash (2*CAP words)
+    int* n_distinct;
+    int vb, sb, db;
+    bool ovf;
+    // k in N(m), m a pure neighbour of vb: is (m,k) an edge of the bipartite graph M_b – M_a?  Split in two so that the
+    // streaming loops stay small: hit() is the per-element filter (one shared-memory load), slow() runs once per
+    // candidate — ONE copy of it per loop, shared by all the elements of a window.
+    __device__ __forceinline__ bool hit(int k) const { return mem.maybe((uint32_t)k) && k != vb; }
+    __device__ __forceinline__ int slow(int k) {
+        const uint32_t kk = (uint32_t)k;
+        if (mem.confirm(kk)) {   // k in N(va); a common neighbour only if its triangle bit is set AND it is in N(vb)
+            const bool maybe_tri = (tb[(kk >> 5) & (TBW - 1)] >> (kk & 31u)) & 1u;
+            if (!maybe_tri || find_sorted(colidx, sb, db, k) < 0) {
+                if (!match_add<CAP>(mh, n_distinct, kk)) ovf = true;
+                return 1;
+            }
+        }
+        return 0;
+    }
+};
+
+// the u-th of UNROLL registers (u is not a compile-time constant: a select chain instead of local memory)
+template <int N>
+__device__ __forceinline__ int pick(const int (&v)[N], int u) {
+    int r = v[0];
+#pragma unroll
+    for (int q = 1; q < N; ++q) r = (u == q) ? v[q] : r;
+    return r;
+}
+
+// `len` consecutive entries of one neighbour list, streamed by the whole warp (p already includes the lane offset):
+// returns this lane's number of matches.  Lanes past the end test vb, which never matches.
+template <class Ctx>
+__device__ __forceinline__ int stream_segment(Ctx& cx, const int32_t* __restrict__ p, int len, int lane) {
+    int c = 0;
+    for (int F = 0; F < len; F += 32 * UNROLL) {       // all loads of a window are in flight before the first test
+        int k[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) k[u] = (F + 32 * u + lane < len) ? __ldg(p + F + 32 * u) : cx.vb;
+        uint32_t hm = 0;                                // this lane's candidates among its UNROLL elements
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        while (hm) {
+            const int u = __ffs(hm) - 1;
+            hm &= hm - 1;
+            c += cx.slow(pick(k, u));
+        }
+    }
+    return c;
+}
+
+// One chunk of 32 heads of N(vb) (positions c0 .. c0+31) by one warp: lists of at least LONG_LIST entries are
+// streamed one at a time by the whole warp (no ownership arithmetic at all); the shorter ones form ONE flat stream —
+// the (begin - prefix) of each list lives in a lane's register, the owner of flat element f is found with one
+// warp-wide OR-reduction of the "a list starts here" bits plus a popc, its data come through one shuffle.
+// Adds to the lane-partial sq_b (#lists with a match) and g_b (largest per-list count).
+template <class Ctx>
+__device__ __forceinline__ void warp_chunk(const PaperArgs& a, Ctx& cx, int va, int c0, int* st, int lane,
+                                           int& sq_b, int& g_b) {
+    const int32_t* __restrict__ colidx = cx.colidx;
+    int mb = 0, md = 0;
+    if (c0 + lane < cx.db) {
+        const int m = colidx[cx.sb + c0 + lane];
+        if (m != va && !cx.mem.has((uint32_t)m)) {
+            mb = a.rowptr[m];
+            md = a.rowptr[m + 1] - mb;
+        }
+    }
+    // long lists
+    uint32_t lm = __ballot_sync(FULL, md >= LONG_LIST);
+    while (lm) {
+        const int src = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int len = __shfl_sync(FULL, md, src);
+        int c = stream_segment(cx, colidx + __shfl_sync(FULL, mb, src) + lane, len, lane);
+        c = __reduce_add_sync(FULL, c);
+        sq_b += (lane == 0 && c > 0);
+        g_b = max(g_b, c);
+    }
+    // short lists (a list that holds only vb cannot match)
+    const bool shortl = md > 1 && md < LONG_LIST;
+    const uint32_t pm = __ballot_sync(FULL, shortl);
+    if (pm == 0u) return;
+    int* sbeg = st + WS_BEG;
+    int* slen = st + WS_LEN;
+    int* lcnt = st + WS_LCNT;
+    const int nl = __popc(pm);
+    if (shortl) {
+        const int r = __popc(pm & ((1u << lane) - 1u));
+        sbeg[r] = mb;
+        slen[r] = md;
+    }
+    lcnt[lane] = 0;
+    __syncwarp();
+    const int len_l = lane < nl ? slen[lane] : 0;
+    int inc = len_l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += up;
+    }
+    const int total = __shfl_sync(FULL, inc, 31);
+    const int pre_l = lane < nl ? inc - len_l : 0x3fffffff;      // flat position of the first element of list `lane`
+    const int base_l = (lane < nl ? sbeg[lane] : 0) - pre_l;     // colidx index of flat element f of this list: base + f
+    const uint32_t le_mask = 0xffffffffu >> (31 - lane);
+    int below = 0;                                               // #lists that start before the current group
+    constexpr int FU = DCR_FLAT_UNROLL;
+    for (int F = 0; F < total; F += 32 * FU) {
+        int k[FU], own[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int Fu = F + 32 * u;
+            const unsigned rel = (unsigned)(pre_l - Fu);
+            const uint32_t starts = __reduce_or_sync(FULL, rel < 32u ? (1u << rel) : 0u);
+            own[u] = (below + __popc(starts & le_mask) - 1) & 31;
+            below += __popc(starts);
+            const int bs = __shfl_sync(FULL, base_l, own[u]);
+            const int f = Fu + lane;
+            k[u] = f < total ? __ldg(colidx + bs + f) : cx.vb;
+        }
+        uint32_t hm = 0;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        while (hm) {
+            const int u = __ffs(hm) - 1;
+            hm &= hm - 1;
+            if (cx.slow(pick(k, u))) atomicAdd(&lcnt[pick(own, u)], 1);
+        }
+    }
+    __syncwarp();
+    const int c = lcnt[lane];
+    sq_b += c > 0;
+    g_b = max(g_b, c);
+    __syncwarp();
+}
+
+// One edge by one warp.  `st` = the warp's scratch, `tb` = its triangle bitmap (TB_WORDS words), `mh` = its match
+// hash (2*CAP words, all zero on entry and on exit).  Writes the four integer fields of local edge t and returns
+// true, or returns false when the match hash filled up (nothing written; the hash is clean again).
+template <int CAP, bool DENSE>
+__device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st,
+                                          uint32_t* tb, uint32_t* mh, int lane) {
+    const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const bool swapped = (va == j);                      // stream i's side, test j
+    EdgeCtx<CAP, TB_WORDS, DENSE> cx;
+    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.mh = mh; cx.n_distinct = st + WS_NDIST;
+    cx.vb = swapped ? i : j;
+    cx.sb = a.rowptr[cx.vb];
+    cx.db = a.rowptr[cx.vb + 1] - cx.sb;
+    cx.ovf = false;
+    // pass 1 over the heads: common neighbours (triangles) and their bitmap
+    tb[lane] = 0u;
+    __syncwarp();
+    int tri = 0;
+    for (int p = lane; p < cx.db; p += 32) {
+        const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+        if ((int)m != va && mem.has(m)) {
+            ++tri;
+            atomicOr(&tb[(m >> 5) & (TB_WORDS - 1)], 1u << (m & 31u));
+        }
+    }
+    __syncwarp();
+    // pass 2: the lists of the pure heads
+    int sq_b = 0, g_b = 0;
+    for (int c0 = 0; c0 < cx.db; c0 += 32) warp_chunk(a, cx, va, c0, st, lane, sq_b, g_b);
+    tri = __reduce_add_sync(FULL, tri);
+    sq_b = __reduce_add_sync(FULL, sq_b);
+    g_b = __reduce_max_sync(FULL, g_b);
+    int sq_a = 0, g_a = 0;
+    if (sq_b > 0) {                                      // the match hash is non-empty iff some list matched
+        match_collect<CAP>(mh, lane, 32, sq_a, g_a);
+        sq_a = __reduce_add_sync(FULL, sq_a);
+        g_a = __reduce_max_sync(FULL, g_a);
+        if (lane == 0) st[WS_NDIST] = 0;
+    }
+    const bool ovf = __any_sync(FULL, cx.ovf);
+    if (lane == 0 && !ovf) {
+        a.out_tri[t] = tri;
+        a.out_sq_i[t] = swapped ? sq_b : sq_a;
+        a.out_sq_j[t] = swapped ? sq_a : sq_b;
+        a.out_gamma[t] = (sq_b > 0 && sq_a > 0) ? max(g_a, g_b) : 0;
+    }
+    __syncwarp();
+    return !ovf;
+}
+
+// L0: warp-private hashed table, kept while consecutive edges (sorted by tested endpoint) share va.
+__global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_warp_kernel(PaperArgs a) {
+    extern __shared__ uint32_t smem_dyn[];
+    constexpr int PER_WARP = WSTATE_INTS + TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* base = smem_dyn + warp * PER_WARP;
+    int* st = (int*)base;
+    uint32_t* tb = base + WSTATE_INTS;
+    uint32_t* mh = tb + TB_WORDS;
+    uint32_t* bm = mh + 2 * L0_CAP;
+    uint32_t* tab = bm + L0_BITS / 32;
+    for (int p = lane; p < 2 * L0_CAP; p += 32) mh[p] = 0u;
+    if (lane == 0) st[WS_NDIST] = 0;
+    __syncwarp();
+    const WorkSource ws = work_source(a, CL_L0);
+    const uint32_t* ova = a.ova + a.plan->class_begin[CL_L0];
+    int cur_va = -1;
+    Member<false> mem;
+    mem.tab = tab; mem.bm = bm; mem.bmask = L0_BITS - 1; mem.mask = 0; mem.shift = 0;
+    while (true) {
+        unsigned int idx0 = 0;
+        if (lane == 0) idx0 = atomicAdd(ws.next, (unsigned)DCR_L0_GRAB);
+        idx0 = __shfl_sync(FULL, idx0, 0);
+        if (idx0 >= ws.count) break;
+        const unsigned int idx1 = min(ws.count, idx0 + (unsigned)DCR_L0_GRAB);
+        for (unsigned int q = idx0; q < idx1; ++q) {
+            const int va = (int)ova[q];
+            if (va != cur_va) {
+                const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
+                ro_geometry<L0_SLOTS, 2>(da, mem.mask, mem.shift);
+                for (uint32_t s = lane; s <= mem.mask; s += 32) tab[s] = EMPTY;
+                for (int s = lane; s < L0_BITS / 32; s += 32) bm[s] = 0u;
+                __syncwarp();
+                for (int p = lane; p < da; p += 32) {
+                    const uint32_t k = (uint32_t)a.colidx[sa + p];
+                    ro_insert(tab, mem.mask, mem.shift, k);
+                    atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
+                }
+                __syncwarp();
+                cur_va = va;
+            }
+            // d_a <= 128 distinct matches always fit the hash (L0_CAP * 3/4 = 192)
+            warp_edge<L0_CAP, false>(a, mem, ws.order[q], va, st, tb, mh, lane);
+        }
+    }
+}
+
+// One COOPERATIVE edge by the whole CTA (stream too long, or too many distinct matches, for one warp).  Rounds of
+// THREADS heads: every thread resolves one head, a CTA-wide prefix sum compacts the lists of the pure heads and lays
+// them out as one flat stream, and the warps pull slices of COOP_SLICE flat elements from a shared counter — a hub's
+// list next to twenty short ones does not serialise, and a slice that is dense in matches does not hold the others
+// up.  A warp walks the list segments inside its slice with the search-free segment loop.  The per-warp triangle
+// bitmaps and match hashes, contiguous in shared memory, act as ONE bitmap / ONE hash of NWARPS times the size; the
+// per-warp scratch blocks together hold pre[THREADS+1] | beg[THREADS] | lcnt[THREADS].
+// s_acc: [0] tri [1] sq_b [2] g_b [3] next slice [4] n_distinct [5] overflow [6] sq_a [7] g_a [11] #lists.  All
+// threads call it; the caller synchronises the CTA before the next use of s_acc.  An edge that overflows even the
+// CTA-wide hash goes to the global overflow list.
+template <int NWARPS, int CAP, bool DENSE>
+__device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st_all,
+                                         uint32_t* tb_all, uint32_t* mh_all, int* s_acc, unsigned long long* s_wtot) {
+    constexpr int THREADS = NWARPS * 32, TBW = NWARPS * TB_WORDS, CCAP = NWARPS * CAP;
+    static_assert(3 * THREADS + 1 <= NWARPS * WSTATE_INTS, "cooperative stream state must fit the warp scratch");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* pre = st_all;                    // [THREADS + 1]
+    int* beg = pre + THREADS + 1;         // [THREADS]
+    int* lcnt = beg + THREADS;            // [THREADS]
+    const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const bool swapped = (va == j);
+    EdgeCtx<CCAP, TBW, DENSE> cx;
+    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb_all; cx.mh = mh_all; cx.n_distinct = s_acc + 4;
+    cx.vb = swapped ? i : j;
+    cx.sb = a.rowptr[cx.vb];
+    cx.db = a.rowptr[cx.vb + 1] - cx.sb;
+    cx.ovf = false;
+    for (int s = tid; s < TBW; s += THREADS) tb_all[s] = 0u;
+    if (tid < 8) s_acc[tid] = 0;
+    __syncthreads();
+    int tri = 0;
+    for (int p = tid; p < cx.db; p += THREADS) {
+        const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+        if ((int)m != va && mem.has(m)) {
+            ++tri;
+            atomicOr(&tb_all[(m >> 5) & (TBW - 1)], 1u << (m & 31u));
+        }
+    }
+    tri = __reduce_add_sync(FULL, tri);
+    if (lane == 0 && tri) atomicAdd(&s_acc[0], tri);
+    __syncthreads();
+    int sq_b = 0, g_b = 0;
+    for (int h0 = 0; h0 < cx.db; h0 += THREADS) {
+        int mb = 0, md = 0;
+        if (h0 + tid < cx.db) {
+            const int m = a.colidx[cx.sb + h0 + tid];
+            if (m != va && !mem.has((uint32_t)m)) {
+                mb = a.rowptr[m];
+                md = a.rowptr[m + 1] - mb;
+                if (md <= 1) md = 0;                  // a list that holds only vb cannot match
+            }
+        }
+        // CTA-wide exclusive scan of (1 if the list is non-empty, its length), packed in 64 bits: the non-empty
+        // lists are compacted (rank -> pre/beg), so the walk below never steps over empty entries
+        unsigned long long inc = ((unsigned long long)(md > 0) << 40) | (unsigned long long)md;
+        const unsigned long long mine = inc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) s_wtot[warp] = inc;
+        if (tid == 0) s_acc[3] = 0;                   // slice counter of this round
+        __syncthreads();
+        unsigned long long off = inc - mine;
+        for (int w = 0; w < warp; ++w) off += s_wtot[w];
+        const int rank = (int)(off >> 40), fpos = (int)(off & 0xffffffffffull);
+        if (md > 0) { pre[rank] = fpos; beg[rank] = mb; }
+        lcnt[tid] = 0;
+        if (tid == THREADS - 1) {
+            const unsigned long long tot = off + mine;
+            pre[(int)(tot >> 40)] = (int)(tot & 0xffffffffffull);
+            s_acc[3 + 8] = (int)(tot >> 40);          // number of non-empty lists
+        }
+        __syncthreads();
+        const int nlists = s_acc[3 + 8];
+        const int total = pre[nlists];
+        if (total > 0) {
+            while (true) {                             // slices of the flat stream, pulled from a shared counter
+                int sl = 0;
+                if (lane == 0) sl = atomicAdd(&s_acc[3], 1);
+                sl = __shfl_sync(FULL, sl, 0);
+                int f0 = sl * COOP_SLICE;
+                if (f0 >= total) break;
+                const int f1 = min(total, f0 + COOP_SLICE);
+                int lo = 0, hi = nlists - 1;           // last l with pre[l] <= f0 (warp-uniform search)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (pre[mid] <= f0) lo = mid; else hi = mid - 1;
+                }
+                int l = lo;
+                while (f0 < f1) {
+                    const int seg_end = min(f1, pre[l + 1]);
+                    int c = stream_segment(cx, a.colidx + beg[l] + (f0 - pre[l]) + lane, seg_end - f0, lane);
+                    c = __reduce_add_sync(FULL, c);
+                    if (lane == 0 && c) atomicAdd(&lcnt[l], c);
+                    f0 = seg_end;
+                    ++l;
+                }
+            }
+            __syncthreads();
+            const int c = tid < nlists ? lcnt[tid] : 0;
+            sq_b += c > 0;
+            g_b = max(g_b, c);
+        }
+        __syncthreads();
+    }
+    sq_b = __reduce_add_sync(FULL, sq_b);
+    g_b = __reduce_max_sync(FULL, g_b);
+    const bool ovf = __any_sync(FULL, cx.ovf);
+    if (lane == 0) {
+        if (sq_b) { atomicAdd(&s_acc[1], sq_b); atomicMax(&s_acc[2], g_b); }
+        if (ovf) s_acc[5] = 1;
+    }
+    __syncthreads();
+    if (s_acc[1] > 0) {
+        int sq_a = 0, g_a = 0;
+        match_collect<CCAP>(mh_all, tid, THREADS, sq_a, g_a);
+        sq_a = __reduce_add_sync(FULL, sq_a);
+        g_a = __reduce_max_sync(FULL, g_a);
+        if (lane == 0 && sq_a) { atomicAdd(&s_acc[6], sq_a); atomicMax(&s_acc[7], g_a); }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (s_acc[5]) {
+            a.ovf_order[atomicAdd(&a.plan->ovf_count, 1u)] = t;
+        } else {
+            const int sb_ = s_acc[1], sa_ = s_acc[6];
+            a.out_tri[t] = s_acc[0];
+            a.out_sq_i[t] = swapped ? sb_ : sa_;
+            a.out_sq_j[t] = swapped ? sa_ : sb_;
+            a.out_gamma[t] = (sb_ > 0 && sa_ > 0) ? max(s_acc[2], s_acc[7]) : 0;
+        }
+    }
+}
+
+// Group kernel: the CTA builds the membership structures of N(va) for a run of edges with the same tested endpoint.
+// The cooperative edges of the run (they come first) are processed by the whole CTA one at a time; then the warps
+// pull the remaining edges — ordered by size, heaviest first — from a shared counter, one warp per edge; edges whose
+// per-warp match hash filled up are retried cooperatively at the end of the run.
+// DENSE: exact bitmap over all n node ids (dense_words 32-bit words); otherwise hashed bitmap + table.
+template <int NWARPS, int MAX_SLOTS, int BITS, int CAP, int CTAS_PER_SM, bool DENSE>
+__global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(PaperArgs a, int cls, int dense_words) {
+    extern __shared__ uint32_t smem_dyn[];
+    __shared__ unsigned int s_idx, s_next;
+    __shared__ int s_ndefer;
+    __shared__ int s_acc[12];
+    __shared__ unsigned long long s_wtot[NWARPS];
+    __shared__ uint32_t s_defer[RUN_EDGES];
+    constexpr int THREADS = NWARPS * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // [triangle bitmaps: NWARPS x TB_WORDS][match hashes: NWARPS x 2*CAP][warp scratch: NWARPS x WSTATE_INTS]
+    // [table (hashed only)][bitmap: hashed BITS/32 words | dense dense_words]
+    uint32_t* tb_all = smem_dyn;
+    uint32_t* mh_all = tb_all + NWARPS * TB_WORDS;
+    int* st_all = (int*)(mh_all + NWARPS * 2 * CAP);
+    uint32_t* tab = (uint32_t*)(st_all + NWARPS * WSTATE_INTS);
+    uint32_t* bm = tab + (DENSE ? 0 : MAX_SLOTS);
+    const int bm_words = DENSE ? dense_words : BITS / 32;
+    int* st = st_all + warp * WSTATE_INTS;
+    uint32_t* tb = tb_all + warp * TB_WORDS;
+    // warp-private view: keys[CAP] | counts[CAP] inside the warp's 2*CAP words; cooperative view: keys[NWARPS*CAP] |
+    // counts[NWARPS*CAP] over the whole region.  Both rely on the region being all zero between edges.
+    uint32_t* mh = mh_all + warp * 2 * CAP;
+    for (int p = tid; p < NWARPS * 2 * CAP; p += THREADS) mh_all[p] = 0u;
+    if (lane == 0) st[WS_NDIST] = 0;
+    if (DENSE) for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+    const uint2* runs = a.runs + (size_t)run_table_of(cls) * a.max_runs;
+    const unsigned int n_runs = a.plan->n_runs[run_table_of(cls)];
+    Member<DENSE> mem;
+    mem.tab = tab; mem.bm = bm; mem.bmask = BITS - 1; mem.mask = 0; mem.shift = 0;
+    int prev_va = -1;
+    while (true) {
+        __syncthreads();                                  // s_idx reuse
+        if (tid == 0) { s_idx = atomicAdd(&a.plan->next[cls], 1u); s_ndefer = 0; }
+        __syncthreads();
+        if (s_idx >= n_runs) break;
+        const uint2 run = runs[s_idx];                    // (first position in `order`, length); one tested endpoint
+        const uint32_t* ord = a.order + run.x;
+        const uint32_t* ova = a.ova + run.x;
+        const int q_end = (int)run.y;
+        const int va = (int)(ova[0] & 0x7fffffffu);
+        if (prev_va != va) {
+            const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
+            if (DENSE) {
+                if (prev_va >= 0) {                        // un-set the previous endpoint's bits (no full clear)
+                    const int ps = a.rowptr[prev_va], pd = a.rowptr[prev_va + 1] - ps;
+                    for (int p = tid; p < pd; p += THREADS) {
+                        const uint32_t k = (uint32_t)a.colidx[ps + p];
+                        atomicAnd(&bm[k >> 5], ~(1u << (k & 31u)));
+                    }
+                }
+            } else {
+                ro_geometry<MAX_SLOTS, 2>(da, mem.mask, mem.shift);
+                for (uint32_t s = tid; s <= mem.mask; s += THREADS) tab[s] = EMPTY;
+                for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+            }
+            __syncthreads();
+            for (int p = tid; p < da; p += THREADS) {
+                const uint32_t k = (uint32_t)a.colidx[sa + p];
+                if (DENSE) {
+                    atomicOr(&bm[k >> 5], 1u << (k & 31u));
+                } else {
+                    ro_insert(tab, mem.mask, mem.shift, k);
+                    atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
+                }
+            }
+            prev_va = va;
+            __syncthreads();
+        }
+        int p = 0;
+        while (p < q_end && (ova[p] >> 31)) {                // cooperative edges: the CTA is the team
+            cta_edge<NWARPS, CAP, DENSE>(a, mem, ord[p], va, st_all, tb_all, mh_all, s_acc, s_wtot);
+            __syncthreads();
+            ++p;
+        }
+        if (p > 0 && lane == 0) st[WS_NDIST] = 0;            // the cooperative stream state overlays the warp scratch
+        if (tid == 0) s_next = (unsigned)p;
+        __syncthreads();
+        while (true) {                                       // one warp per edge
+            unsigned int my = 0;
+            if (lane == 0) my = atomicAdd(&s_next, 1u);
+            my = __shfl_sync(FULL, my, 0);
+            if ((int)my >= q_end) break;
+            const uint32_t t = ord[my];
+            if (!warp_edge<CAP, DENSE>(a, mem, t, va, st, tb, mh, lane) && lane == 0)
+                s_defer[atomicAdd(&s_ndefer, 1)] = t;
+        }
+        __syncthreads();                                  // every warp is done with the run
+        const int nd = s_ndefer;
+        for (int d = 0; d < nd; ++d) {                       // too many distinct matches for one warp's hash
+            cta_edge<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_all, mh_all, s_acc, s_wtot);
+            __syncthreads();
+        }
+        if (nd > 0 && lane == 0) st[WS_NDIST] = 0;
     }
 }
 
@@ -668,8 +1247,17 @@ static inline uint32_t next_pow2_u32(uint64_t v) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// DCR_PAPER_MODE=hashed forces the hashed-table kernels (the path of graphs with more than DENSE_MAX_N nodes) on a
+// small graph — used by the parity tests to cover both paths.
+static bool use_dense_mode(int n) {
+    const char* m = getenv("DCR_PAPER_MODE");
+    if (m && m[0] == 'h') return false;
+    return n <= DENSE_MAX_N;
+}
+
 struct ScratchLayout {
-    size_t plan, node_s, bucket, order, va_cnt, va_cur, gtables, total;
+    size_t plan, node_s, bucket, order, ova, ovf, va_cnt, va_cur, grp, runs, gtables, total;
+    uint32_t max_runs;
     uint32_t gslots;
     int g_ctas;
 };
@@ -681,16 +1269,19 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.node_s = off; off = align_up(off + (size_t)n * sizeof(int64_t), 256);
     L.bucket = off; off = align_up(off + (size_t)count, 256);
     L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
-    L.va_cnt = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
-    L.va_cur = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
-    L.gslots = 0;
-    L.g_ctas = 0;
+    L.ova = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
+    L.ovf = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
+    L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
+    L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
+    L.grp = off; off = align_up(off + (size_t)4 * n * sizeof(uint32_t), 256);
+    // a group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(2n, count) groups (own + promoted)
+    L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>(2 * (int64_t)n, count) + 1);
+    L.runs = off; off = align_up(off + (size_t)2 * L.max_runs * sizeof(uint2), 256);
+    // tables of the CTA-team kernel (class X and the overflow list) live in global memory
+    L.gslots = next_pow2_u32((uint64_t)std::max(max_degree, 16) * 4);
+    L.g_ctas = sm_count();
     L.gtables = off;
-    if (max_degree > CLASS_DA2) {  // some edge may need a table beyond shared memory (or 32-bit slot counters)
-        L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
-        L.g_ctas = sm_count();
-        off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
-    }
+    off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
     L.total = off;
     return L;
 }
@@ -723,20 +1314,26 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.node_s = node_s;
     a.bucket = (uint8_t*)(base + L.bucket);
     a.order = (uint32_t*)(base + L.order);
+    a.ova = (uint32_t*)(base + L.ova);
+    a.ovf_order = (uint32_t*)(base + L.ovf);
     a.va_cnt = (uint32_t*)(base + L.va_cnt);
     a.va_cur = (uint32_t*)(base + L.va_cur);
+    a.grp = (uint32_t*)(base + L.grp);
+    a.runs = (uint2*)(base + L.runs);
+    a.max_runs = L.max_runs;
     a.n = n;
+    a.dense = use_dense_mode(n) ? 1 : 0;
     a.gtables = (uint32_t*)(base + L.gtables);
     a.gslots = L.gslots;
 
     DCR_CUDA(cudaMemsetAsync(a.plan, 0, sizeof(PaperPlan), st));
-    DCR_CUDA(cudaMemsetAsync(a.va_cnt, 0, (size_t)n * sizeof(uint32_t), st));
+    DCR_CUDA(cudaMemsetAsync(a.va_cnt, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
     int32_t* deg = (int32_t*)a.va_cur;     // va_cur is not used before order_kernel; cleared again below
     degree_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr, n, deg);
     DCR_LAUNCH_CHECK();
     node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, deg, n, node_s);
     DCR_LAUNCH_CHECK();
-    DCR_CUDA(cudaMemsetAsync(a.va_cur, 0, (size_t)n * sizeof(uint32_t), st));
+    DCR_CUDA(cudaMemsetAsync(a.va_cur, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
@@ -749,59 +1346,71 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
 
     const int sms = sm_count();
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
-    // heavy classes first: they own the long tail.  Persistent grids = SM count x resident CTAs per SM.
+    // Persistent grids = SM count x resident CTAs per SM.
     static bool attr_done_dev[MAX_DEVICES] = {false};
     const int dev = current_device();
     bool& attr_done = attr_done_dev[dev];
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
-    constexpr int mid_stream = 3 * heads_per_thread(MID_THREADS) * MID_THREADS + 8;
+    const int dense_words = (n + 31) / 32;
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
-    const int smem_big = (big_stream + BIG_BITS / 32 + BIG_SLOTS + BIG_SLOTS / 2) * (int)sizeof(uint32_t);
-    const int smem_mid = (mid_stream + MID_BITS / 32 + MID_SLOTS + MID_SLOTS / 2) * (int)sizeof(uint32_t);
-    const int smem_warp = WARP_TEAM_WARPS * (STREAM_INTS + WARP_BITS / 32 + WARP_SLOTS + WARP_SLOTS / 2) * (int)sizeof(uint32_t);
+    const int smem_l0 = L0_WARPS * (WSTATE_INTS + TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS) * (int)sizeof(uint32_t);
+    const int smem_g1 = (G1_SLOTS + G1_BITS / 32 + G1_WARPS * (TB_WORDS + 2 * G1_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    const int smem_g2 = (G2_SLOTS + G2_BITS / 32 + G2_WARPS * (TB_WORDS + 2 * G2_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    const int smem_gd = (dense_words + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    auto* k_g1 = paper_group_kernel<G1_WARPS, G1_SLOTS, G1_BITS, G1_CAP, G1_CTAS_PER_SM, false>;
+    auto* k_g2 = paper_group_kernel<G2_WARPS, G2_SLOTS, G2_BITS, G2_CAP, 1, false>;
+    auto* k_gd = paper_group_kernel<GD_WARPS, 64, 32, GD_CAP, GD_CTAS_PER_SM, true>;
     if (!attr_done) {
-        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big));
-        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<MID_THREADS, MID_SLOTS, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mid));
-        DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<32, WARP_SLOTS, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
         DCR_CUDA(cudaFuncSetAttribute(paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
+        DCR_CUDA(cudaFuncSetAttribute(paper_light_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l0));
+        DCR_CUDA(cudaFuncSetAttribute(k_g1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g1));
+        DCR_CUDA(cudaFuncSetAttribute(k_g2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g2));
+        const int smem_gd_max = (DENSE_MAX_N / 32 + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+        DCR_CUDA(cudaFuncSetAttribute(k_gd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gd_max));
         attr_done = true;
     }
-    // The class kernels are independent (disjoint edges, disjoint outputs).  They are launched on three streams
-    // forked from `st` — heaviest class first — so that, as the persistent CTAs of one class run out of work, CTAs
-    // of the next class take over the freed SMs instead of waiting for the slowest CTA (tail filling).
-    static cudaStream_t aux_dev[MAX_DEVICES][2] = {};
-    static cudaEvent_t fork_dev[MAX_DEVICES] = {}, join_dev[MAX_DEVICES][2] = {};
+    // The class kernels are independent (disjoint edges, disjoint outputs).  They are launched on streams forked
+    // from `st` so that, as the persistent CTAs of one class run out of work, CTAs of another class take over the
+    // freed SMs instead of waiting for the slowest CTA.
+    constexpr int N_AUX = 3;
+    static cudaStream_t aux_dev[MAX_DEVICES][N_AUX] = {};
+    static cudaEvent_t fork_dev[MAX_DEVICES] = {}, join_dev[MAX_DEVICES][N_AUX] = {};
     cudaStream_t* aux = aux_dev[dev];
     cudaEvent_t& ev_fork = fork_dev[dev];
     cudaEvent_t* ev_join = join_dev[dev];
     if (!aux[0]) {
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < N_AUX; ++q) {
             DCR_CUDA(cudaStreamCreateWithFlags(&aux[q], cudaStreamNonBlocking));
             DCR_CUDA(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
         }
         DCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     }
     DCR_CUDA(cudaEventRecord(ev_fork, st));
-    DCR_CUDA(cudaStreamWaitEvent(aux[0], ev_fork, 0));
-    DCR_CUDA(cudaStreamWaitEvent(aux[1], ev_fork, 0));
-    if (L.gslots) {
-        paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, st>>>(a, 3);
+    const int n_aux = a.dense ? 1 : N_AUX;
+    for (int q = 0; q < n_aux; ++q) DCR_CUDA(cudaStreamWaitEvent(aux[q], ev_fork, 0));
+    if (a.dense) {
+        k_gd<<<sms * GD_CTAS_PER_SM, GD_WARPS * 32, smem_gd, st>>>(a, CL_G1, dense_words);
+        DCR_LAUNCH_CHECK();
+    } else {
+        if (max_degree > CLASS_DA2) {
+            paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, aux[2]>>>(a, CL_X);
+            DCR_LAUNCH_CHECK();
+        }
+        k_g2<<<sms, G2_WARPS * 32, smem_g2, st>>>(a, CL_G2, 0);
+        DCR_LAUNCH_CHECK();
+        k_g1<<<sms * G1_CTAS_PER_SM, G1_WARPS * 32, smem_g1, aux[1]>>>(a, CL_G1, 0);
         DCR_LAUNCH_CHECK();
     }
-    paper_edge_kernel<BIG_THREADS, BIG_SLOTS, false><<<sms, BIG_THREADS, smem_big, st>>>(a, 2);
+    paper_light_warp_kernel<<<sms * L0_CTAS_PER_SM, L0_WARPS * 32, smem_l0, aux[0]>>>(a);
     DCR_LAUNCH_CHECK();
-    paper_edge_kernel<MID_THREADS, MID_SLOTS, false><<<sms * MID_CTAS_PER_SM, MID_THREADS, smem_mid, aux[0]>>>(a, 1);
-    DCR_LAUNCH_CHECK();
-    paper_edge_kernel<32, WARP_SLOTS, false><<<sms * WARP_CTAS_PER_SM, WARP_TEAM_WARPS * 32, smem_warp, aux[1]>>>(a, 0);
-    DCR_LAUNCH_CHECK();
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < n_aux; ++q) {
         DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));
         DCR_CUDA(cudaStreamWaitEvent(st, ev_join[q], 0));
     }
+    // edges whose CTA-wide match hash overflowed (rare: thousands of distinct matched neighbours of va)
+    paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, st>>>(a, CL_OVF);
+    DCR_LAUNCH_CHECK();
     paper_value_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));

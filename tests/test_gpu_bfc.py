@@ -11,6 +11,18 @@ from helpers import dense_of, gnp, golden, sym_edge_index, toy_graphs
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "hashed"])
+def paper_mode(request, monkeypatch):
+    """Both membership structures of the paper-flavour kernels: ``auto`` picks the exact shared-memory bitmap of
+    N(a) (every graph here has n <= DENSE_MAX_N), ``hashed`` forces the hashed-bitmap + table kernels that graphs
+    with more nodes take (dcr_bfc_paper.cu reads DCR_PAPER_MODE on every call)."""
+    if request.param == "hashed":
+        monkeypatch.setenv("DCR_PAPER_MODE", "hashed")
+    else:
+        monkeypatch.delenv("DCR_PAPER_MODE", raising=False)
+    return request.param
+
+
 def _csr(ei, n):
     from dcr import bfc, graph
     rowptr, col = graph.undirected_csr(ei, n)
@@ -36,7 +48,7 @@ def _check_paper(ei, n, tag):
     return got
 
 
-def test_paper_flavour_golden_reference_values():
+def test_paper_flavour_golden_reference_values(paper_mode):
     z = golden("paper_kat.npz")
     for name in (str(s) for s in z["names"]):
         ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
@@ -48,12 +60,12 @@ def test_paper_flavour_golden_reference_values():
 
 
 @pytest.mark.parametrize("seed", range(8))
-def test_paper_flavour_random_graphs(seed):
+def test_paper_flavour_random_graphs(seed, paper_mode):
     n = 20 + 17 * seed
     _check_paper(gnp(n, [0.05, 0.1, 0.2, 0.4][seed % 4], seed), n, f"gnp{seed}")
 
 
-def test_paper_flavour_edge_cases():
+def test_paper_flavour_edge_cases(paper_mode):
     # single edge, star (deg_min == 1 everywhere), disjoint union with isolated nodes, complete graph
     _check_paper(sym_edge_index([(0, 1)], 2), 2, "k2")
     _check_paper(sym_edge_index([(0, i) for i in range(1, 40)], 45), 45, "star+isolated")
@@ -62,8 +74,9 @@ def test_paper_flavour_edge_cases():
         _check_paper(ei, n, name)
 
 
-def test_paper_flavour_cta_team_and_global_table_paths():
-    # hubs push d_i + d_j past 512 (CTA team, shared-memory table) and past 16384 (CTA team, global table)
+def test_paper_flavour_cta_team_and_global_table_paths(paper_mode):
+    # hubs: tested endpoints of degree ~700-900 (group kernel G1 / dense group) and ~17000 (hashed: class X, the
+    # CTA-team kernel with its table in global memory; dense: still the group kernel), cooperative edges included
     rng = np.random.default_rng(5)
     n = 3000
     pairs = [(0, i) for i in range(1, 700)] + [(1, i) for i in range(2, 900)]
@@ -88,7 +101,30 @@ def test_paper_flavour_cta_team_and_global_table_paths():
         assert got["bfc"][e] == float(f[6])
 
 
-def test_paper_flavour_named_shapes_vs_oracle():
+def _many_distinct_matches(n_k, n_m, per_m):
+    """Edge (0,1): 0 has n_k pure neighbours, 1 has n_m; every pure neighbour of 1 is adjacent to per_m DISTINCT pure
+    neighbours of 0 -> #squares at 0 is n_m*per_m distinct vertices although the stream is short."""
+    a, b = 0, 1
+    ks = list(range(2, 2 + n_k))
+    ms = list(range(2 + n_k, 2 + n_k + n_m))
+    pairs = [(a, b)] + [(a, k) for k in ks] + [(b, m) for m in ms]
+    for q, m in enumerate(ms):
+        pairs += [(m, ks[q * per_m + r]) for r in range(per_m)]
+    n = 2 + n_k + n_m
+    return sym_edge_index(pairs, n), n
+
+
+def test_paper_flavour_match_hash_overflow_paths(paper_mode):
+    # 500 distinct matched neighbours: more than one warp's match hash holds -> retried by the whole CTA;
+    # 2400: more than the CTA-wide hash holds -> global overflow list -> CTA-team kernel
+    for n_k, n_m, per_m in ((600, 10, 50), (2600, 40, 60)):
+        ei, n = _many_distinct_matches(n_k, n_m, per_m)
+        got = _check_paper(ei, n, f"distinct{n_m * per_m}")
+        e01 = np.flatnonzero((got["edges"][:, 0] == 0) & (got["edges"][:, 1] == 1))[0]
+        assert max(got["sq_i"][e01], got["sq_j"][e01]) == n_m * per_m
+
+
+def test_paper_flavour_named_shapes_vs_oracle(paper_mode):
     from dcr.synth import named_graph
     for name in ("cornell", "wisconsin", "cora"):
         ei, n = named_graph(name)
@@ -315,7 +351,7 @@ def test_tensor_core_cuda_flavour_matches_sparse_route_and_oracle():
             assert np.array_equal(C.cpu().numpy().view(np.uint32), ref["C"].view(np.uint32))
 
 
-def test_full_size_arxiv_shape_exact_against_c_oracle():
+def test_full_size_arxiv_shape_exact_against_c_oracle(paper_mode):
     """Config 5 at full size: every one of the 1,166,243 edges against the plain-C restatement of bfc_naive.py
     (ints bit-exact, fp64 bit-exact), plus the size-independent properties."""
     import os
