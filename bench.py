@@ -42,7 +42,7 @@ WORKLOADS = {
 # DRAM traffic of the edge kernels of ONE pass over the arxiv-shaped graph, from the committed ncu capture
 # (17.64 + 22.60 + 26.82 MB read, 0.23 + 1.58 + 3.26 MB written): the CSR is L2-resident, so this is ~1000x below the
 # algorithmic gather bytes.
-NCU_DRAM_BYTES_PER_PASS = 72.13e6
+NCU_DRAM_BYTES_PER_PASS = 78.37e6
 
 
 def load_peaks():
@@ -381,6 +381,11 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     step_ms = [a.elapsed_time(b) for a, b in step_ev]
     edge_ms = [a.elapsed_time(b) for a, b in edge_ev]
+    # where a step's time goes on this rank: planning (step begin -> first edge kernel), the edge kernels + value
+    # kernel, and what follows them (all-gather + re-interleave at N > 1)
+    plan_ms = [s0.elapsed_time(e0) for (s0, _), (e0, _) in zip(step_ev, edge_ev)]
+    tail_ms = [e1.elapsed_time(s1) for (_, s1), (_, e1) in zip(step_ev, edge_ev)]
+
     def untimed_step():
         flush.zero_()
         sh.run()
@@ -451,7 +456,9 @@ def run_ours(args):
         ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
         checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
 
-    launches_per_step = 6 + 3 + (1 if csr.max_degree > 16384 else 0) + 1 + (1 if world > 1 else 0)   # plan(6), edge classes, value, unshard
+    # kernels of one pass (dense mode, n <= 262144): degree, node_s, classify, split_zero, plan_ranges, plan_groups, order;
+    # paper_group_kernel + paper_light_warp_kernel; paper_value_kernel; unshard at N > 1
+    launches_per_step = 7 + 2 + 1 + (1 if world > 1 else 0)
     line = {
         "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -460,19 +467,21 @@ def run_ours(args):
                    "sharding": f"edge e -> rank e % {world}, graph replicated, one all-gather" if world > 1 else "single GPU",
                    "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
                    "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks", "wall_s_timed_region": wall,
-                   "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms]},
+                   "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms],
+                   "phase_ms_rank0": {"plan": round(float(np.mean(plan_ms)), 4), "edge_kernels": round(edge_ms_avg, 4),
+                                      "gather_unshard": round(float(np.mean(tail_ms)), 4)}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / args.steps,
                 "what": "dcr.dist.ShardedPaperBFC.run on host (pinned) CSR + edge list; results copied back to pinned host memory"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {
-            "bound": "hbm", "kernel": "paper_edge_kernel (CTA-team + warp-team launches of one step)",
+            "bound": "hbm", "kernel": "paper_group_kernel + paper_light_warp_kernel (the two edge kernels of one step, concurrent)",
             "achieved": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
             "traffic": NCU_DRAM_BYTES_PER_PASS if (world == 1 and args.workload == "arxiv") else None,
-            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the three class "
-                              "launches of one pass (profiles/r01_v10_ncu_full_paper_edge_kernel.csv)",
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the two edge-kernel "
+                              "launches of one pass (profiles/r01_v18_ncu_full_edge_kernels.csv)",
             "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
             "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
             "note": "algorithmic bytes = SURVEY.md §8d B_gather of this rank's edges (every 2-hop list once per edge, "

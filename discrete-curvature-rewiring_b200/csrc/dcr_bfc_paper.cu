@@ -39,35 +39,66 @@ namespace dcr {
 constexpr uint32_t EMPTY = 0xffffffffu;
 constexpr uint32_t KEYMASK = 0x3fffffffu;
 // Edge classes.  d_a = degree of the TESTED endpoint (the one whose neighbour set goes into the hash table).
-//   L0  d_a <= 128, stream <= COOP_G1    warp per edge, warp-private 256-slot table
-//   G1  d_a <= 1024                      CTA-shared 2048-slot table, 8 warps:  warp per edge; CTA per edge above COOP_G1
-//   G2  d_a <= 16384                     CTA-shared 32768-slot table, 16 warps: warp per edge; CTA per edge above COOP_G2
+//   L0  d_a <= 128, stream <= COOP_L0    warp per edge, warp-private 256-slot table
+//   G1  d_a <= 1024, stream <= COOP_G    CTA-shared 2048-slot table, 8 warps, warp per edge
+//   G2  d_a <= 16384, stream <= COOP_G   CTA-shared 32768-slot table, 16 warps, warp per edge
+//   C1 / C2  the longer streams          same kernels and tables as G1 / G2, one CTA per edge, drained FIRST
 //   X   d_a > 16384                      1024-thread CTA team, table and 32-bit counters in global memory (L2)
 //   dense mode (n <= DENSE_MAX_N): L0 as above, everything else in ONE group class (G1 id) whose membership
 //   structure is an exact bitmap over all node ids in shared memory — no table, no false positives, any degree
-//   (overflow list: light / cooperative edges whose match hash filled up -> the 1024-thread CTA-team kernel)
-enum { CL_L0 = 0, CL_G1, CL_G2, CL_X, N_CLASSES, CL_OVF = N_CLASSES };
+//   (an edge whose per-warp match hash fills up is retried by its CTA with the CTA-wide hash, and if that fills up
+//    too, with a hash in global memory sized for the largest degree)
+enum { CL_L0 = 0, CL_G1, CL_G2, CL_C1, CL_C2, CL_X, N_CLASSES };   // C1 / C2: the cooperative edges of G1 / G2
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
-#ifndef DCR_COOP_G1
-#define DCR_COOP_G1 24576
+#ifndef DCR_COOP_L0
+#define DCR_COOP_L0 8192
 #endif
-#ifndef DCR_COOP_G2
-#define DCR_COOP_G2 24576
+#ifndef DCR_COOP_G
+#define DCR_COOP_G 24576
 #endif
-constexpr long long COOP_G1 = DCR_COOP_G1, COOP_G2 = DCR_COOP_G2;
-// Inside the range of one tested endpoint the edges are ordered by size bucket, heaviest first (cooperative edges,
-// then stream > 2048, > 512, the rest): warps that pull edges of a run from a shared counter then finish together.
-constexpr int N_SIZE_BUCKETS = 4, N_SLOTS = N_SIZE_BUCKETS + 1;   // slot 4: edges of an L0 vertex promoted to G1
+// stream length above which an edge is cooperative (one CTA per edge; L0 vertices hand such edges to C1).  Measured on
+// the arxiv shape at 1/1 and 1/8 of the edges per call: finer items (8192 / 4096) lose at both sizes — the CTA path
+// costs more per element than the warp path.
+constexpr long long COOP_L0 = DCR_COOP_L0, COOP_G = DCR_COOP_G;
+// Inside the range of one tested endpoint the light edges are ordered by size bucket, heaviest first (stream > 2048,
+// > 512, the rest): warps that pull edges of a run from a shared counter then finish together.  Slot 0 of a vertex
+// counts its cooperative edges: they form a second group of the vertex, in the cooperative class of its degree.
+constexpr int N_SLOTS = 4;
+// SPLIT edges: a stream beyond SPLIT_STREAM entries (hub–hub edges; a handful per graph, but each would occupy one CTA
+// for longer than the rest of the pass takes) is cut by head ranges into parts of about SPLIT_PART entries that
+// different CTAs process as independent work items; per-list results add up, the per-neighbour match counts meet in
+// ONE hash in global memory per split edge, and the part that finishes last collects it and writes the result.
+#ifndef DCR_SPLIT_STREAM
+#define DCR_SPLIT_STREAM 98304
+#endif
+constexpr long long SPLIT_STREAM = DCR_SPLIT_STREAM, SPLIT_PART = 16384;
+constexpr int MAX_SPLIT = 2048, MAX_PARTS = 32;
+constexpr size_t SHASH_WORDS = (size_t)32 << 20;      // pool of the split edges' match hashes (128 MiB per kernel)
+constexpr int SPLIT_HASH_CAP = 8192;                  // largest hash of a split edge (an edge that fills it is redone by one CTA)
+struct SplitEdge {            // one per split edge, in the scratch buffer (zeroed with the plan)
+    uint32_t t;               // local edge index
+    int parts;                // number of parts
+    int first_item;           // index of its first work item
+    int tri, sq_b, g_b;       // accumulated over the parts
+    int n_distinct;           // of the global hash
+    int parts_done;
+    int overflow;             // some part found the hash full
+    uint32_t hash_off, hash_cap;   // its match hash inside the pool: 2*hash_cap words at word offset hash_off
+};
 constexpr long long SIZE_B1 = 2048, SIZE_B2 = 512;
 // A group (all edges with the same tested endpoint) of a group class is cut into R = ceil(count / RUN_EDGES) runs;
 // the edge with rank s in the size order goes to run s mod R, so EVERY run holds the same mix — heaviest first,
 // lightest last — and the warps of a CTA that pull its edges from a shared counter finish together.
-constexpr int RUN_EDGES = 64;
+#ifndef DCR_RUN_EDGES
+#define DCR_RUN_EDGES 64
+#endif
+constexpr int RUN_EDGES = DCR_RUN_EDGES;
 #ifndef DCR_COOP_SLICE
 #define DCR_COOP_SLICE 512
 #endif
 constexpr int COOP_SLICE = DCR_COOP_SLICE;        // cooperative edges: flat-stream elements per work item of a warp
 __host__ __device__ inline int run_table_of(int cls) { return cls == CL_G2 ? 1 : 0; }
+__host__ __device__ inline int coop_class_of(int cls) { return cls == CL_G2 ? CL_C2 : CL_C1; }
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
 __host__ __device__ constexpr int heads_per_thread(int team) { return team >= 1024 ? 1 : 4; }   // CTA stream state must fit beside the table
 // Membership pre-filter: a hashed bitmap of N(va) (bit index = node id mod B).  Almost every streamed element is NOT
@@ -108,16 +139,26 @@ constexpr int G2_SLOTS = 32768, G2_BITS = 131072, G2_CAP = 256, G2_WARPS = 16;
 constexpr int GD_CAP = 256, GD_WARPS = 8, GD_CTAS_PER_SM = DCR_GD_CTAS, DENSE_MAX_N = 262144;
 // per-warp scratch (ints): beg[32] | len[32] | lcnt[32] | n_distinct + pad
 constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 96, WSTATE_INTS = 100;
-constexpr int TB_WORDS = 32;                 // per-warp triangle bitmap: 1024 bits
+// Common neighbours T = N(va) ∩ N(vb) must not count as matches, and they are FREQUENT in the stream of a hub–hub
+// edge (hubs are each other's neighbours), so membership in T has to be exact and on chip:
+//   TRI_SET     warp path: exact open-addressing set of T in the warp's scratch (TB_WORDS slots, |T| <= TRI_DEFER in
+//               the group kernels — richer edges go to the CTA path; 256 slots in L0 where |T| <= d_a <= 128)
+//   TRI_DENSE   CTA path, dense mode: a second exact bitmap over all node ids
+//   TRI_HASHED  CTA path, hashed mode: 64K-bit hashed bitmap, positives confirmed by binary search in N(vb)
+enum { TRI_SET = 0, TRI_DENSE = 1, TRI_HASHED = 2 };
+constexpr int TB_WORDS = 64, L0_TB_WORDS = 256;
+constexpr int COOP_TB_WORDS = 2048;
+constexpr int TRI_DEFER = 32;                // light edges with more triangles go to the CTA path
 
 struct PaperPlan {           // lives at the head of the scratch buffer
     unsigned int grouped[N_CLASSES + 1];         // [c] = #edges of class c
     unsigned int group_cursor[N_CLASSES];        // range reservation inside the classes
     unsigned int class_begin[N_CLASSES + 1];
-    unsigned int next[N_CLASSES + 1];            // work-stealing counters ([CL_OVF] = overflow list)
+    unsigned int next[N_CLASSES + 1];            // work-stealing counters
     unsigned int n_runs[2];                      // run tables of the group classes (G1, G2)
-    unsigned int ovf_count;                      // edges deferred to the CTA-team path
-    unsigned int pad[3];
+    unsigned int n_split[2], split_items[2], split_next[2];   // split edges of the kernels of G1 / G2
+    unsigned long long shash_used[2];            // words of the hash pools handed out
+    SplitEdge split[2][MAX_SPLIT];
 };
 
 struct PaperArgs {
@@ -135,17 +176,20 @@ struct PaperArgs {
     const int64_t* node_s;
     uint8_t* bucket;       // [count] class of local edge t (BUCKET_TRIVIAL: nothing to do)
     uint32_t* order;       // [count] local indices t, class by class, grouped by tested endpoint inside a class
-    uint32_t* ova;         // [count] tested endpoint of order[pos]; bit 31: cooperative (CTA per edge)
-    uint32_t* ovf_order;   // [count] overflow list (local indices t)
-    uint32_t* va_cnt;      // [N_SLOTS][n] #edges per (size bucket | promoted, tested endpoint); then: rank offset inside the group
+    uint32_t* ova;         // [count] tested endpoint of order[pos]
+    uint32_t* va_cnt;      // [N_SLOTS][n] #edges per (cooperative | size bucket, tested endpoint); then: rank offset inside the group
     uint32_t* va_cur;      // [N_SLOTS][n] fill cursors
-    uint32_t* grp;         // [4][n] (start, count) of the vertex's own group and of its promoted group in `order`
+    uint32_t* grp;         // [4][n] (start, count) of the vertex's light group and of its cooperative group in `order`
     uint2* runs;           // [2][max_runs] (first position, length) of the runs of the group classes
     uint32_t max_runs;
     int n;
     int dense;             // 1: n is small enough for an exact bitmap of N(va) in shared memory (classes L0 + G1 only)
     uint32_t* gtables;     // class-X tables in global memory, gslots per CTA
     uint32_t gslots;
+    uint32_t* ghash;       // last-resort match hashes in global memory: 2*ghash_cap words per CTA of a group kernel
+    uint32_t ghash_cap;
+    uint32_t* shash;       // [2][SHASH_WORDS] pools of the split edges' match hashes (the used part is zeroed per call)
+    uint32_t* split_item;  // [2][MAX_SPLIT * MAX_PARTS] work item -> split edge << 8 | part
 };
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 2654435761u) >> shift; }
@@ -221,7 +265,7 @@ __global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t*
     if (lane == 0) node_s[v] = s;
 }
 
-constexpr int BUCKET_TRIVIAL = 255;
+constexpr int BUCKET_TRIVIAL = 255, BUCKET_SPLIT = 254;
 
 __device__ __forceinline__ int degree_class(int da, int dense) {
     if (dense) return da <= CLASS_DA0 ? CL_L0 : CL_G1;       // the dense group kernel takes any degree
@@ -229,7 +273,7 @@ __device__ __forceinline__ int degree_class(int da, int dense) {
 }
 
 // (tested endpoint, its degree, the other degree, stream size) of an edge, and where the plan puts it
-struct EdgeRole { int va, da, db, cls, slot; bool coop; long long stream; };
+struct EdgeRole { int va, da, db, cls, slot; long long stream; };
 __device__ __forceinline__ EdgeRole edge_role(const PaperArgs& a, int i, int j, int di, int dj) {
     const long long ca = a.node_s[j] - di, cb = a.node_s[i] - dj;     // 2-hop entries behind j / behind i
     const bool swapped = cb < ca;                                      // stream i's side, test j
@@ -239,16 +283,9 @@ __device__ __forceinline__ EdgeRole edge_role(const PaperArgs& a, int i, int j, 
     r.db = swapped ? di : dj;
     r.stream = swapped ? cb : ca;
     r.cls = degree_class(r.da, a.dense);
-    r.coop = false;
     r.slot = r.stream > SIZE_B1 ? 1 : (r.stream > SIZE_B2 ? 2 : 3);
-    if (r.cls == CL_L0 && r.stream > COOP_G1) {          // too long for one warp: promoted to the G1 kernel
-        r.cls = CL_G1;
-        r.coop = true;
-        r.slot = N_SIZE_BUCKETS;
-    } else if ((r.cls == CL_G1 && r.stream > COOP_G1) || (r.cls == CL_G2 && r.stream > COOP_G2)) {
-        r.coop = true;
-        r.slot = 0;
-    } else if (r.cls == CL_X) {
+    if (r.cls == CL_L0 ? r.stream > COOP_L0 : (r.cls != CL_X && r.stream > COOP_G)) {
+        r.cls = coop_class_of(r.cls);                    // too long for one warp (L0 -> C1: the G1 kernel takes any degree below its own)
         r.slot = 0;
     }
     return r;
@@ -268,13 +305,46 @@ __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
             a.bucket[t] = BUCKET_TRIVIAL;
         } else {
             const EdgeRole r = edge_role(a, i, j, di, dj);
-            a.bucket[t] = (uint8_t)r.cls;
-            atomicAdd(&s_grp[r.cls], 1u);
-            atomicAdd(&a.va_cnt[(size_t)r.slot * a.n + r.va], 1u);
+            bool split = false;
+            if ((r.cls == CL_C1 || r.cls == CL_C2) && r.stream > SPLIT_STREAM) {
+                const int k = r.cls == CL_C2 ? 1 : 0;
+                // distinct matched neighbours <= d_a: a hash of >= 2*d_a slots never passes its 3/4 fill limit
+                const uint32_t cap = 1u << (32 - __clz(min(max(2 * r.da, 1024), SPLIT_HASH_CAP) - 1));
+                const unsigned long long off = atomicAdd(&a.plan->shash_used[k], 2ull * cap);
+                const unsigned int sidx = (off + 2ull * cap <= SHASH_WORDS) ? atomicAdd(&a.plan->n_split[k], 1u) : MAX_SPLIT;
+                if (sidx < (unsigned)MAX_SPLIT) {        // (table or pool exhausted: an ordinary cooperative edge)
+                    SplitEdge& se = a.plan->split[k][sidx];
+                    se.t = (uint32_t)t;
+                    se.parts = (int)min((long long)min(MAX_PARTS, r.db), (r.stream + SPLIT_PART - 1) / SPLIT_PART);
+                    se.first_item = (int)atomicAdd(&a.plan->split_items[k], (unsigned)se.parts);
+                    se.hash_off = (uint32_t)off;
+                    se.hash_cap = cap;
+                    for (int q = 0; q < se.parts; ++q)
+                        a.split_item[(size_t)k * MAX_SPLIT * MAX_PARTS + se.first_item + q] = (sidx << 8) | (unsigned)q;
+                    split = true;
+                }
+            }
+            if (split) {
+                a.bucket[t] = BUCKET_SPLIT;
+            } else {
+                a.bucket[t] = (uint8_t)r.cls;
+                atomicAdd(&s_grp[r.cls], 1u);
+                atomicAdd(&a.va_cnt[(size_t)r.slot * a.n + r.va], 1u);
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
+}
+
+// zero the handed-out part of the split edges' hash pools
+__global__ void __launch_bounds__(256) split_zero_kernel(PaperArgs a) {
+    for (int k = 0; k < 2; ++k) {
+        const size_t used = (size_t)min(a.plan->shash_used[k], (unsigned long long)SHASH_WORDS);
+        uint4* p = (uint4*)(a.shash + (size_t)k * SHASH_WORDS);
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < used / 4; q += (size_t)gridDim.x * blockDim.x)
+            p[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // Class ranges (one thread).
@@ -302,35 +372,47 @@ __device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned 
 }
 
 // Every vertex that is the tested endpoint of edges reserves a contiguous range of `order` inside the class of its
-// degree, and L0 vertices a second one in G1 for their promoted edges.  The order of the ranges is irrelevant — only
-// contiguity matters for the table reuse — so one atomicAdd per such vertex replaces a scan over all vertices.
-// Inside a group the size buckets follow each other, heaviest first; group classes also get their run table.
+// degree for its light edges and a second one inside the cooperative class for its cooperative edges.  The order of
+// the ranges is irrelevant — only contiguity matters for the table reuse — so one atomicAdd per such vertex replaces
+// a scan over all vertices.  Inside a light group the size buckets follow each other, heaviest first; the group
+// classes also get their run table.
 __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
+    // ranges are reserved per block (shared-memory counters, then ONE global atomic per class and block): one global
+    // atomic per vertex would serialise ~n operations on a handful of addresses
+    __shared__ unsigned int s_cnt[N_CLASSES], s_base[N_CLASSES];
+    if (threadIdx.x < N_CLASSES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.n) return;
-    unsigned int c[N_SLOTS], own = 0;
+    unsigned int c[N_SLOTS] = {0, 0, 0, 0}, own = 0, own_off = 0, coop_off = 0;
+    int cls = 0, cc = 0;
+    if (v < a.n) {
 #pragma unroll
-    for (int q = 0; q < N_SLOTS; ++q) {
-        c[q] = a.va_cnt[(size_t)q * a.n + v];
-        if (q < N_SIZE_BUCKETS) {
-            a.va_cnt[(size_t)q * a.n + v] = own;        // rank offset of the bucket inside the group
-            own += c[q];
+        for (int q = 0; q < N_SLOTS; ++q) {
+            c[q] = a.va_cnt[(size_t)q * a.n + v];
+            if (q > 0) {
+                a.va_cnt[(size_t)q * a.n + v] = own;        // rank offset of the bucket inside the light group
+                own += c[q];
+            }
         }
+        a.va_cnt[v] = 0;
+        cls = degree_class(a.rowptr[v + 1] - a.rowptr[v], a.dense);
+        cc = coop_class_of(cls);
+        if (own) own_off = atomicAdd(&s_cnt[cls], own);
+        if (c[0]) coop_off = atomicAdd(&s_cnt[cc], c[0]);
     }
-    a.va_cnt[(size_t)N_SIZE_BUCKETS * a.n + v] = 0;
+    __syncthreads();
+    if (threadIdx.x < N_CLASSES && s_cnt[threadIdx.x])
+        s_base[threadIdx.x] = a.plan->class_begin[threadIdx.x] + atomicAdd(&a.plan->group_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
     if (own) {
-        const int cls = degree_class(a.rowptr[v + 1] - a.rowptr[v], a.dense);
-        const unsigned int gstart = a.plan->class_begin[cls] + atomicAdd(&a.plan->group_cursor[cls], own);
+        const unsigned int gstart = s_base[cls] + own_off;
         a.grp[v] = gstart;
         a.grp[(size_t)a.n + v] = own;
         if (cls == CL_G1 || cls == CL_G2) emit_runs(a, cls, gstart, own);
     }
-    const unsigned int cp = c[N_SIZE_BUCKETS];
-    if (cp) {
-        const unsigned int gstart = a.plan->class_begin[CL_G1] + atomicAdd(&a.plan->group_cursor[CL_G1], cp);
-        a.grp[(size_t)2 * a.n + v] = gstart;
-        a.grp[(size_t)3 * a.n + v] = cp;
-        emit_runs(a, CL_G1, gstart, cp);
+    if (c[0]) {
+        a.grp[(size_t)2 * a.n + v] = s_base[cc] + coop_off;
+        a.grp[(size_t)3 * a.n + v] = c[0];
     }
 }
 
@@ -338,31 +420,26 @@ __global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.count) return;
     const int b = a.bucket[t];
-    if (b == BUCKET_TRIVIAL) return;
+    if (b == BUCKET_TRIVIAL || b == BUCKET_SPLIT) return;
     const int64_t e = a.e_first + t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
     const EdgeRole r = edge_role(a, i, j, di, dj);
     const size_t slot = (size_t)r.slot * a.n + r.va;
     const unsigned int s = a.va_cnt[slot] + atomicAdd(&a.va_cur[slot], 1u);
-    const size_t g = (r.slot == N_SIZE_BUCKETS ? (size_t)2 * a.n : 0) + r.va;
+    const size_t g = (r.slot == 0 ? (size_t)2 * a.n : 0) + r.va;
     const unsigned int gstart = a.grp[g], cnt = a.grp[g + a.n];
     const unsigned int pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, s) : gstart + s;
     a.order[pos] = (uint32_t)t;
-    a.ova[pos] = (uint32_t)r.va | (r.coop ? 0x80000000u : 0u);
+    a.ova[pos] = (uint32_t)r.va;
 }
 
 // where a class kernel finds its work: a range of `order` (classes) or the overflow list
 struct WorkSource { const uint32_t* order; unsigned int count; unsigned int* next; };
 __device__ __forceinline__ WorkSource work_source(const PaperArgs& a, int cls) {
     WorkSource w;
-    if (cls == CL_OVF) {
-        w.order = a.ovf_order;
-        w.count = a.plan->ovf_count;
-    } else {
-        w.order = a.order + a.plan->class_begin[cls];
-        w.count = a.plan->class_begin[cls + 1] - a.plan->class_begin[cls];
-    }
+    w.order = a.order + a.plan->class_begin[cls];
+    w.count = a.plan->class_begin[cls + 1] - a.plan->class_begin[cls];
     w.next = &a.plan->next[cls];
     return w;
 }
@@ -711,65 +788,92 @@ struct Member {
     __device__ __forceinline__ bool has(uint32_t k) const { return maybe(k) && confirm(k); }
 };
 
-// Match hash: keys[CAP] (node id + 1) | counts[CAP].  Returns false when the hash is (nearly) full.
-template <int CAP>
-__device__ __forceinline__ bool match_add(uint32_t* mh, int* n_distinct, uint32_t k) {
-    const uint32_t key = k + 1u;
-    uint32_t p = (key * 0x9E3779B1u) >> (32 - ilog2_c(CAP));
-    for (int tries = 0; tries < CAP; ++tries) {
-        uint32_t v = *(volatile uint32_t*)(mh + p);
-        if (v == 0u) {
-            if (*(volatile int*)n_distinct >= CAP / 4 * 3) return false;
-            v = atomicCAS(&mh[p], 0u, key);
-            if (v == 0u) atomicAdd(n_distinct, 1);
-        }
-        if (v == 0u || v == key) {
-            atomicAdd(&mh[CAP + p], 1u);
-            return true;
-        }
-        p = (p + 1) & (CAP - 1);
+// Match hash: keys[cap] (node id + 1) | counts[cap], cap a power of two; lives in shared memory (per warp, or the
+// per-warp hashes of a CTA taken together) or, as a last resort, in global memory.
+struct MatchHash {
+    uint32_t* mh;
+    int* n_distinct;
+    uint32_t cap;
+    int shift;            // 32 - log2(cap)
+    __device__ __forceinline__ void init(uint32_t* p, int* nd, uint32_t c) {
+        mh = p; n_distinct = nd; cap = c; shift = __clz(c) + 1;
     }
-    return false;
-}
-// (#distinct keys, largest count) of this thread's share of the hash; clears what it reads
-template <int CAP>
-__device__ __forceinline__ void match_collect(uint32_t* mh, int first, int stride, int& sq_a, int& g_a) {
-    for (int p = first; p < CAP; p += stride) {
-        if (mh[p]) {
-            ++sq_a;
-            g_a = max(g_a, (int)mh[CAP + p]);
-            mh[p] = 0u;
-            mh[CAP + p] = 0u;
+    // false when the hash is (nearly) full
+    __device__ __forceinline__ bool add(uint32_t k) {
+        const uint32_t key = k + 1u;
+        uint32_t p = (key * 0x9E3779B1u) >> shift;
+        for (uint32_t tries = 0; tries < cap; ++tries) {
+            uint32_t v = *(volatile uint32_t*)(mh + p);
+            if (v == 0u) {
+                if (*(volatile int*)n_distinct >= (int)(cap / 4 * 3)) return false;
+                v = atomicCAS(&mh[p], 0u, key);
+                if (v == 0u) atomicAdd(n_distinct, 1);
+            }
+            if (v == 0u || v == key) {
+                atomicAdd(&mh[cap + p], 1u);
+                return true;
+            }
+            p = (p + 1) & (cap - 1);
+        }
+        return false;
+    }
+    // (#distinct keys, largest count) of this thread's share of the hash; clears what it reads
+    __device__ __forceinline__ void collect(int first, int stride, int& sq_a, int& g_a) {
+        for (uint32_t p = first; p < cap; p += stride) {
+            if (*(volatile uint32_t*)(mh + p)) {
+                ++sq_a;
+                g_a = max(g_a, (int)*(volatile uint32_t*)(mh + cap + p));
+                mh[p] = 0u;
+                mh[cap + p] = 0u;
+            }
         }
     }
-}
+};
 
 // Everything a warp needs to test streamed elements of one edge (va tested, vb streamed).
-template <int CAP, int TBW, bool DENSE>
+template <bool DENSE, int TM>
 struct EdgeCtx {
     const int32_t* __restrict__ colidx;
     Member<DENSE> mem;
-    const uint32_t* tb;      // hashed bitmap of the common neighbours N(va) ∩ N(vb) (TBW words)
-    uint32_t* mh;            // match hash (2*CAP words)
-    int* n_distinct;
+    const uint32_t* tb;      // the structure that answers "k in T" (see TRI_*)
+    uint32_t tb_mask;        // TRI_SET: slots - 1; TRI_HASHED: words - 1
+    MatchHash hash;
     int vb, sb, db;
     bool ovf;
+    __device__ __forceinline__ bool in_triangle(uint32_t kk) const {
+        if (TM == TRI_DENSE) return (tb[kk >> 5] >> (kk & 31u)) & 1u;
+        if (TM == TRI_SET) {
+            uint32_t h = (kk * 2654435761u) >> 16 & tb_mask;
+            while (true) {
+                const uint32_t v = tb[h];
+                if (v == kk) return true;
+                if (v == EMPTY) return false;
+                h = (h + 1) & tb_mask;
+            }
+        }
+        return ((tb[(kk >> 5) & tb_mask] >> (kk & 31u)) & 1u) && find_sorted(colidx, sb, db, (int)kk) >= 0;
+    }
     // k in N(m), m a pure neighbour of vb: is (m,k) an edge of the bipartite graph M_b – M_a?  Split in two so that the
     // streaming loops stay small: hit() is the per-element filter (one shared-memory load), slow() runs once per
     // candidate — ONE copy of it per loop, shared by all the elements of a window.
     __device__ __forceinline__ bool hit(int k) const { return mem.maybe((uint32_t)k) && k != vb; }
     __device__ __forceinline__ int slow(int k) {
         const uint32_t kk = (uint32_t)k;
-        if (mem.confirm(kk)) {   // k in N(va); a common neighbour only if its triangle bit is set AND it is in N(vb)
-            const bool maybe_tri = (tb[(kk >> 5) & (TBW - 1)] >> (kk & 31u)) & 1u;
-            if (!maybe_tri || find_sorted(colidx, sb, db, k) < 0) {
-                if (!match_add<CAP>(mh, n_distinct, kk)) ovf = true;
-                return 1;
-            }
+        if (mem.confirm(kk) && !in_triangle(kk)) {     // k in N(va) and not a common neighbour
+            if (!hash.add(kk)) ovf = true;
+            return 1;
         }
         return 0;
     }
 };
+__device__ __forceinline__ void tri_set_insert(uint32_t* ts, uint32_t mask, uint32_t kk) {
+    uint32_t h = (kk * 2654435761u) >> 16 & mask;
+    while (true) {
+        const uint32_t v = atomicCAS(&ts[h], EMPTY, kk);
+        if (v == EMPTY || v == kk) return;
+        h = (h + 1) & mask;
+    }
+}
 
 // the u-th of UNROLL registers (u is not a compile-time constant: a select chain instead of local memory)
 template <int N>
@@ -888,40 +992,50 @@ __device__ __forceinline__ void warp_chunk(const PaperArgs& a, Ctx& cx, int va, 
 
 // One edge by one warp.  `st` = the warp's scratch, `tb` = its triangle bitmap (TB_WORDS words), `mh` = its match
 // hash (2*CAP words, all zero on entry and on exit).  Writes the four integer fields of local edge t and returns
-// true, or returns false when the match hash filled up (nothing written; the hash is clean again).
-template <int CAP, bool DENSE>
+// true, or returns false when the match hash filled up or the edge has too many triangles for the warp's filter
+// (nothing written; the hash is clean again).
+template <int CAP, int TSLOTS, bool DENSE, bool CAN_DEFER>
 __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st,
                                           uint32_t* tb, uint32_t* mh, int lane) {
     const int64_t e = a.e_first + (int64_t)t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const bool swapped = (va == j);                      // stream i's side, test j
-    EdgeCtx<CAP, TB_WORDS, DENSE> cx;
-    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.mh = mh; cx.n_distinct = st + WS_NDIST;
+    EdgeCtx<DENSE, TRI_SET> cx;
+    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.tb_mask = TSLOTS - 1; cx.hash.init(mh, st + WS_NDIST, CAP);
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
     cx.ovf = false;
-    // pass 1 over the heads: common neighbours (triangles) and their bitmap
-    tb[lane] = 0u;
-    __syncwarp();
+    // pass 1 over the heads: the common neighbours (triangles)
     int tri = 0;
     for (int p = lane; p < cx.db; p += 32) {
         const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-        if ((int)m != va && mem.has(m)) {
-            ++tri;
-            atomicOr(&tb[(m >> 5) & (TB_WORDS - 1)], 1u << (m & 31u));
-        }
+        tri += ((int)m != va && mem.has(m));
     }
+    tri = __reduce_add_sync(FULL, tri);
+    // the warp's exact set of T holds TSLOTS/2 keys: a richer edge goes to the CTA path
+    if (CAN_DEFER && tri > TRI_DEFER) return false;
+    if (tri > 0) {
+        for (int p = lane; p < TSLOTS; p += 32) tb[p] = EMPTY;
+        __syncwarp();
+        for (int p = lane; p < cx.db; p += 32) {
+            const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+            if ((int)m != va && mem.has(m)) tri_set_insert(tb, TSLOTS - 1, m);
+        }
+        __syncwarp();
+    } else if (lane == 0) {
+        tb[0] = EMPTY;                                   // an empty set is recognised by its first probe ...
+    }
+    if (tri == 0) cx.tb_mask = 0;                        // ... every key hashes to slot 0
     __syncwarp();
     // pass 2: the lists of the pure heads
     int sq_b = 0, g_b = 0;
     for (int c0 = 0; c0 < cx.db; c0 += 32) warp_chunk(a, cx, va, c0, st, lane, sq_b, g_b);
-    tri = __reduce_add_sync(FULL, tri);
     sq_b = __reduce_add_sync(FULL, sq_b);
     g_b = __reduce_max_sync(FULL, g_b);
     int sq_a = 0, g_a = 0;
     if (sq_b > 0) {                                      // the match hash is non-empty iff some list matched
-        match_collect<CAP>(mh, lane, 32, sq_a, g_a);
+        cx.hash.collect(lane, 32, sq_a, g_a);
         sq_a = __reduce_add_sync(FULL, sq_a);
         g_a = __reduce_max_sync(FULL, g_a);
         if (lane == 0) st[WS_NDIST] = 0;
@@ -940,12 +1054,12 @@ __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE
 // L0: warp-private hashed table, kept while consecutive edges (sorted by tested endpoint) share va.
 __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_warp_kernel(PaperArgs a) {
     extern __shared__ uint32_t smem_dyn[];
-    constexpr int PER_WARP = WSTATE_INTS + TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS;
+    constexpr int PER_WARP = WSTATE_INTS + L0_TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* base = smem_dyn + warp * PER_WARP;
     int* st = (int*)base;
     uint32_t* tb = base + WSTATE_INTS;
-    uint32_t* mh = tb + TB_WORDS;
+    uint32_t* mh = tb + L0_TB_WORDS;
     uint32_t* bm = mh + 2 * L0_CAP;
     uint32_t* tab = bm + L0_BITS / 32;
     for (int p = lane; p < 2 * L0_CAP; p += 32) mh[p] = 0u;
@@ -979,7 +1093,7 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
                 cur_va = va;
             }
             // d_a <= 128 distinct matches always fit the hash (L0_CAP * 3/4 = 192)
-            warp_edge<L0_CAP, false>(a, mem, ws.order[q], va, st, tb, mh, lane);
+            warp_edge<L0_CAP, L0_TB_WORDS, false, false>(a, mem, ws.order[q], va, st, tb, mh, lane);
         }
     }
 }
@@ -994,10 +1108,11 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
 // s_acc: [0] tri [1] sq_b [2] g_b [3] next slice [4] n_distinct [5] overflow [6] sq_a [7] g_a [11] #lists.  All
 // threads call it; the caller synchronises the CTA before the next use of s_acc.  An edge that overflows even the
 // CTA-wide hash goes to the global overflow list.
-template <int NWARPS, int CAP, bool DENSE>
+template <int NWARPS, bool DENSE>
 __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st_all,
-                                         uint32_t* tb_all, uint32_t* mh_all, int* s_acc, unsigned long long* s_wtot) {
-    constexpr int THREADS = NWARPS * 32, TBW = NWARPS * TB_WORDS, CCAP = NWARPS * CAP;
+                                      uint32_t* tb_all, uint32_t* hash_words, uint32_t hash_cap, int* s_acc,
+                                      unsigned long long* s_wtot, int part, int parts, SplitEdge* se) {
+    constexpr int THREADS = NWARPS * 32, TBW = COOP_TB_WORDS, TM = DENSE ? TRI_DENSE : TRI_HASHED;
     static_assert(3 * THREADS + 1 <= NWARPS * WSTATE_INTS, "cooperative stream state must fit the warp scratch");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* pre = st_all;                    // [THREADS + 1]
@@ -1006,30 +1121,33 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
     const int64_t e = a.e_first + (int64_t)t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const bool swapped = (va == j);
-    EdgeCtx<CCAP, TBW, DENSE> cx;
-    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb_all; cx.mh = mh_all; cx.n_distinct = s_acc + 4;
+    EdgeCtx<DENSE, TM> cx;
+    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb_all; cx.tb_mask = TBW - 1;
+    cx.hash.init(hash_words, se ? &se->n_distinct : s_acc + 4, hash_cap);
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
     cx.ovf = false;
-    for (int s = tid; s < TBW; s += THREADS) tb_all[s] = 0u;
+    // a part of a split edge takes the heads [h_lo, h_hi) (the triangle structure always covers all heads)
+    const int h_lo = (int)((long long)cx.db * part / parts), h_hi = (int)((long long)cx.db * (part + 1) / parts);
+    if (TM == TRI_HASHED) for (int s = tid; s < TBW; s += THREADS) tb_all[s] = 0u;   // (the dense one is kept clean)
     if (tid < 8) s_acc[tid] = 0;
     __syncthreads();
     int tri = 0;
     for (int p = tid; p < cx.db; p += THREADS) {
         const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
         if ((int)m != va && mem.has(m)) {
-            ++tri;
-            atomicOr(&tb_all[(m >> 5) & (TBW - 1)], 1u << (m & 31u));
+            tri += (p >= h_lo && p < h_hi);
+            atomicOr(&tb_all[TM == TRI_DENSE ? (m >> 5) : ((m >> 5) & (TBW - 1))], 1u << (m & 31u));
         }
     }
     tri = __reduce_add_sync(FULL, tri);
     if (lane == 0 && tri) atomicAdd(&s_acc[0], tri);
     __syncthreads();
     int sq_b = 0, g_b = 0;
-    for (int h0 = 0; h0 < cx.db; h0 += THREADS) {
+    for (int h0 = h_lo; h0 < h_hi; h0 += THREADS) {
         int mb = 0, md = 0;
-        if (h0 + tid < cx.db) {
+        if (h0 + tid < h_hi) {
             const int m = a.colidx[cx.sb + h0 + tid];
             if (m != va && !mem.has((uint32_t)m)) {
                 mb = a.rowptr[m];
@@ -1057,10 +1175,10 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
         if (tid == THREADS - 1) {
             const unsigned long long tot = off + mine;
             pre[(int)(tot >> 40)] = (int)(tot & 0xffffffffffull);
-            s_acc[3 + 8] = (int)(tot >> 40);          // number of non-empty lists
+            s_acc[11] = (int)(tot >> 40);             // number of non-empty lists
         }
         __syncthreads();
-        const int nlists = s_acc[3 + 8];
+        const int nlists = s_acc[11];
         const int total = pre[nlists];
         if (total > 0) {
             while (true) {                             // slices of the flat stream, pulled from a shared counter
@@ -1100,26 +1218,82 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
         if (ovf) s_acc[5] = 1;
     }
     __syncthreads();
-    if (s_acc[1] > 0) {
+    int tri_all = s_acc[0], sq_b_all = s_acc[1], g_b_all = s_acc[2];
+    bool finalise = true;
+    if (se) {     // publish this part; the part that finishes last collects the shared hash and writes the result
+        if (tid == 0) {
+            atomicAdd(&se->tri, s_acc[0]);
+            atomicAdd(&se->sq_b, s_acc[1]);
+            atomicMax(&se->g_b, s_acc[2]);
+            if (s_acc[5]) atomicOr(&se->overflow, 1);
+            __threadfence();
+            s_acc[8] = (atomicAdd(&se->parts_done, 1) == parts - 1);
+            s_acc[5] = 0;
+        }
+        __syncthreads();
+        finalise = s_acc[8] != 0;
+        if (finalise) {
+            __threadfence();
+            if (tid == 0) s_acc[5] = *(volatile int*)&se->overflow;   // the caller redoes the edge on its own
+            __syncthreads();
+            tri_all = *(volatile int*)&se->tri;
+            sq_b_all = *(volatile int*)&se->sq_b;
+            g_b_all = *(volatile int*)&se->g_b;
+        }
+    }
+    if (finalise && sq_b_all > 0) {
         int sq_a = 0, g_a = 0;
-        match_collect<CCAP>(mh_all, tid, THREADS, sq_a, g_a);
+        cx.hash.collect(tid, THREADS, sq_a, g_a);
         sq_a = __reduce_add_sync(FULL, sq_a);
         g_a = __reduce_max_sync(FULL, g_a);
         if (lane == 0 && sq_a) { atomicAdd(&s_acc[6], sq_a); atomicMax(&s_acc[7], g_a); }
         __syncthreads();
     }
-    if (tid == 0) {
-        if (s_acc[5]) {
-            a.ovf_order[atomicAdd(&a.plan->ovf_count, 1u)] = t;
-        } else {
-            const int sb_ = s_acc[1], sa_ = s_acc[6];
-            a.out_tri[t] = s_acc[0];
-            a.out_sq_i[t] = swapped ? sb_ : sa_;
-            a.out_sq_j[t] = swapped ? sa_ : sb_;
-            a.out_gamma[t] = (sb_ > 0 && sa_ > 0) ? max(s_acc[2], s_acc[7]) : 0;
+    if (finalise && tid == 0 && !s_acc[5]) {
+        const int sa_ = s_acc[6];
+        a.out_tri[t] = tri_all;
+        a.out_sq_i[t] = swapped ? sq_b_all : sa_;
+        a.out_sq_j[t] = swapped ? sa_ : sq_b_all;
+        a.out_gamma[t] = (sq_b_all > 0 && sa_ > 0) ? max(g_b_all, s_acc[7]) : 0;
+    }
+    if (TM == TRI_DENSE) {                               // un-set the triangle bits: the bitmap stays all zero between edges
+        for (int p = tid; p < cx.db; p += THREADS) {
+            const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+            if ((int)m != va && mem.has(m)) atomicAnd(&tb_all[m >> 5], ~(1u << (m & 31u)));
         }
     }
 }
+
+// cooperative edge with the CTA-wide shared hash; on overflow once more with this CTA's hash in global memory
+// (2*ghash_cap words, ghash_cap >= 2 * max degree: it cannot fill up).  Ends with the CTA synchronised.
+template <int NWARPS, int CAP, bool DENSE>
+__device__ __forceinline__ void cta_edge_retry(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va,
+                                               int* st_all, uint32_t* tb_all, uint32_t* mh_all, int* s_acc,
+                                               unsigned long long* s_wtot) {
+    cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, mh_all, NWARPS * CAP, s_acc, s_wtot, 0, 1, nullptr);
+    __syncthreads();
+    if (s_acc[5]) {
+        uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
+        for (uint32_t p = threadIdx.x; p < 2 * a.ghash_cap; p += NWARPS * 32) gh[p] = 0u;
+        __threadfence_block();
+        __syncthreads();
+        cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, gh, a.ghash_cap, s_acc, s_wtot, 0, 1, nullptr);
+        __syncthreads();
+    }
+}
+
+#ifdef DCR_PAPER_TRACE
+// debug: per CTA of the group kernel [t_begin, t_phase1_end, t_end, longest item ns, its (phase<<30 | index), #items]
+__device__ unsigned long long g_trace[4096 * 6];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(...) __VA_ARGS__
+#else
+#define TRACE(...)
+#endif
 
 // Group kernel: the CTA builds the membership structures of N(va) for a run of edges with the same tested endpoint.
 // The cooperative edges of the run (they come first) are processed by the whole CTA one at a time; then the warps
@@ -1131,14 +1305,16 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     extern __shared__ uint32_t smem_dyn[];
     __shared__ unsigned int s_idx, s_next;
     __shared__ int s_ndefer;
-    __shared__ int s_acc[12];
-    __shared__ unsigned long long s_wtot[NWARPS];
     __shared__ uint32_t s_defer[RUN_EDGES];
+    __shared__ int s_acc[12];      // [8]: "this part finalises its split edge"
+    __shared__ unsigned long long s_wtot[NWARPS];
     constexpr int THREADS = NWARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // [triangle bitmaps: NWARPS x TB_WORDS][match hashes: NWARPS x 2*CAP][warp scratch: NWARPS x WSTATE_INTS]
-    // [table (hashed only)][bitmap: hashed BITS/32 words | dense dense_words]
-    uint32_t* tb_all = smem_dyn;
+    // [CTA-path triangle structure: COOP_TB_WORDS | dense_words][per-warp triangle sets: NWARPS x TB_WORDS][match hashes: NWARPS x
+    // 2*CAP][warp scratch: NWARPS x WSTATE_INTS][table (hashed only)][bitmap: hashed BITS/32 words | dense dense_words]
+    uint32_t* tb_coop = smem_dyn;                          // dense: exact triangle bitmap, dense_words words, kept all zero
+    const int tb_coop_words = DENSE ? dense_words : COOP_TB_WORDS;
+    uint32_t* tb_all = tb_coop + tb_coop_words;
     uint32_t* mh_all = tb_all + NWARPS * TB_WORDS;
     int* st_all = (int*)(mh_all + NWARPS * 2 * CAP);
     uint32_t* tab = (uint32_t*)(st_all + NWARPS * WSTATE_INTS);
@@ -1151,76 +1327,125 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     uint32_t* mh = mh_all + warp * 2 * CAP;
     for (int p = tid; p < NWARPS * 2 * CAP; p += THREADS) mh_all[p] = 0u;
     if (lane == 0) st[WS_NDIST] = 0;
-    if (DENSE) for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+    if (DENSE) {
+        for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+        for (int s = tid; s < tb_coop_words; s += THREADS) tb_coop[s] = 0u;
+    }
     const uint2* runs = a.runs + (size_t)run_table_of(cls) * a.max_runs;
     const unsigned int n_runs = a.plan->n_runs[run_table_of(cls)];
+    const int ccls = coop_class_of(cls);
+    const WorkSource cws = work_source(a, ccls);
+    const uint32_t* cova = a.ova + a.plan->class_begin[ccls];
     Member<DENSE> mem;
     mem.tab = tab; mem.bm = bm; mem.bmask = BITS - 1; mem.mask = 0; mem.shift = 0;
     int prev_va = -1;
+    // (re)build the membership structures of N(va); all threads; ends synchronised
+    auto build = [&](int va) {
+        if (prev_va == va) return;
+        const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
+        if (DENSE) {
+            if (prev_va >= 0) {                        // un-set the previous endpoint's bits (no full clear)
+                const int ps = a.rowptr[prev_va], pd = a.rowptr[prev_va + 1] - ps;
+                for (int p = tid; p < pd; p += THREADS) {
+                    const uint32_t k = (uint32_t)a.colidx[ps + p];
+                    atomicAnd(&bm[k >> 5], ~(1u << (k & 31u)));
+                }
+            }
+        } else {
+            ro_geometry<MAX_SLOTS, 2>(da, mem.mask, mem.shift);
+            for (uint32_t s = tid; s <= mem.mask; s += THREADS) tab[s] = EMPTY;
+            for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+        }
+        __syncthreads();
+        for (int p = tid; p < da; p += THREADS) {
+            const uint32_t k = (uint32_t)a.colidx[sa + p];
+            if (DENSE) {
+                atomicOr(&bm[k >> 5], 1u << (k & 31u));
+            } else {
+                ro_insert(tab, mem.mask, mem.shift, k);
+                atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
+            }
+        }
+        prev_va = va;
+        __syncthreads();
+    };
+    TRACE(unsigned long long tr_t0 = gtimer(), tr_long = 0, tr_id = 0, tr_n = 0;)
+    // phase 0: the parts of the split edges — by far the longest streams of the pass
+    {
+        const int k = run_table_of(cls);
+        const unsigned int items = a.plan->split_items[k];
+        while (true) {
+            __syncthreads();
+            if (tid == 0) s_idx = atomicAdd(&a.plan->split_next[k], 1u);
+            __syncthreads();
+            const int item = (int)s_idx;
+            if ((unsigned)item >= items) break;
+            TRACE(const unsigned long long tr_a = gtimer();)
+            const uint32_t code = a.split_item[(size_t)k * MAX_SPLIT * MAX_PARTS + item];
+            const int sidx = (int)(code >> 8), part = (int)(code & 255u);
+            SplitEdge* se = &a.plan->split[k][sidx];
+            const uint32_t t = se->t;
+            const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+            const int i = a.esrc[e], j = a.edst[e];
+            const int va = edge_role(a, i, j, a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j]).va;
+            build(va);
+            cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, a.shash + (size_t)k * SHASH_WORDS + se->hash_off,
+                                    se->hash_cap, s_acc, s_wtot, part, se->parts, se);
+            __syncthreads();
+            if (s_acc[8] && s_acc[5]) {                  // its hash filled up: once more, whole, with this CTA's big hash
+                uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
+                for (uint32_t p = tid; p < 2 * a.ghash_cap; p += THREADS) gh[p] = 0u;
+                __threadfence_block();
+                __syncthreads();
+                cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, gh, a.ghash_cap, s_acc, s_wtot, 0, 1, nullptr);
+            }
+            TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (3ull << 30) | t; })
+        }
+    }
+    // phase 1: the cooperative edges, one per work item — the heaviest work of the pass starts first
     while (true) {
         __syncthreads();                                  // s_idx reuse
-        if (tid == 0) { s_idx = atomicAdd(&a.plan->next[cls], 1u); s_ndefer = 0; }
+        if (tid == 0) s_idx = atomicAdd(cws.next, 1u);
+        __syncthreads();
+        const unsigned int idx = s_idx;
+        if (idx >= cws.count) break;
+        TRACE(const unsigned long long tr_a = gtimer();)
+        const int va = (int)cova[idx];
+        build(va);
+        cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, cws.order[idx], va, st_all, tb_coop, mh_all, s_acc, s_wtot);
+        TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (1ull << 30) | cws.order[idx]; })
+    }
+    TRACE(const unsigned long long tr_t1 = gtimer();)
+    if (lane == 0) st[WS_NDIST] = 0;                      // the cooperative stream state overlays the warp scratch
+    // phase 2: runs of light edges of one tested endpoint, ordered by size; one warp per edge
+    while (true) {
+        __syncthreads();
+        if (tid == 0) { s_idx = atomicAdd(&a.plan->next[cls], 1u); s_next = 0; s_ndefer = 0; }
         __syncthreads();
         if (s_idx >= n_runs) break;
-        const uint2 run = runs[s_idx];                    // (first position in `order`, length); one tested endpoint
+        TRACE(const unsigned long long tr_a = gtimer();)
+        const uint2 run = runs[s_idx];                    // (first position in `order`, length)
         const uint32_t* ord = a.order + run.x;
-        const uint32_t* ova = a.ova + run.x;
         const int q_end = (int)run.y;
-        const int va = (int)(ova[0] & 0x7fffffffu);
-        if (prev_va != va) {
-            const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
-            if (DENSE) {
-                if (prev_va >= 0) {                        // un-set the previous endpoint's bits (no full clear)
-                    const int ps = a.rowptr[prev_va], pd = a.rowptr[prev_va + 1] - ps;
-                    for (int p = tid; p < pd; p += THREADS) {
-                        const uint32_t k = (uint32_t)a.colidx[ps + p];
-                        atomicAnd(&bm[k >> 5], ~(1u << (k & 31u)));
-                    }
-                }
-            } else {
-                ro_geometry<MAX_SLOTS, 2>(da, mem.mask, mem.shift);
-                for (uint32_t s = tid; s <= mem.mask; s += THREADS) tab[s] = EMPTY;
-                for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
-            }
-            __syncthreads();
-            for (int p = tid; p < da; p += THREADS) {
-                const uint32_t k = (uint32_t)a.colidx[sa + p];
-                if (DENSE) {
-                    atomicOr(&bm[k >> 5], 1u << (k & 31u));
-                } else {
-                    ro_insert(tab, mem.mask, mem.shift, k);
-                    atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
-                }
-            }
-            prev_va = va;
-            __syncthreads();
-        }
-        int p = 0;
-        while (p < q_end && (ova[p] >> 31)) {                // cooperative edges: the CTA is the team
-            cta_edge<NWARPS, CAP, DENSE>(a, mem, ord[p], va, st_all, tb_all, mh_all, s_acc, s_wtot);
-            __syncthreads();
-            ++p;
-        }
-        if (p > 0 && lane == 0) st[WS_NDIST] = 0;            // the cooperative stream state overlays the warp scratch
-        if (tid == 0) s_next = (unsigned)p;
-        __syncthreads();
-        while (true) {                                       // one warp per edge
+        const int va = (int)a.ova[run.x];
+        build(va);
+        while (true) {
             unsigned int my = 0;
             if (lane == 0) my = atomicAdd(&s_next, 1u);
             my = __shfl_sync(FULL, my, 0);
             if ((int)my >= q_end) break;
             const uint32_t t = ord[my];
-            if (!warp_edge<CAP, DENSE>(a, mem, t, va, st, tb, mh, lane) && lane == 0)
-                s_defer[atomicAdd(&s_ndefer, 1)] = t;
+            if (!warp_edge<CAP, TB_WORDS, DENSE, true>(a, mem, t, va, st, tb, mh, lane) && lane == 0)
+                s_defer[atomicAdd(&s_ndefer, 1)] = t;     // too many triangles / distinct matches for one warp: CTA path
         }
         __syncthreads();                                  // every warp is done with the run
         const int nd = s_ndefer;
-        for (int d = 0; d < nd; ++d) {                       // too many distinct matches for one warp's hash
-            cta_edge<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_all, mh_all, s_acc, s_wtot);
-            __syncthreads();
-        }
+        for (int d = 0; d < nd; ++d)
+            cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, s_acc, s_wtot);
         if (nd > 0 && lane == 0) st[WS_NDIST] = 0;
+        TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (2ull << 30) | ((unsigned long long)nd << 20) | s_idx; })
     }
+    TRACE(if (tid == 0 && blockIdx.x < 4096) { unsigned long long* r = g_trace + blockIdx.x * 6; r[0] = tr_t0; r[1] = tr_t1; r[2] = gtimer(); r[3] = tr_long; r[4] = tr_id; r[5] = tr_n; })
 }
 
 // bfc_naive.py:31-32 / :39-40 for every edge of the call, one thread per edge: the eight fp64 divisions would
@@ -1256,10 +1481,10 @@ static bool use_dense_mode(int n) {
 }
 
 struct ScratchLayout {
-    size_t plan, node_s, bucket, order, ova, ovf, va_cnt, va_cur, grp, runs, gtables, total;
+    size_t plan, node_s, bucket, order, ova, va_cnt, va_cur, grp, runs, gtables, ghash, shash, split_item, total;
     uint32_t max_runs;
-    uint32_t gslots;
-    int g_ctas;
+    uint32_t gslots, ghash_cap;
+    int g_ctas, group_ctas;
 };
 
 static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
@@ -1270,18 +1495,27 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.bucket = off; off = align_up(off + (size_t)count, 256);
     L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.ova = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
-    L.ovf = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
     L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
     L.grp = off; off = align_up(off + (size_t)4 * n * sizeof(uint32_t), 256);
-    // a group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(2n, count) groups (own + promoted)
-    L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>(2 * (int64_t)n, count) + 1);
+    // a light group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(n, count) light groups
+    L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>((int64_t)n, count) + 1);
     L.runs = off; off = align_up(off + (size_t)2 * L.max_runs * sizeof(uint2), 256);
-    // tables of the CTA-team kernel (class X and the overflow list) live in global memory
-    L.gslots = next_pow2_u32((uint64_t)std::max(max_degree, 16) * 4);
-    L.g_ctas = sm_count();
+    // tables of the CTA-team kernel (class X: tested endpoints beyond the shared-memory tables, hashed mode only)
+    L.gslots = 0;
+    L.g_ctas = 0;
     L.gtables = off;
-    off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
+    if (max_degree > CLASS_DA2 && !use_dense_mode(n)) {
+        L.gslots = next_pow2_u32((uint64_t)max_degree * 4);
+        L.g_ctas = sm_count();
+        off = align_up(off + (size_t)L.g_ctas * L.gslots * 2 * sizeof(uint32_t), 256);   // keys + counters
+    }
+    // last-resort match hashes of the group kernels (one per CTA; zeroed by the CTA that needs one)
+    L.ghash_cap = std::max<uint32_t>(4096u, next_pow2_u32((uint64_t)max_degree * 2));
+    L.group_ctas = sm_count() * std::max(GD_CTAS_PER_SM, G1_CTAS_PER_SM);
+    L.ghash = off; off = align_up(off + (size_t)L.group_ctas * 2 * L.ghash_cap * sizeof(uint32_t), 256);
+    L.shash = off; off = align_up(off + (size_t)2 * SHASH_WORDS * sizeof(uint32_t), 256);
+    L.split_item = off; off = align_up(off + (size_t)2 * MAX_SPLIT * MAX_PARTS * sizeof(uint32_t), 256);
     L.total = off;
     return L;
 }
@@ -1315,7 +1549,6 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.bucket = (uint8_t*)(base + L.bucket);
     a.order = (uint32_t*)(base + L.order);
     a.ova = (uint32_t*)(base + L.ova);
-    a.ovf_order = (uint32_t*)(base + L.ovf);
     a.va_cnt = (uint32_t*)(base + L.va_cnt);
     a.va_cur = (uint32_t*)(base + L.va_cur);
     a.grp = (uint32_t*)(base + L.grp);
@@ -1325,6 +1558,10 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.dense = use_dense_mode(n) ? 1 : 0;
     a.gtables = (uint32_t*)(base + L.gtables);
     a.gslots = L.gslots;
+    a.ghash = (uint32_t*)(base + L.ghash);
+    a.ghash_cap = L.ghash_cap;
+    a.shash = (uint32_t*)(base + L.shash);
+    a.split_item = (uint32_t*)(base + L.split_item);
 
     DCR_CUDA(cudaMemsetAsync(a.plan, 0, sizeof(PaperPlan), st));
     DCR_CUDA(cudaMemsetAsync(a.va_cnt, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
@@ -1336,6 +1573,8 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     DCR_CUDA(cudaMemsetAsync(a.va_cur, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
+    DCR_LAUNCH_CHECK();
+    split_zero_kernel<<<sm_count() * 4, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     plan_ranges_kernel<<<1, 32, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
@@ -1353,10 +1592,10 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
     const int dense_words = (n + 31) / 32;
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
-    const int smem_l0 = L0_WARPS * (WSTATE_INTS + TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS) * (int)sizeof(uint32_t);
-    const int smem_g1 = (G1_SLOTS + G1_BITS / 32 + G1_WARPS * (TB_WORDS + 2 * G1_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
-    const int smem_g2 = (G2_SLOTS + G2_BITS / 32 + G2_WARPS * (TB_WORDS + 2 * G2_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
-    const int smem_gd = (dense_words + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    const int smem_l0 = L0_WARPS * (WSTATE_INTS + L0_TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS) * (int)sizeof(uint32_t);
+    const int smem_g1 = (COOP_TB_WORDS + G1_SLOTS + G1_BITS / 32 + G1_WARPS * (TB_WORDS + 2 * G1_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    const int smem_g2 = (COOP_TB_WORDS + G2_SLOTS + G2_BITS / 32 + G2_WARPS * (TB_WORDS + 2 * G2_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    const int smem_gd = (2 * dense_words + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
     auto* k_g1 = paper_group_kernel<G1_WARPS, G1_SLOTS, G1_BITS, G1_CAP, G1_CTAS_PER_SM, false>;
     auto* k_g2 = paper_group_kernel<G2_WARPS, G2_SLOTS, G2_BITS, G2_CAP, 1, false>;
     auto* k_gd = paper_group_kernel<GD_WARPS, 64, 32, GD_CAP, GD_CTAS_PER_SM, true>;
@@ -1366,7 +1605,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_CUDA(cudaFuncSetAttribute(paper_light_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l0));
         DCR_CUDA(cudaFuncSetAttribute(k_g1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g1));
         DCR_CUDA(cudaFuncSetAttribute(k_g2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g2));
-        const int smem_gd_max = (DENSE_MAX_N / 32 + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+        const int smem_gd_max = (2 * (DENSE_MAX_N / 32) + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
         DCR_CUDA(cudaFuncSetAttribute(k_gd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gd_max));
         attr_done = true;
     }
@@ -1393,7 +1632,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         k_gd<<<sms * GD_CTAS_PER_SM, GD_WARPS * 32, smem_gd, st>>>(a, CL_G1, dense_words);
         DCR_LAUNCH_CHECK();
     } else {
-        if (max_degree > CLASS_DA2) {
+        if (L.gslots) {
             paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, aux[2]>>>(a, CL_X);
             DCR_LAUNCH_CHECK();
         }
@@ -1408,14 +1647,17 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));
         DCR_CUDA(cudaStreamWaitEvent(st, ev_join[q], 0));
     }
-    // edges whose CTA-wide match hash overflowed (rare: thousands of distinct matched neighbours of va)
-    paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, st>>>(a, CL_OVF);
-    DCR_LAUNCH_CHECK();
     paper_value_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
     return 0;
 }
+
+#ifdef DCR_PAPER_TRACE
+extern "C" int dcr_paper_trace_read(unsigned long long* host_out, int n_ctas) {
+    return cudaMemcpyFromSymbol(host_out, dcr::g_trace, sizeof(unsigned long long) * 6 * n_ctas) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // multi-GPU: re-interleave the all-gathered per-rank shards (rank r holds edges e = r + t*world at local t)

@@ -124,6 +124,31 @@ def test_paper_flavour_match_hash_overflow_paths(paper_mode):
         assert max(got["sq_i"][e01], got["sq_j"][e01]) == n_m * per_m
 
 
+def test_paper_flavour_split_hub_hub_edge(paper_mode):
+    """Two hubs with ~3000 neighbours each (500 shared: triangles are frequent in the stream) over a random background
+    of average degree ~20: the stream of edge (0,1) exceeds SPLIT_STREAM, so it is cut into parts processed by
+    different CTAs and merged through the global match hash."""
+    from oracle.paper_flavour import adjacency_sets, bfc_edge_fields
+    rng = np.random.default_rng(11)
+    n = 6000
+    pairs = [(0, 1)] + [(0, i) for i in range(2, 3002)] + [(1, i) for i in range(2502, 5502)]
+    extra = rng.integers(2, n, size=(60000, 2))
+    ei = sym_edge_index(pairs + [tuple(q) for q in extra.tolist()], n)
+    from dcr import bfc
+    csr = _csr(ei, n)
+    out = bfc.paper_flavour(csr)
+    es, ed = out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()
+    adj = adjacency_sets(ei, n)
+    assert sum(len(adj[m]) for m in adj[1]) > 49152        # the streamed side of (0,1), whichever it is
+    pick = np.concatenate([np.flatnonzero((es == 0) & (ed == 1)), np.flatnonzero(es == 0)[:40],
+                           np.flatnonzero(es == 1)[:40], rng.choice(es.size, 80, replace=False)])
+    got = {k: out[k].cpu().numpy() for k in ("tri", "sq_i", "sq_j", "gamma", "bfc")}
+    for e in pick.tolist():
+        f = bfc_edge_fields(adj, int(es[e]), int(ed[e]))
+        assert (got["tri"][e], got["sq_i"][e], got["sq_j"][e], got["gamma"][e]) == f[2:6], (e, es[e], ed[e])
+        assert got["bfc"][e] == float(f[6])
+
+
 def test_paper_flavour_named_shapes_vs_oracle(paper_mode):
     from dcr.synth import named_graph
     for name in ("cornell", "wisconsin", "cora"):
