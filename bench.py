@@ -297,6 +297,49 @@ def sdrf_bench(args, torch):
     out["prefix_matches_cpu"] = bool(same)
     if "iters_per_s" in out:
         out["speedup_vs_cpu"] = out["iters_per_s"] / out["cpu_baseline"]["value"]
+    # The reference's OWN numba kernels on this GPU (oracle/_ref PTX, built from /root/reference by oracle/build_ref.py,
+    # loaded with the driver API) driven the reference's way: two A@A + an N^2 x N kernel per iteration, one .item()
+    # per candidate.  A reported baseline ("the repo's numba bfc_cuda on the same B200"), present when oracle/_ref is.
+    try:
+        from oracle import ref_gpu
+        if ref_gpu.available():
+            budget = 6.0
+            ref_gpu.sdrf_reference_gpu(ei, n, 2, True, bound, tau, uni)                       # JIT + warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, rlog = ref_gpu.sdrf_reference_gpu(ei, n, loops, True, bound, tau, uni, time_budget_s=budget)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            k = len(rlog)
+            same_ref = [tuple(int(v) for v in r) for r in glog[:k]] == [
+                (r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
+                 -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
+                for r in rlog]
+            A = torch.zeros(n, n, device="cuda")
+            A[torch.from_numpy(ei[0]).cuda(), torch.from_numpy(ei[1]).cuda()] = 1
+            from curvature.bfc_cuda import balanced_forman_curvature as ours_dense
+            def timed(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+            ref_ms = timed(lambda: ref_gpu.balanced_forman_curvature(A), 3)
+            our_ms = timed(lambda: ours_dense(A), 10)
+            out["reference_numba_on_this_gpu"] = {
+                "sdrf_iters_per_s": k / dt, "iterations": k, "wall_s": dt, "sequence_prefix_matches_ours": bool(same_ref),
+                "dense_bfc_ms_reference": ref_ms, "dense_bfc_ms_ours_dropin": our_ms,
+                "what": "unmodified numba kernels of curvature/bfc_cuda.py (PTX via numba.cuda.compile_ptx, driver JIT to "
+                        "sm_100) + the reference's host statements (oracle/ref_gpu.py); dense_bfc = "
+                        "balanced_forman_curvature(A) on the same cora-shaped dense A, ours through the drop-in module"}
+            if "iters_per_s" in out:
+                out["speedup_vs_reference_numba"] = out["iters_per_s"] / (k / dt)
+    except Exception as exc:                     # a reported baseline must never take the bench down
+        out["reference_numba_on_this_gpu"] = {"unavailable": repr(exc)[:200]}
     return out
 
 

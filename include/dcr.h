@@ -96,9 +96,14 @@ int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n,
  * e = e_first + t*e_stride, t in [0,count) (single GPU: e_first=0, e_stride=1, count=E; rank r of W ranks:
  * e_first=r, e_stride=W) and writes the COMPACT outputs out_*[t]:  tri, sq_i (#squares at esrc), sq_j
  * (#squares at edst), gamma (0 where the reference never computes it), bfc (fp64, evaluated left to right
- * as bfc_naive.py:31-32,39-40).  Edges are classed and ordered heavy-first on the device inside the call.
- * scratch: opaque device workspace of dcr_bfc_paper_scratch_bytes(n, max_degree, count) bytes;
- * max_degree = the largest row length of the CSR.
+ * as bfc_naive.py:31-32,39-40).  Edges are classed, grouped by tested endpoint and ordered on the device inside
+ * the call.  rowptr/colidx must be a SORTED CSR of a simple undirected graph (both directions present).
+ * scratch: opaque device workspace of dcr_bfc_paper_scratch_bytes(n, max_degree, count) bytes (plan, orderings,
+ * run tables, and the global-memory match hashes: a few hundred MB for the benchmark graphs; contents need not be
+ * preserved or initialised between calls); max_degree = the largest row length of the CSR.
+ * Graphs of up to 262144 nodes use an exact shared-memory bitmap of the tested endpoint's neighbours, larger ones a
+ * hashed bitmap + table; the environment variable DCR_PAPER_MODE=hashed (read on every call) forces the latter —
+ * results are identical, the parity tests run both.
  * ---------------------------------------------------------------------------------------------------------- */
 int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t count);
 int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree, const int32_t* esrc,
