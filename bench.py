@@ -524,7 +524,7 @@ def run_ours(args):
             "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
             "traffic": NCU_DRAM_BYTES_PER_PASS if (world == 1 and args.workload == "arxiv") else None,
             "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the two edge-kernel "
-                              "launches of one pass (profiles/r01_v18_ncu_full_edge_kernels.csv)",
+                              "launches of one pass (profiles/r01_v20_ncu_full_edge_kernels.csv)",
             "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
             "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
             "note": "algorithmic bytes = SURVEY.md §8d B_gather of this rank's edges (every 2-hop list once per edge, "

@@ -136,7 +136,10 @@ constexpr int G2_SLOTS = 32768, G2_BITS = 131072, G2_CAP = 256, G2_WARPS = 16;
 #ifndef DCR_GD_CTAS
 #define DCR_GD_CTAS 4
 #endif
-constexpr int GD_CAP = 256, GD_WARPS = 8, GD_CTAS_PER_SM = DCR_GD_CTAS, DENSE_MAX_N = 262144;
+#ifndef DCR_GD_WARPS
+#define DCR_GD_WARPS 8
+#endif
+constexpr int GD_CAP = 256, GD_WARPS = DCR_GD_WARPS, GD_CTAS_PER_SM = DCR_GD_CTAS, DENSE_MAX_N = 262144;
 // per-warp scratch (ints): beg[32] | len[32] | lcnt[32] | n_distinct + pad
 constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 96, WSTATE_INTS = 100;
 // Common neighbours T = N(va) ∩ N(vb) must not count as matches, and they are FREQUENT in the stream of a hub–hub
@@ -1181,13 +1184,15 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
         const int nlists = s_acc[11];
         const int total = pre[nlists];
         if (total > 0) {
+            // at least ~4 slices per warp, so that a short round does not leave most warps waiting at its barrier
+            const int slice = max(128, min(COOP_SLICE, ((total / (NWARPS * 4)) + 127) & ~127));
             while (true) {                             // slices of the flat stream, pulled from a shared counter
                 int sl = 0;
                 if (lane == 0) sl = atomicAdd(&s_acc[3], 1);
                 sl = __shfl_sync(FULL, sl, 0);
-                int f0 = sl * COOP_SLICE;
+                int f0 = sl * slice;
                 if (f0 >= total) break;
-                const int f1 = min(total, f0 + COOP_SLICE);
+                const int f1 = min(total, f0 + slice);
                 int lo = 0, hi = nlists - 1;           // last l with pre[l] <= f0 (warp-uniform search)
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;

@@ -146,3 +146,24 @@ def test_c_oracle_agrees_with_python_oracle():
     c = bfc_paper_c(rowptr, col, ref["edges"][:, 0], ref["edges"][:, 1], threads=2)
     for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
         assert np.array_equal(c[k], ref[k]), k
+
+
+def test_reference_kernel_ptx_recipe_when_reference_is_present():
+    """oracle/build_ref.py: the reference's two numba kernels compile to PTX without a GPU (build container only —
+    /root/reference does not exist on the GPU box, where the prebuilt oracle/_ref travels instead)."""
+    import json
+    import os
+    import pytest
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present")
+    from oracle import build_ref
+    assert build_ref.build()
+    with open(os.path.join(build_ref.OUT, "manifest.json")) as f:
+        m = json.load(f)
+    k = m["kernels"]
+    # numba's flattened Array ABI: 5 + 2*ndim params per array (oracle/ref_gpu.py builds exactly these)
+    assert k["_balanced_forman_curvature"]["n_params"] == 9 + 9 + 7 + 7 + 1 + 9
+    assert k["_balanced_forman_post_delta"]["n_params"] == 9 + 9 + 1 + 1 + 1 + 9 + 1 + 1 + 7 + 7 + 1 + 1
+    for v in k.values():
+        ptx = open(os.path.join(build_ref.OUT, v["file"])).read()
+        assert v["entry"] in ptx and ".target sm_90" in ptx
