@@ -315,8 +315,6 @@ def sdrf_bench(args, torch):
                 (r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
                  -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
                 for r in rlog]
-            A = torch.zeros(n, n, device="cuda")
-            A[torch.from_numpy(ei[0]).cuda(), torch.from_numpy(ei[1]).cuda()] = 1
             from curvature.bfc_cuda import balanced_forman_curvature as ours_dense
             def timed(fn, reps):
                 fn()
@@ -328,11 +326,24 @@ def sdrf_bench(args, torch):
                 e1.record()
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / reps
-            ref_ms = timed(lambda: ref_gpu.balanced_forman_curvature(A), 3)
-            our_ms = timed(lambda: ours_dense(A), 10)
+            dense = []          # balanced_forman_curvature(A) on dense A: configs 1-4 (SURVEY.md §8d baseline 3)
+            for shape in ("cornell", "wisconsin", "cora", "squirrel"):
+                gei, gn = named_graph(shape)
+                A = torch.zeros(gn, gn, device="cuda")
+                A[torch.from_numpy(gei[0]).cuda(), torch.from_numpy(gei[1]).cuda()] = 1
+                big = gn > 4000
+                r_ms = timed(lambda: ref_gpu.balanced_forman_curvature(A), 1 if big else 3)
+                o_ms = timed(lambda: ours_dense(A), 10)
+                same_bits = bool(torch.equal(ref_gpu.balanced_forman_curvature(A).view(torch.int32),
+                                             ours_dense(A).view(torch.int32)))
+                dense.append({"shape": shape, "n": gn, "reference_ms": r_ms, "ours_dropin_ms": o_ms,
+                              "bit_identical": same_bits})
+                del A
+            ref_ms = [d["reference_ms"] for d in dense if d["shape"] == "cora"][0]
+            our_ms = [d["ours_dropin_ms"] for d in dense if d["shape"] == "cora"][0]
             out["reference_numba_on_this_gpu"] = {
                 "sdrf_iters_per_s": k / dt, "iterations": k, "wall_s": dt, "sequence_prefix_matches_ours": bool(same_ref),
-                "dense_bfc_ms_reference": ref_ms, "dense_bfc_ms_ours_dropin": our_ms,
+                "dense_bfc_ms_reference": ref_ms, "dense_bfc_ms_ours_dropin": our_ms, "dense_bfc": dense,
                 "what": "unmodified numba kernels of curvature/bfc_cuda.py (PTX via numba.cuda.compile_ptx, driver JIT to "
                         "sm_100) + the reference's host statements (oracle/ref_gpu.py); dense_bfc = "
                         "balanced_forman_curvature(A) on the same cora-shaped dense A, ours through the drop-in module"}

@@ -1537,6 +1537,10 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     if (count <= 0 || n <= 0) return 0;
     if (count > 0xfffffff0LL) { set_error("dcr_bfc_paper: more than 2^32 edges per call"); return 1; }
     if (n >= (1 << 30) - 1) { set_error("dcr_bfc_paper: node ids must fit 30 bits (table keys carry 2 tag bits)"); return 1; }
+    if (max_degree > (1 << 22)) {   // 256 lists of a cooperative round are laid out as one 32-bit flat stream
+        set_error("dcr_bfc_paper: max_degree %d above 2^22 is not supported", max_degree);
+        return 1;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const ScratchLayout L = scratch_layout(n, max_degree, count);
     if ((int64_t)L.total > scratch_bytes) {
