@@ -5,8 +5,9 @@
 
 The reference multiplies dense ``A @ A`` (:53, :146) and runs an O(N^3) numba kernel.  Here the dense fp32 ``A`` is
 converted on the device to a sorted CSR (one streaming pass), the hand-written sm_100a kernels of ``libdcr.so``
-compute the same numbers from sorted-list intersections, and the dense ``C`` / ``D`` the callers expect is written
-back.  Values are the fp32 numbers the compiled reference kernel stores (fp64 arithmetic, two fp32 roundings).
+compute the same numbers from sorted-list intersections (or, in the dense regime, two tcgen05 int8 products), and the
+dense ``C`` / ``D`` the callers expect is written back; graphs of up to 1024 nodes skip the CSR altogether
+(bit-packed rows, one kernel).  Values are the fp32 numbers the compiled reference kernel stores (fp64 arithmetic, two fp32 roundings).
 Covered: symmetric 0/1 ``A`` without self-loops (what ``is_undirected=True`` produces, sdrf_cuda_bfc.py:26-29);
 anything else raises ``NotImplementedError`` — there is no CPU or dense fallback.
 """
@@ -23,6 +24,15 @@ def _dense_regime(csr) -> bool:
 
 def balanced_forman_curvature(A, C=None):
     N = A.shape[0]
+    if C is not None and (C.dtype != torch.float32 or not C.is_contiguous() or C.shape != (N, N)):
+        raise ValueError("C must be a contiguous float32 [N, N] tensor")
+    if 0 < N <= _bfc.SMALL_DENSE_MAX_N and A.is_cuda and A.dim() == 2 and A.shape[1] == N:
+        # WebKB-sized graphs: bit-packed rows + one kernel, no CSR and no host round trip before the result
+        if A.dtype != torch.float32 or not A.is_contiguous():
+            A = A.to(torch.float32).contiguous()
+        if C is None:
+            C = torch.empty(N, N, dtype=torch.float32, device=A.device)
+        return _bfc.cuda_flavour_dense_small(A, C)
     csr = _bfc.DeviceCSR.from_dense(A)
     if _dense_regime(csr):
         out = _bfc.cuda_flavour_tc(csr, want_fields=False)     # A·A on the tensor cores (tcgen05 int8)
@@ -30,8 +40,6 @@ def balanced_forman_curvature(A, C=None):
         out = _bfc.cuda_flavour(csr, want_fields=False)        # sorted-list intersections
     if C is None:
         C = torch.empty(N, N, dtype=torch.float32, device=A.device)   # every element is written by the scatter
-    elif C.dtype != torch.float32 or not C.is_contiguous() or C.shape != (N, N):
-        raise ValueError("C must be a contiguous float32 [N, N] tensor")
     _bfc.scatter_dense(csr, out["c32"], C)
     return C
 

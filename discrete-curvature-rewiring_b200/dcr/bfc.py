@@ -132,6 +132,30 @@ def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None,
     return {"tri": tri, "sharp": sharp, "lam": lam, "c64": c64, "c32": c32}
 
 
+SMALL_DENSE_MAX_N = 1024
+_UNSUPPORTED = ((1, "entries other than 0/1"), (2, "a non-zero diagonal (self-loops)"), (4, "asymmetry (directed graph)"))
+
+
+def cuda_flavour_dense_small(A: torch.Tensor, C: torch.Tensor) -> torch.Tensor:
+    """cuda-flavour BFC of a small dense adjacency (``n <= 1024``) written into the dense ``C`` — two launches, no
+    CSR (``dcr_dense_small.cu``).  Raises ``NotImplementedError`` for inputs outside the covered domain."""
+    L.require_cuda()
+    lib = L.load()
+    n = A.shape[0]
+    nbytes = int(lib.dcr_bfc_cuda_dense_small_workspace_bytes(n))
+    ws = torch.empty(max(nbytes, 4) + 4, dtype=torch.uint8, device=A.device)    # last 4 bytes: the flags word
+    flags = ws[-4:].view(torch.int32)
+    flags.zero_()
+    L.check(lib.dcr_bfc_cuda_dense_small(A.data_ptr(), n, C.data_ptr(), flags.data_ptr(), ws.data_ptr(), nbytes,
+                                         L.current_stream()), "dcr_bfc_cuda_dense_small")
+    fl = int(flags.item())
+    if fl:
+        raise NotImplementedError(
+            "the B200 BFC kernels cover symmetric 0/1 adjacency without self-loops (is_undirected=True, the only "
+            "mode the reference's callers use); A has " + ", ".join(s for b, s in _UNSUPPORTED if fl & b))
+    return C
+
+
 class PaperWorkspace:
     """Reusable outputs + scratch of the paper-flavour kernel for one (graph, shard) shape.
 

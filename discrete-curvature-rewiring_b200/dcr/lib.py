@@ -42,6 +42,8 @@ SIGNATURES = {
     "dcr_bfc_support_tc": (_I, [_P, _P, _I, _P, _P, _L, _P]),
     "dcr_bfc_cuda_flavour_tc_workspace_bytes": (_L, [_I, _L]),
     "dcr_bfc_cuda_flavour_tc": (_I, [_P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "dcr_bfc_cuda_dense_small_workspace_bytes": (_L, [_I]),
+    "dcr_bfc_cuda_dense_small": (_I, [_P, _I, _P, _P, _P, _L, _P]),
     "dcr_bfc_paper_scratch_bytes": (_L, [_I, _I, _L]),
     "dcr_bfc_paper": (_I, [_P, _P, _I, _I, _P, _P, _L, _L, _L, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "dcr_bfc_paper_unshard": (_I, [_P, _I, _L, _L, _P, _P, _P, _P, _P, _P]),

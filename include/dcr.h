@@ -90,6 +90,16 @@ int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n,
                             int32_t* sharp, int32_t* lam, double* c64, float* c32, void* workspace,
                             int64_t workspace_bytes, void* stream);
 
+/* Small dense graphs (n <= 1024: the WebKB shapes of configs 1-2): balanced_forman_curvature(A, C) of
+ * curvature/bfc_cuda.py:51-65 straight from the dense fp32 A — rows bit-packed once, then one kernel computes supports,
+ * the "support == 1" counts and the closing formula per entry and writes ALL n*n entries of C (+0.0 off-edge).  Two
+ * launches and no host round trip, where the CSR route is launch-bound.  *flags receives the validation bits of
+ * dcr_dense_count (the caller zeroes it and decides what to do with a non-zero value; C is then unspecified).
+ * workspace: dcr_bfc_cuda_dense_small_workspace_bytes(n) bytes of device memory. */
+int64_t dcr_bfc_cuda_dense_small_workspace_bytes(int n);
+int dcr_bfc_cuda_dense_small(const float* A, int n, float* C, int32_t* flags, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * paper-flavour BFC over CSR.  Replaces bfc_edge / bfc (curvature/bfc_naive.py:7-40, :43-52).
  * Undirected edges are given explicitly: edge e = (esrc[e], edst[e]).  One call handles the strided subset

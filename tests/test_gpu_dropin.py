@@ -23,6 +23,35 @@ def test_balanced_forman_curvature_signature_and_inplace_semantics():
     assert out is C2 and torch.equal(C2, C)          # written in place and returned (bfc_cuda.py:56-57,65)
 
 
+def test_small_dense_path_bitwise_and_validation():
+    """n <= 1024: bit-packed one-kernel path (dcr_dense_small.cu) against the compiled-dataflow oracle; inputs outside
+    the covered domain raise like the CSR route does."""
+    import torch
+    from curvature.bfc_cuda import balanced_forman_curvature
+    from dcr import bfc
+    from helpers import toy_graphs
+    from oracle.cuda_flavour import bfc_cuda_dense
+    graphs = dict(toy_graphs())
+    for s, (n, p) in enumerate([(33, 0.3), (64, 0.1), (257, 0.05), (700, 0.02), (1024, 0.01)]):
+        graphs[f"gnp{n}"] = (gnp(n, p, 40 + s), n)
+    for name, (ei, n) in graphs.items():
+        assert n <= bfc.SMALL_DENSE_MAX_N
+        An = dense_of(ei, n)
+        C = torch.full((n, n), 7.0, device="cuda")
+        out = balanced_forman_curvature(torch.from_numpy(An).cuda(), C=C)
+        assert out is C
+        ref = bfc_cuda_dense(An)["C"]
+        assert np.array_equal(C.cpu().numpy().view(np.uint32), ref.view(np.uint32)), name
+    bad = torch.zeros(8, 8, device="cuda")
+    bad[0, 1] = 1                                        # asymmetric
+    with pytest.raises(NotImplementedError):
+        balanced_forman_curvature(bad)
+    bad = torch.zeros(8, 8, device="cuda")
+    bad[2, 2] = 1                                        # self-loop
+    with pytest.raises(NotImplementedError):
+        balanced_forman_curvature(bad)
+
+
 def test_balanced_forman_post_delta_signature():
     import torch
     from curvature.bfc_cuda import balanced_forman_post_delta
@@ -83,8 +112,8 @@ def test_balanced_forman_curvature_dense_regime_uses_tensor_path_and_matches_ora
     from curvature import bfc_cuda
     from dcr.synth import chung_lu_graph
     from oracle.cuda_flavour import bfc_cuda_dense
-    n = 220
-    ei = chung_lu_graph(n, 5000, 0.5, 0.3, 4)          # average degree 45: dense regime
+    n = 1100                                            # above the small-graph path (n <= 1024)
+    ei = chung_lu_graph(n, 30000, 0.5, 0.3, 4)         # average degree 55: dense regime
     An = dense_of(ei, n)
     from dcr import bfc
     assert bfc_cuda._dense_regime(bfc.DeviceCSR.from_dense(torch.from_numpy(An).cuda()))
