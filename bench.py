@@ -339,11 +339,30 @@ def sdrf_bench(args, torch):
                 dense.append({"shape": shape, "n": gn, "reference_ms": r_ms, "ours_dropin_ms": o_ms,
                               "bit_identical": same_bits})
                 del A
+            # config 2: the WebKB shapes with the reference's own hyper-parameters, whole rewiring, both sides end to end
+            from dcr.synth import SDRF_PARAMS
+            config2 = []
+            for shape in ("wisconsin", "texas"):
+                gei, gn = named_graph(shape)
+                lp, tu, bd = SDRF_PARAMS[shape]
+                for t_ in (tu, float("inf")):
+                    u2 = np.random.RandomState(11).random_sample(lp)
+                    sdrf.sdrf(gei, gn, lp, True, bd, t_, uniforms=u2)                     # warm-up
+                    t0 = time.perf_counter()
+                    g_out, g_log = sdrf.sdrf(gei, gn, lp, True, bd, t_, uniforms=u2, return_log=True)
+                    ours_s = time.perf_counter() - t0
+                    t0 = time.perf_counter()
+                    r_out, r_log = ref_gpu.sdrf_reference_gpu(gei, gn, lp, True, bd, t_, u2)
+                    torch.cuda.synchronize()
+                    ref_s = time.perf_counter() - t0
+                    config2.append({"shape": shape, "loops": lp, "tau": "inf" if t_ == float("inf") else t_,
+                                    "removal_bound": bd, "iterations": len(r_log), "ours_e2e_s": ours_s,
+                                    "reference_numba_s": ref_s, "identical_edge_index": bool(np.array_equal(g_out, r_out))})
             ref_ms = [d["reference_ms"] for d in dense if d["shape"] == "cora"][0]
             our_ms = [d["ours_dropin_ms"] for d in dense if d["shape"] == "cora"][0]
             out["reference_numba_on_this_gpu"] = {
                 "sdrf_iters_per_s": k / dt, "iterations": k, "wall_s": dt, "sequence_prefix_matches_ours": bool(same_ref),
-                "dense_bfc_ms_reference": ref_ms, "dense_bfc_ms_ours_dropin": our_ms, "dense_bfc": dense,
+                "dense_bfc_ms_reference": ref_ms, "dense_bfc_ms_ours_dropin": our_ms, "dense_bfc": dense, "sdrf_config2": config2,
                 "what": "unmodified numba kernels of curvature/bfc_cuda.py (PTX via numba.cuda.compile_ptx, driver JIT to "
                         "sm_100) + the reference's host statements (oracle/ref_gpu.py); dense_bfc = "
                         "balanced_forman_curvature(A) on the same cora-shaped dense A, ours through the drop-in module"}
