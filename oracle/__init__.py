@@ -12,8 +12,11 @@ Rules (DESIGN.md §"Oracle"):
     the build container (``curvature/bfc_naive.py`` directly; ``curvature/bfc_cuda.py`` and
     ``rewiring/sdrf_cuda_bfc.py`` under ``NUMBA_ENABLE_CUDASIM=1``), committed as ``tests/golden/*.npz`` with
     the generating script ``tests/golden/generate_golden.py``, and against the known answers of SURVEY.md
-    Appendix G.  The fp32 bit patterns of the compiled (non-simulator) numba kernel are specified by its PTX
-    dataflow (``numba.cuda.compile_ptx``) — rounding model ``"compiled"``; the simulator's
-    all-fp32 arithmetic is rounding model ``"sim32"`` and is what the golden files generated under the
-    simulator are compared with bit for bit.
+    Appendix G.  The fp32 bit patterns of the compiled (non-simulator) numba kernel follow its PTX dataflow
+    (``numba.cuda.compile_ptx``) — rounding model ``"compiled"`` — and are pinned BY
+    EXECUTION: ``oracle/build_ref.py`` compiles the reference's own kernels to PTX (``oracle/_ref/``, derived from
+    /root/reference, not committed), ``oracle/ref_gpu.py`` runs them on the GPU through the driver API, and
+    ``tests/test_gpu_ref_kernels.py`` checks this oracle and the CUDA product path against them bit for bit.
+    The simulator's all-fp32 arithmetic is rounding model ``"sim32"`` and is what the golden files generated
+    under the simulator are compared with bit for bit.
 """
