@@ -436,7 +436,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    for _ in range(args.warmup):
+    # N > 1: NCCL sets up channels lazily over the first collectives of a given shape; a 2-GPU run with 3 warm-up steps
+    # once showed two 70-120 ms all-gathers among the first timed steps.  A few extra untimed steps keep that out.
+    settle = 5 if world > 1 else 0
+    for _ in range(args.warmup + settle):
         flush.zero_()
         sh.run()
     step_ev, edge_ev = new_events(args.steps), new_events(args.steps)
@@ -541,6 +544,7 @@ def run_ours(args):
                    "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
                    "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks", "wall_s_timed_region": wall,
                    "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms],
+                   "extra_untimed_steps_after_warmup": settle,
                    "phase_ms_rank0": {"plan": round(float(np.mean(plan_ms)), 4), "edge_kernels": round(edge_ms_avg, 4),
                                       "gather_unshard": round(float(np.mean(tail_ms)), 4)}},
         "clocks": clocks,
