@@ -91,6 +91,7 @@ class ClockSampler:
         self.probe_out = None
         self.probe_stream = None
         self.n_probes = 0
+        self.probe_where = "during the timed steps"
 
     def start(self):
         import torch
@@ -165,7 +166,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz,
                 "reasons": [name for name, bit in self.REASONS if mask & bit],
                 "samples": len(mhz), "reason_samples": len(self.masks),
-                "source": "sm_mhz: in-band clock64/globaltimer probes on a side stream during the timed steps; reasons: NVML "
+                "source": f"sm_mhz: in-band clock64/globaltimer probes on a side stream {self.probe_where}; reasons: NVML "
                           "every 20 ms over an untimed batch of the same steps run right after the timed region (NVML polling "
                           "inside the region stalls GPU work on these hosts, see profiles/)"}
 
@@ -436,8 +437,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    # N > 1: NCCL sets up channels lazily over the first collectives of a given shape; a 2-GPU run with 3 warm-up steps
-    # once showed two 70-120 ms all-gathers among the first timed steps.  A few extra untimed steps keep that out.
+    # N > 1: 2-GPU runs intermittently showed one or two 7-120 ms all-gathers among the first timed steps (never at
+    # N = 1, never in the run without the clock probes).  Extra untimed steps and a host head start did not remove
+    # them; the only rank-asymmetric work inside the timed region was rank 0's in-band clock probe, so at N > 1 the
+    # probes now ride on the untimed batch of the same steps that is run right after (where NVML is polled too).
     settle = 5 if world > 1 else 0
     for _ in range(args.warmup + settle):
         flush.zero_()
@@ -451,7 +454,7 @@ def run_ours(args):
         step_ev[k][0].record()
         res = sh.run(events=edge_ev[k])
         step_ev[k][1].record()
-        if rank == 0 and not args.no_clocks and k % max(1, args.steps // 8) == 0:
+        if world == 1 and not args.no_clocks and k % max(1, args.steps // 8) == 0:
             sampler.probe()         # runs on a side stream while this step's kernels execute
     barrier()
     wall = time.perf_counter() - wall0
@@ -465,8 +468,12 @@ def run_ours(args):
     def untimed_step():
         flush.zero_()
         sh.run()
+        if world > 1 and rank == 0 and not args.no_clocks:
+            sampler.probe()         # N > 1: SM-clock probes ride on the untimed batch of the same steps (see below)
 
     if world > 1:
+        sampler.probe_where = ("during an untimed batch of the same steps run right after the timed region (at N > 1 the "
+                               "probe is kept out of the timed steps: it was the only rank-asymmetric work in them)")
         n_untimed = max(args.steps, 16)              # every rank runs the same untimed batch (collectives inside)
         if rank == 0 and not args.no_clocks:
             sampler.under_load(untimed_step, n_untimed, exact=True)
