@@ -552,6 +552,7 @@ def run_ours(args):
                    "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks", "wall_s_timed_region": wall,
                    "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms],
                    "extra_untimed_steps_after_warmup": settle,
+                   "step_ms_median_rank0": round(float(np.median(step_ms)), 4),
                    "phase_ms_rank0": {"plan": round(float(np.mean(plan_ms)), 4), "edge_kernels": round(edge_ms_avg, 4),
                                       "gather_unshard": round(float(np.mean(tail_ms)), 4)}},
         "clocks": clocks,
