@@ -122,3 +122,24 @@ def test_no_gpu_means_loud_failure_not_fallback():
     from dcr.bfc import DeviceCSR
     with pytest.raises(L.DcrError):
         DeviceCSR.from_host(np.array([0, 1, 2], dtype=np.int32), np.array([1, 0], dtype=np.int32))
+
+
+def test_dense_entry_points_fail_loudly_without_cuda():
+    """No CPU fallback anywhere on the dense signatures: small-graph path, CSR route and post_delta all raise."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    from curvature.bfc_cuda import balanced_forman_curvature, balanced_forman_post_delta
+    from dcr import bfc
+    from dcr.lib import DcrError
+    A = torch.zeros(6, 6)
+    A[0, 1] = A[1, 0] = 1
+    with pytest.raises(DcrError):
+        balanced_forman_curvature(A)
+    with pytest.raises(DcrError):
+        bfc.cuda_flavour_dense_small(A, torch.zeros(6, 6))
+    with pytest.raises(DcrError):
+        balanced_forman_post_delta(A, 0, 1, [1, 0], [0, 1])
+    big = torch.zeros(1100, 1100)                       # above the small-graph path: the CSR route
+    with pytest.raises(DcrError):
+        balanced_forman_curvature(big)
