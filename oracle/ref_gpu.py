@@ -15,7 +15,8 @@ the reference's host wrappers do.  It serves two purposes:
 Host-side statements restated here (the kernels themselves are the reference's):
   ``balanced_forman_curvature``  ``curvature/bfc_cuda.py:51-65``,
   ``balanced_forman_post_delta`` ``curvature/bfc_cuda.py:144-159``,
-  ``sdrf_reference_gpu``         ``rewiring/sdrf_cuda_bfc.py:14-93`` (graph bookkeeping shared with ``oracle/sdrf.py``).
+  ``sdrf_reference_gpu``         ``rewiring/sdrf_cuda_bfc.py:14-93`` (graph bookkeeping shared with ``oracle/sdrf.py``;
+                                 both modes — ``is_undirected=False`` is there for the directed row of SURVEY.md §8f).
 
 numba kernel ABI (numba ``Array`` data model, flattened): an ``ndim``-d array is passed as
 ``meminfo*, parent*, nitems:i64, itemsize:i64, data*, shape[ndim]:i64, strides[ndim]:i64`` (strides in bytes).
@@ -139,7 +140,7 @@ def balanced_forman_post_delta(A, x, y, i_neighbors, j_neighbors, D=None, A2=Non
 
 
 def sdrf_reference_gpu(edge_index, num_nodes, loops, remove_edges, removal_bound, tau, uniforms,
-                       time_budget_s: float | None = None):
+                       time_budget_s: float | None = None, is_undirected: bool = True):
     """``rewiring/sdrf_cuda_bfc.py:14-93`` driven the reference's way on the GPU (``is_undirected=True``):
     full ``balanced_forman_curvature`` every iteration, ``C.argmin().item()``, a second ``A @ A`` inside
     ``balanced_forman_post_delta`` and one ``.item()`` per candidate.  Returns ``(edge_index_out, log)`` with
@@ -149,11 +150,15 @@ def sdrf_reference_gpu(edge_index, num_nodes, loops, remove_edges, removal_bound
 
     import torch
 
-    from .sdrf import (choice_index, dense_adjacency, edge_index_from_adjacency, networkx_adjacency, softmax)
+    from .sdrf import (choice_index, dense_adjacency, edge_index_from_adjacency, edge_index_from_digraph,
+                       networkx_adjacency, networkx_digraph, softmax)
 
-    A = torch.from_numpy(dense_adjacency(edge_index, True)).cuda()        # :26-29, :34
+    A = torch.from_numpy(dense_adjacency(edge_index, is_undirected)).cuda()   # :26-29, :34
     N = A.shape[0]                                                        # :30
-    adj = networkx_adjacency(edge_index, max(num_nodes, N))               # :31-33
+    if is_undirected:
+        adj, pred = networkx_adjacency(edge_index, max(num_nodes, N)), None   # :31-33
+    else:
+        adj, pred = networkx_digraph(edge_index, max(num_nodes, N))       # :31 (adj = successors)
     Cm = torch.zeros(N, N, device="cuda")                                 # :35
     n_draws = 0
     log = []
@@ -165,8 +170,8 @@ def sdrf_reference_gpu(edge_index, num_nodes, loops, remove_edges, removal_bound
         balanced_forman_curvature(A, C_out=Cm)                            # :39
         ix_min = Cm.argmin().item()                                       # :40
         x, y = ix_min // N, ix_min % N                                    # :41-42
-        x_neighbors = list(adj[x]) + [x]                                  # :45
-        y_neighbors = list(adj[y]) + [y]                                  # :46
+        x_neighbors = list(adj[x]) + [x]                                  # :45 / :48
+        y_neighbors = list(adj[y] if is_undirected else pred[y]) + [y]    # :46 / :49
         candidates = [(i, j) for i in x_neighbors for j in y_neighbors
                       if (i != j) and (j not in adj[i])]                  # :50-54
         rec = {"x": x, "y": y, "n_candidates": len(candidates), "k": -1, "l": -1, "choice": -1,
@@ -182,8 +187,12 @@ def sdrf_reference_gpu(edge_index, num_nodes, loops, remove_edges, removal_bound
             n_draws += 1
             k, l = candidates[choice]
             adj[k][l] = None                                              # :69
-            adj[l][k] = None
-            A[k, l] = A[l, k] = 1                                         # :70-71
+            if is_undirected:
+                adj[l][k] = None
+                A[k, l] = A[l, k] = 1                                     # :70-71
+            else:
+                pred[l][k] = None
+                A[k, l] = 1                                               # :72-73
             rec.update(k=k, l=l, choice=choice, improvements=improvements)
         else:
             can_add = False                                               # :75
@@ -196,13 +205,17 @@ def sdrf_reference_gpu(edge_index, num_nodes, loops, remove_edges, removal_bound
                 if yr not in adj[xr]:
                     raise KeyError(f"The edge {xr}-{yr} is not in the graph")
                 del adj[xr][yr]                                           # :84
-                if xr != yr:
-                    del adj[yr][xr]
-                A[xr, yr] = A[yr, xr] = 0                                 # :85-86
+                if is_undirected:
+                    if xr != yr:
+                        del adj[yr][xr]
+                    A[xr, yr] = A[yr, xr] = 0                             # :85-86
+                else:
+                    del pred[yr][xr]
+                    A[xr, yr] = 0                                         # :87-88
                 rec["removed"] = (xr, yr)
             elif can_add is False:                                        # :89-91
                 stop = True
         log.append(rec)
         if stop:
             break
-    return edge_index_from_adjacency(adj), log                           # :93
+    return (edge_index_from_adjacency(adj) if is_undirected else edge_index_from_digraph(adj)), log   # :93

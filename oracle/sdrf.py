@@ -111,6 +111,28 @@ def edge_index_from_adjacency(adj: list[dict]) -> np.ndarray:
     return np.array([src, dst], dtype=np.int64).reshape(2, -1)
 
 
+def networkx_digraph(edge_index: np.ndarray, num_nodes: int):
+    """``(succ, pred)`` adjacency dicts, in networkx insertion order, of ``to_networkx(data)`` — a ``DiGraph`` built
+    by ``add_edge(u, v)`` in column order of ``edge_index`` (:31, directed mode keeps it as is)."""
+    succ = [dict() for _ in range(num_nodes)]
+    pred = [dict() for _ in range(num_nodes)]
+    for u, v in zip(np.asarray(edge_index[0]).tolist(), np.asarray(edge_index[1]).tolist()):
+        succ[u][v] = None
+        pred[v][u] = None
+    return succ, pred
+
+
+def edge_index_from_digraph(succ: list[dict]) -> np.ndarray:
+    """``from_networkx(G).edge_index`` for a ``DiGraph`` (:93): ``convert_node_labels_to_integers`` re-adds the edges
+    in ``G.edges`` order (node order, successors in insertion order), which is also the order of the result."""
+    src, dst = [], []
+    for u, nbrs in enumerate(succ):
+        for v in nbrs:
+            src.append(u)
+            dst.append(v)
+    return np.array([src, dst], dtype=np.int64).reshape(2, -1)
+
+
 def first_argmin(C: np.ndarray) -> int:
     """``C.argmin().item()`` (:40): first row-major occurrence; ``-0.0 == 0.0``."""
     return int(np.argmin(C))
@@ -125,25 +147,33 @@ def first_argmax(C: np.ndarray) -> int:
 # ----------------------------------------------------------------------------------------------------------
 def sdrf_oracle(edge_index: np.ndarray, num_nodes: int, loops: int, remove_edges: bool, removal_bound: float,
                 tau, uniforms: np.ndarray | None = None, rounding: str = "compiled",
-                incremental_a2: bool = True, verify_a2_every: int = 0):
+                incremental_a2: bool = True, verify_a2_every: int = 0, is_undirected: bool = True):
     """Returns ``(edge_index_out, log)``.
 
     ``log`` is a list with one dict per executed iteration:
     ``{"x","y","n_candidates","k","l","choice","removed": (a,b) or None, "improvements": fp64 array}``
     (``k = l = choice = -1`` when nothing was added).  ``uniforms[t]`` is the t-th double ``np.random`` would
     have produced (one is consumed per iteration that has candidates, also for ``tau == inf``).
-    Only ``is_undirected=True`` (the only mode any caller of the reference uses, rewire.py:10) is restated.
+    ``is_undirected=False`` (no caller of the reference uses it, rewire.py:10) restates the directed branches
+    (:47-49, :72-73, :87-88): candidates from the successors of ``x`` and the predecessors of ``y``, one directed
+    entry added / removed, ``G`` a ``DiGraph``.
     """
-    A = dense_adjacency(edge_index, True)                       # :26-29
+    A = dense_adjacency(edge_index, is_undirected)              # :26-29
     N = A.shape[0]                                              # :30
-    adj = networkx_adjacency(edge_index, max(num_nodes, N))     # :31-33
+    if is_undirected:
+        adj = networkx_adjacency(edge_index, max(num_nodes, N)) # :31-33
+        pred = None
+    else:
+        adj, pred = networkx_digraph(edge_index, max(num_nodes, N))   # :31 (adj = successors)
     A2 = (A @ A).astype(F32)
     n_draws = 0
     log = []
 
     def toggle(a, b, val):
         nonlocal A2
-        A[a, b] = A[b, a] = val
+        A[a, b] = val
+        if is_undirected:
+            A[b, a] = val
         if not incremental_a2:
             A2 = (A @ A).astype(F32)
 
@@ -155,8 +185,8 @@ def sdrf_oracle(edge_index: np.ndarray, num_nodes: int, loops: int, remove_edges
         C = res
         ix_min = first_argmin(C)                                # :40
         x, y = ix_min // N, ix_min % N                          # :41-42
-        x_neighbors = list(adj[x]) + [x]                        # :45
-        y_neighbors = list(adj[y]) + [y]                        # :46
+        x_neighbors = list(adj[x]) + [x]                        # :45 / :48 (successors)
+        y_neighbors = list(adj[y] if is_undirected else pred[y]) + [y]   # :46 / :49 (predecessors)
         candidates = [(i, j) for i in x_neighbors for j in y_neighbors
                       if (i != j) and (j not in adj[i])]        # :50-54
         rec = {"x": x, "y": y, "n_candidates": len(candidates), "k": -1, "l": -1, "choice": -1,
@@ -176,8 +206,12 @@ def sdrf_oracle(edge_index: np.ndarray, num_nodes: int, loops: int, remove_edges
             n_draws += 1
             k, l = candidates[choice]
             adj[k][l] = None                                    # :69  G.add_edge(k, l)
-            adj[l][k] = None
-            _a2_toggle(A, A2, k, l, +1) if incremental_a2 else None
+            if is_undirected:
+                adj[l][k] = None
+            else:
+                pred[l][k] = None
+            if incremental_a2:
+                (_a2_toggle if is_undirected else _a2_toggle_directed)(A, A2, k, l, +1)
             toggle(k, l, F32(1))                                # :70-71
             rec.update(k=k, l=l, choice=choice, improvements=improvements)
         else:
@@ -191,9 +225,13 @@ def sdrf_oracle(edge_index: np.ndarray, num_nodes: int, loops: int, remove_edges
                 if yr not in adj[xr]:
                     raise KeyError(f"The edge {xr}-{yr} is not in the graph")   # networkx.NetworkXError
                 del adj[xr][yr]                                 # :84  G.remove_edge
-                if xr != yr:
-                    del adj[yr][xr]
-                _a2_toggle(A, A2, xr, yr, -1) if incremental_a2 else None
+                if is_undirected:
+                    if xr != yr:
+                        del adj[yr][xr]
+                else:
+                    del pred[yr][xr]
+                if incremental_a2:
+                    (_a2_toggle if is_undirected else _a2_toggle_directed)(A, A2, xr, yr, -1)
                 toggle(xr, yr, F32(0))                          # :85-86
                 rec["removed"] = (xr, yr)
             else:
@@ -202,7 +240,7 @@ def sdrf_oracle(edge_index: np.ndarray, num_nodes: int, loops: int, remove_edges
         log.append(rec)
         if stop:
             break
-    return edge_index_from_adjacency(adj), log                 # :93
+    return (edge_index_from_adjacency(adj) if is_undirected else edge_index_from_digraph(adj)), log   # :93
 
 
 def _a2_toggle(A: np.ndarray, A2: np.ndarray, k: int, l: int, sign: int) -> None:
@@ -217,6 +255,16 @@ def _a2_toggle(A: np.ndarray, A2: np.ndarray, k: int, l: int, sign: int) -> None
     A2[l, :] += s * A[k, :]
     A2[k, k] += F32(1)
     A2[l, l] += F32(1)
+
+
+def _a2_toggle_directed(A: np.ndarray, A2: np.ndarray, k: int, l: int, sign: int) -> None:
+    """Exact update of ``A2 = A @ A`` for the single directed entry ``A[k,l] += sign`` (call BEFORE changing ``A``):
+    ``(A+Δ)² = A² + AΔ + ΔA + Δ²`` with ``Δ = sign·e_k e_lᵀ``; ``Δ² = 0`` for ``k != l``."""
+    s = F32(sign)
+    A2[:, l] += s * A[:, k]
+    A2[k, :] += s * A[l, :]
+    if k == l:
+        A2[k, k] += F32(1)
 
 
 def _bfc_with_a2(A: np.ndarray, A2: np.ndarray, rounding: str) -> np.ndarray:

@@ -239,8 +239,69 @@ def gen_sdrf(out):
     print("sdrf_seq:", len(cases), "cases")
 
 
+def run_reference_directed(ei, n, loops, bound, tau, seed):
+    """Unmodified ``sdrf_cuda_bfc(..., is_undirected=False)`` (rewiring/sdrf_cuda_bfc.py:47-49,72-73,87-88): ``G`` is a
+    ``DiGraph``; the add/remove sequence is captured on ``nx.DiGraph``."""
+    log = []
+    orig_add, orig_rm = nx.DiGraph.add_edge, nx.DiGraph.remove_edge
+
+    def add_edge(self, u, v, **kw):
+        log.append((1, int(u), int(v)))
+        return orig_add(self, u, v, **kw)
+
+    def remove_edge(self, u, v):
+        log.append((-1, int(u), int(v)))
+        return orig_rm(self, u, v)
+
+    data = Data(edge_index=torch.from_numpy(ei).long())
+    data.num_nodes = n
+    np.random.seed(seed)
+    uniforms = np.random.RandomState(seed).random_sample(loops)
+    # to_networkx builds the DiGraph with add_edge as well: patch only around the loop's own mutations by recording
+    # the length of the log after set-up
+    nx.DiGraph.add_edge, nx.DiGraph.remove_edge = add_edge, remove_edge
+    try:
+        out = ref_sdrf.sdrf_cuda_bfc(data, loops, True, bound, tau, False)
+    finally:
+        nx.DiGraph.add_edge, nx.DiGraph.remove_edge = orig_add, orig_rm
+    # the first ei.shape[1] additions are to_networkx's (:31); from_networkx rebuilds the graph once more at the end
+    # (convert_node_labels_to_integers -> add_edges_from, which does not call add_edge)
+    loop_log = log[ei.shape[1]:]
+    return out.edge_index.numpy().copy(), np.array(loop_log, dtype=np.int64).reshape(-1, 3), uniforms
+
+
+def gen_sdrf_directed(out):
+    rng = np.random.default_rng(21)
+    cases = []
+    for q, (n, m, loops, bound, tau, seed) in enumerate([(12, 30, 6, 0.3, 5, 31), (14, 40, 6, 0.5, float("inf"), 32),
+                                                         (16, 45, 6, 0.2, 20, 33), (10, 40, 5, 0.8, float("inf"), 34),
+                                                         (15, 36, 6, 100.0, 3, 35)]):
+        ei = rng.integers(0, n, size=(2, m))
+        ei = ei[:, ei[0] != ei[1]]
+        ei = np.unique(ei, axis=1)                      # sorted, no duplicate directed edges
+        ei = ei[:, rng.permutation(ei.shape[1])]        # insertion order is not sorted order
+        cases.append((f"dir{q}", ei, n, loops, bound, tau, seed))
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, ei, n, loops, bound, tau, seed in cases:
+        t0 = time.time()
+        eo, log, uni = run_reference_directed(ei, n, loops, bound, tau, seed)
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/loops"] = np.int64(loops)
+        pack[f"{name}/bound"] = np.float64(bound)
+        pack[f"{name}/tau"] = np.float64(tau)
+        pack[f"{name}/uniforms"] = uni
+        pack[f"{name}/out"] = eo
+        pack[f"{name}/log"] = log
+        print(f"  sdrf-directed {name}: n={n} loops={loops} log={len(log)} {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(out, **pack)
+    print("sdrf_directed_seq:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["paper", "cuda", "sdrf"]
+    which = sys.argv[1:] or ["paper", "cuda", "sdrf", "sdrf_directed"]
+    if "sdrf_directed" in which:
+        gen_sdrf_directed(os.path.join(HERE, "sdrf_directed_seq.npz"))
     if "paper" in which:
         gen_paper(os.path.join(HERE, "paper_kat.npz"))
     if "cuda" in which:

@@ -54,6 +54,26 @@ def test_sdrf_oracle_sim32_reproduces_reference_sequences():
         assert np.array_equal(out, z[f"{name}/out"]), name
 
 
+def test_sdrf_oracle_directed_mode_reproduces_reference_sequences():
+    """is_undirected=False (rewiring/sdrf_cuda_bfc.py:47-49,72-73,87-88): add/remove sequence and the
+    output edge_index of the UNMODIFIED reference on random directed graphs with unsorted insertion order.  The CUDA
+    path does not cover this mode yet (it raises NotImplementedError); the oracle and the goldens are in place for it."""
+    z = golden("sdrf_directed_seq.npz")
+    for name in _names(z):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        out, log = sdrf_oracle(ei, n, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]),
+                               float(z[f"{name}/tau"]), z[f"{name}/uniforms"], rounding="sim32", verify_a2_every=1,
+                               is_undirected=False)
+        mine = []
+        for r in log:
+            if r["k"] >= 0:
+                mine.append((1, r["k"], r["l"]))
+            if r["removed"] is not None:
+                mine.append((-1,) + tuple(r["removed"]))
+        assert np.array_equal(np.array(mine).reshape(-1, 3), z[f"{name}/log"]), name
+        assert np.array_equal(out, z[f"{name}/out"]), name
+
+
 # SURVEY.md Appendix G: (graph, edge) -> cuda (d_i, d_j, A2ij, sharp, lam, C) ; paper (tri, sq1, sq2, gamma, bfc)
 APP_G = [
     ("path4", (0, 1), (1, 2, 0, 3, 2, 1.75), (0, 0, 0, 0, 0.0)),
