@@ -114,7 +114,7 @@ __host__ __device__ constexpr int filter_bits(int team, bool global_table) {
 constexpr int UNROLL = DCR_UNROLL;
 // light path geometry
 #ifndef DCR_L0_CTAS
-#define DCR_L0_CTAS 6
+#define DCR_L0_CTAS 5
 #endif
 #ifndef DCR_G1_CTAS
 #define DCR_G1_CTAS 4
@@ -134,14 +134,23 @@ constexpr int G1_SLOTS = 2048, G1_BITS = 32768, G1_CAP = 512, G1_WARPS = 8, G1_C
 constexpr int G2_SLOTS = 32768, G2_BITS = 131072, G2_CAP = 256, G2_WARPS = 16;
 // dense mode: exact bitmap of N(va) over all node ids; 8 warps and >= 4 CTAs per SM while n <= DENSE_MAX_N
 #ifndef DCR_GD_CTAS
-#define DCR_GD_CTAS 4
+#define DCR_GD_CTAS 3
 #endif
 #ifndef DCR_GD_WARPS
 #define DCR_GD_WARPS 8
 #endif
 constexpr int GD_CAP = 256, GD_WARPS = DCR_GD_WARPS, GD_CTAS_PER_SM = DCR_GD_CTAS, DENSE_MAX_N = 262144;
-// per-warp scratch (ints): beg[32] | len[32] | lcnt[32] | n_distinct + pad
-constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 96, WSTATE_INTS = 100;
+// per-warp scratch (ints): beg[32] | len[32] | lcnt[64] (short lists by compacted rank, long lists at 32 + head lane) |
+// n_distinct + pad
+constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 128, WSTATE_INTS = 132;
+// Candidate queue of a warp.  A streamed element that passes the membership filter is NOT examined on the spot (that
+// code ran with one or two lanes active and was 16-22 % of all issued instructions): the lanes that hold candidates
+// append (key, list) to the warp's queue with a ballot/popc compaction, and the queue is drained 32 candidates per
+// pass with every lane busy — exact membership, triangle test, match counting.  It is drained when it holds
+// Q_FLUSH entries and at the end of a chunk of heads / a slice, so it never holds more than Q_FLUSH - 1 + one
+// window of elements.
+constexpr int Q_FLUSH = 32, Q_CAP = Q_FLUSH + 32 * (DCR_UNROLL > DCR_FLAT_UNROLL ? DCR_UNROLL : DCR_FLAT_UNROLL);
+constexpr int Q_WORDS = 2 * Q_CAP;
 // Common neighbours T = N(va) ∩ N(vb) must not count as matches, and they are FREQUENT in the stream of a hub–hub
 // edge (hubs are each other's neighbours), so membership in T has to be exact and on chip:
 //   TRI_SET     warp path: exact open-addressing set of T in the warp's scratch (TB_WORDS slots, |T| <= TRI_DEFER in
@@ -833,7 +842,9 @@ struct MatchHash {
     }
 };
 
-// Everything a warp needs to test streamed elements of one edge (va tested, vb streamed).
+// Everything a warp needs to test streamed elements of one edge (va tested, vb streamed) against the CTA-level or
+// warp-level structures of the group kernels: membership in N(va), the structure that answers "k in T", the match
+// hash, the warp's candidate queue and the per-list match counters the queue entries point into.
 template <bool DENSE, int TM>
 struct EdgeCtx {
     const int32_t* __restrict__ colidx;
@@ -841,6 +852,9 @@ struct EdgeCtx {
     const uint32_t* tb;      // the structure that answers "k in T" (see TRI_*)
     uint32_t tb_mask;        // TRI_SET: slots - 1; TRI_HASHED: words - 1
     MatchHash hash;
+    uint2* q;                // candidate queue (key, list)
+    int qn;                  // its length (warp-uniform)
+    int* lcnt;               // per-list match counters
     int vb, sb, db;
     bool ovf;
     __device__ __forceinline__ bool in_triangle(uint32_t kk) const {
@@ -856,17 +870,14 @@ struct EdgeCtx {
         }
         return ((tb[(kk >> 5) & tb_mask] >> (kk & 31u)) & 1u) && find_sorted(colidx, sb, db, (int)kk) >= 0;
     }
-    // k in N(m), m a pure neighbour of vb: is (m,k) an edge of the bipartite graph M_b – M_a?  Split in two so that the
-    // streaming loops stay small: hit() is the per-element filter (one shared-memory load), slow() runs once per
-    // candidate — ONE copy of it per loop, shared by all the elements of a window.
+    // k in N(m), m a pure neighbour of vb: is (m,k) an edge of the bipartite graph M_b – M_a?  hit() is the per-element
+    // filter of the streaming loops (one shared-memory load); handle() runs on queued candidates, 32 per pass.
     __device__ __forceinline__ bool hit(int k) const { return mem.maybe((uint32_t)k) && k != vb; }
-    __device__ __forceinline__ int slow(int k) {
-        const uint32_t kk = (uint32_t)k;
+    __device__ __forceinline__ void handle(uint32_t kk, uint32_t list) {
         if (mem.confirm(kk) && !in_triangle(kk)) {     // k in N(va) and not a common neighbour
             if (!hash.add(kk)) ovf = true;
-            return 1;
+            atomicAdd(&lcnt[list], 1);
         }
-        return 0;
     }
 };
 __device__ __forceinline__ void tri_set_insert(uint32_t* ts, uint32_t mask, uint32_t kk) {
@@ -878,7 +889,7 @@ __device__ __forceinline__ void tri_set_insert(uint32_t* ts, uint32_t mask, uint
     }
 }
 
-// the u-th of UNROLL registers (u is not a compile-time constant: a select chain instead of local memory)
+// the u-th of N registers (u is not a compile-time constant: a select chain instead of local memory)
 template <int N>
 __device__ __forceinline__ int pick(const int (&v)[N], int u) {
     int r = v[0];
@@ -887,133 +898,173 @@ __device__ __forceinline__ int pick(const int (&v)[N], int u) {
     return r;
 }
 
-// `len` consecutive entries of one neighbour list, streamed by the whole warp (p already includes the lane offset):
-// returns this lane's number of matches.  Lanes past the end test vb, which never matches.
-template <class Ctx>
-__device__ __forceinline__ int stream_segment(Ctx& cx, const int32_t* __restrict__ p, int len, int lane) {
-    int c = 0;
-    for (int F = 0; F < len; F += 32 * UNROLL) {       // all loads of a window are in flight before the first test
-        int k[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) k[u] = (F + 32 * u + lane < len) ? __ldg(p + F + 32 * u) : cx.vb;
-        uint32_t hm = 0;                                // this lane's candidates among its UNROLL elements
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
-        while (hm) {
+// Append this window's candidates (bit u of hm: element k[u] of this lane passed the filter) to the warp's queue.
+// One pass per candidate of the busiest lane; all lanes take part in every ballot.
+template <class Ctx, int N>
+__device__ __forceinline__ void q_push(Ctx& cx, uint32_t hm, const int (&k)[N], const int (&own)[N], int lane) {
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t b = __ballot_sync(FULL, hm != 0u);
+    while (b) {
+        if (hm) {
             const int u = __ffs(hm) - 1;
             hm &= hm - 1;
-            c += cx.slow(pick(k, u));
+            cx.q[cx.qn + __popc(b & lt)] = make_uint2((uint32_t)pick(k, u), (uint32_t)pick(own, u));
         }
+        cx.qn += __popc(b);
+        b = __ballot_sync(FULL, hm != 0u);
     }
-    return c;
+}
+template <class Ctx>
+__device__ __forceinline__ void q_flush(Ctx& cx, int lane) {
+    __syncwarp();
+    for (int q = lane; q < cx.qn; q += 32) {
+        const uint2 e = cx.q[q];
+        cx.handle(e.x, e.y);
+    }
+    cx.qn = 0;
+    __syncwarp();
 }
 
-// One chunk of 32 heads of N(vb) (positions c0 .. c0+31) by one warp: lists of at least LONG_LIST entries are
-// streamed one at a time by the whole warp (no ownership arithmetic at all); the shorter ones form ONE flat stream —
-// the (begin - prefix) of each list lives in a lane's register, the owner of flat element f is found with one
-// warp-wide OR-reduction of the "a list starts here" bits plus a popc, its data come through one shuffle.
-// Adds to the lane-partial sq_b (#lists with a match) and g_b (largest per-list count).
+// `len` consecutive entries of ONE neighbour list, streamed by the whole warp (p already includes the lane offset);
+// candidates go to the queue with `owner` as their list.  Full windows carry no bounds test at all; lanes past the
+// end of the last window test vb, which never passes the filter.
 template <class Ctx>
-__device__ __forceinline__ void warp_chunk(const PaperArgs& a, Ctx& cx, int va, int c0, int* st, int lane,
-                                           int& sq_b, int& g_b) {
-    const int32_t* __restrict__ colidx = cx.colidx;
-    int mb = 0, md = 0;
-    if (c0 + lane < cx.db) {
-        const int m = colidx[cx.sb + c0 + lane];
-        if (m != va && !cx.mem.has((uint32_t)m)) {
-            mb = a.rowptr[m];
-            md = a.rowptr[m + 1] - mb;
+__device__ __forceinline__ void stream_list(Ctx& cx, const int32_t* __restrict__ p, int len, int owner, int lane) {
+    int own[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) own[u] = owner;
+    const int32_t* __restrict__ const p_full = p + (len & ~(32 * UNROLL - 1));
+    for (; p < p_full; p += 32 * UNROLL) {                  // all loads of a window are in flight before the first test
+        int k[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) k[u] = __ldg(p + 32 * u);
+        uint32_t hm = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        if (__any_sync(FULL, hm != 0u)) {
+            q_push(cx, hm, k, own, lane);
+            if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
         }
     }
-    // long lists
-    uint32_t lm = __ballot_sync(FULL, md >= LONG_LIST);
-    while (lm) {
-        const int src = __ffs(lm) - 1;
-        lm &= lm - 1;
-        const int len = __shfl_sync(FULL, md, src);
-        int c = stream_segment(cx, colidx + __shfl_sync(FULL, mb, src) + lane, len, lane);
-        c = __reduce_add_sync(FULL, c);
-        sq_b += (lane == 0 && c > 0);
-        g_b = max(g_b, c);
+    const int rem = len & (32 * UNROLL - 1);
+    if (rem) {
+        int k[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) k[u] = (32 * u + lane < rem) ? __ldg(p + 32 * u) : cx.vb;
+        uint32_t hm = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        if (__any_sync(FULL, hm != 0u)) {
+            q_push(cx, hm, k, own, lane);
+            if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
+        }
     }
-    // short lists (a list that holds only vb cannot match)
-    const bool shortl = md > 1 && md < LONG_LIST;
+}
+
+// One chunk of 32 heads of N(vb) by one warp; lane l holds head l of the chunk: (mb, md) = (begin, length) of its
+// neighbour list if the head is a PURE neighbour of vb, else (0, 0).  Lists of at least LONG_LIST entries are streamed
+// one at a time by the whole warp (no ownership arithmetic at all); the shorter ones form ONE flat stream — the
+// (begin - prefix) of each list lives in a lane's register, the owner of flat element f is found with one warp-wide
+// OR-reduction of the "a list starts here" bits plus a popc, its data come through one shuffle.  Candidates of both
+// go through the queue; the chunk ends with the queue drained and the per-list counters folded into the lane-partial
+// sq_b (#lists with a match) and g_b (largest per-list count).
+template <class Ctx>
+__device__ __forceinline__ void warp_chunk(Ctx& cx, int mb, int md, int* st, int lane, int& sq_b, int& g_b) {
+    const int32_t* __restrict__ colidx = cx.colidx;
+    const uint32_t lm0 = __ballot_sync(FULL, md >= LONG_LIST);
+    const bool shortl = md > 1 && md < LONG_LIST;               // (a list that holds only vb cannot match)
     const uint32_t pm = __ballot_sync(FULL, shortl);
-    if (pm == 0u) return;
+    if ((lm0 | pm) == 0u) return;
     int* sbeg = st + WS_BEG;
     int* slen = st + WS_LEN;
     int* lcnt = st + WS_LCNT;
+    lcnt[lane] = 0;
+    lcnt[32 + lane] = 0;
     const int nl = __popc(pm);
     if (shortl) {
         const int r = __popc(pm & ((1u << lane) - 1u));
         sbeg[r] = mb;
         slen[r] = md;
     }
-    lcnt[lane] = 0;
     __syncwarp();
-    const int len_l = lane < nl ? slen[lane] : 0;
-    int inc = len_l;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += up;
+    // long lists
+    uint32_t lm = lm0;
+    while (lm) {
+        const int src = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int len = __shfl_sync(FULL, md, src);
+        stream_list(cx, colidx + __shfl_sync(FULL, mb, src) + lane, len, 32 + src, lane);
     }
-    const int total = __shfl_sync(FULL, inc, 31);
-    const int pre_l = lane < nl ? inc - len_l : 0x3fffffff;      // flat position of the first element of list `lane`
-    const int base_l = (lane < nl ? sbeg[lane] : 0) - pre_l;     // colidx index of flat element f of this list: base + f
-    const uint32_t le_mask = 0xffffffffu >> (31 - lane);
-    int below = 0;                                               // #lists that start before the current group
-    constexpr int FU = DCR_FLAT_UNROLL;
-    for (int F = 0; F < total; F += 32 * FU) {
-        int k[FU], own[FU];
+    // short lists
+    if (pm) {
+        const int len_l = lane < nl ? slen[lane] : 0;
+        int inc = len_l;
 #pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            const int Fu = F + 32 * u;
-            const unsigned rel = (unsigned)(pre_l - Fu);
-            const uint32_t starts = __reduce_or_sync(FULL, rel < 32u ? (1u << rel) : 0u);
-            own[u] = (below + __popc(starts & le_mask) - 1) & 31;
-            below += __popc(starts);
-            const int bs = __shfl_sync(FULL, base_l, own[u]);
-            const int f = Fu + lane;
-            k[u] = f < total ? __ldg(colidx + bs + f) : cx.vb;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
         }
-        uint32_t hm = 0;
+        const int total = __shfl_sync(FULL, inc, 31);
+        const int pre_l = lane < nl ? inc - len_l : 0x3fffffff;      // flat position of the first element of list `lane`
+        const int base_l = (lane < nl ? sbeg[lane] : 0) - pre_l;     // colidx index of flat element f of this list: base + f
+        const uint32_t le_mask = 0xffffffffu >> (31 - lane);
+        int below = 0;                                               // #lists that start before the current group
+        constexpr int FU = DCR_FLAT_UNROLL;
+        for (int F = 0; F < total; F += 32 * FU) {
+            int k[FU], own[FU];
 #pragma unroll
-        for (int u = 0; u < FU; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
-        while (hm) {
-            const int u = __ffs(hm) - 1;
-            hm &= hm - 1;
-            if (cx.slow(pick(k, u))) atomicAdd(&lcnt[pick(own, u)], 1);
+            for (int u = 0; u < FU; ++u) {
+                const int Fu = F + 32 * u;
+                const unsigned rel = (unsigned)(pre_l - Fu);
+                const uint32_t starts = __reduce_or_sync(FULL, rel < 32u ? (1u << rel) : 0u);
+                own[u] = (below + __popc(starts & le_mask) - 1) & 31;
+                below += __popc(starts);
+                const int bs = __shfl_sync(FULL, base_l, own[u]);
+                const int f = Fu + lane;
+                k[u] = f < total ? __ldg(colidx + bs + f) : cx.vb;
+            }
+            uint32_t hm = 0;
+#pragma unroll
+            for (int u = 0; u < FU; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+            if (__any_sync(FULL, hm != 0u)) {
+                q_push(cx, hm, k, own, lane);
+                if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
+            }
         }
     }
-    __syncwarp();
-    const int c = lcnt[lane];
-    sq_b += c > 0;
-    g_b = max(g_b, c);
+    if (cx.qn) q_flush(cx, lane); else __syncwarp();
+    const int c1 = lcnt[lane], c2 = lcnt[32 + lane];
+    sq_b += (c1 > 0) + (c2 > 0);
+    g_b = max(g_b, max(c1, c2));
     __syncwarp();
 }
 
-// One edge by one warp.  `st` = the warp's scratch, `tb` = its triangle bitmap (TB_WORDS words), `mh` = its match
-// hash (2*CAP words, all zero on entry and on exit).  Writes the four integer fields of local edge t and returns
-// true, or returns false when the match hash filled up or the edge has too many triangles for the warp's filter
-// (nothing written; the hash is clean again).
+// One edge by one warp over the CTA-level membership structure (group kernels).  `st` = the warp's scratch, `tb` =
+// its exact triangle set (TSLOTS words), `mh` = its match hash (2*CAP words, all zero on entry and on exit), `q` = its
+// candidate queue.  Writes the four integer fields of local edge t and returns true, or returns false when the match
+// hash filled up or the edge has too many triangles for the warp's set (nothing written; the hash is clean again).
 template <int CAP, int TSLOTS, bool DENSE, bool CAN_DEFER>
 __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st,
-                                          uint32_t* tb, uint32_t* mh, int lane) {
+                                          uint32_t* tb, uint32_t* mh, uint2* q, int lane) {
     const int64_t e = a.e_first + (int64_t)t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const bool swapped = (va == j);                      // stream i's side, test j
     EdgeCtx<DENSE, TRI_SET> cx;
     cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.tb_mask = TSLOTS - 1; cx.hash.init(mh, st + WS_NDIST, CAP);
+    cx.q = q; cx.qn = 0; cx.lcnt = st + WS_LCNT;
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
     cx.ovf = false;
-    // pass 1 over the heads: the common neighbours (triangles)
+    // pass 1 over the heads: the common neighbours (triangles).  Lane l looks at heads l, l+32, ...; whether head
+    // l + 32c is in N(va) is remembered in bit c of `mbits` (heads beyond 1024 are looked up again in pass 2).
     int tri = 0;
-    for (int p = lane; p < cx.db; p += 32) {
+    uint32_t mbits = 0;
+    for (int p = lane, c = 0; p < cx.db; p += 32, ++c) {
         const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-        tri += ((int)m != va && mem.has(m));
+        const bool in = ((int)m != va && mem.has(m));
+        tri += in;
+        if (c < 32) mbits |= in ? (1u << c) : 0u;
     }
     tri = __reduce_add_sync(FULL, tri);
     // the warp's exact set of T holds TSLOTS/2 keys: a richer edge goes to the CTA path
@@ -1021,11 +1072,11 @@ __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE
     if (tri > 0) {
         for (int p = lane; p < TSLOTS; p += 32) tb[p] = EMPTY;
         __syncwarp();
-        for (int p = lane; p < cx.db; p += 32) {
+        for (int p = lane, c = 0; p < cx.db; p += 32, ++c) {
+            if (c < 32 && !((mbits >> c) & 1u)) continue;
             const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-            if ((int)m != va && mem.has(m)) tri_set_insert(tb, TSLOTS - 1, m);
+            if (c < 32 || ((int)m != va && mem.has(m))) tri_set_insert(tb, TSLOTS - 1, m);
         }
-        __syncwarp();
     } else if (lane == 0) {
         tb[0] = EMPTY;                                   // an empty set is recognised by its first probe ...
     }
@@ -1033,7 +1084,18 @@ __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE
     __syncwarp();
     // pass 2: the lists of the pure heads
     int sq_b = 0, g_b = 0;
-    for (int c0 = 0; c0 < cx.db; c0 += 32) warp_chunk(a, cx, va, c0, st, lane, sq_b, g_b);
+    for (int c0 = 0, c = 0; c0 < cx.db; c0 += 32, ++c) {
+        int mb = 0, md = 0;
+        if (c0 + lane < cx.db) {
+            const int m = a.colidx[cx.sb + c0 + lane];
+            const bool in = c < 32 ? ((mbits >> c) & 1u) : mem.has((uint32_t)m);
+            if (m != va && !in) {
+                mb = a.rowptr[m];
+                md = a.rowptr[m + 1] - mb;
+            }
+        }
+        warp_chunk(cx, mb, md, st, lane, sq_b, g_b);
+    }
     sq_b = __reduce_add_sync(FULL, sq_b);
     g_b = __reduce_max_sync(FULL, g_b);
     int sq_a = 0, g_a = 0;
@@ -1054,25 +1116,114 @@ __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE
     return !ovf;
 }
 
-// L0: warp-private hashed table, kept while consecutive edges (sorted by tested endpoint) share va.
+// ------------------------------------------------------------------------------------------------------------
+// L0 (d_a <= 128): everything private to the warp.  The key-only table of N(va) doubles as the match structure:
+// `cnt[h]` belongs to the key in slot h — bit 31 marks a common neighbour (never a match), the low bits count the
+// matches of the current edge — so a candidate costs ONE probe (membership, triangle test and match counter at once)
+// and there is neither a triangle set nor a match hash.  At most 128 distinct keys: nothing can overflow.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t L0_TRI = 0x80000000u;
+struct L0Ctx {
+    const int32_t* __restrict__ colidx;
+    const uint32_t* tab;
+    const uint32_t* bm;
+    uint32_t* cnt;
+    uint32_t mask;
+    int shift;
+    uint2* q;
+    int qn;
+    int* lcnt;
+    int vb, sb, db;
+    __device__ __forceinline__ bool hit(int k) const { return bitmap_test(bm, L0_BITS - 1, (uint32_t)k) && k != vb; }
+    __device__ __forceinline__ void handle(uint32_t kk, uint32_t list) {
+        const int h = ro_probe(tab, mask, shift, kk);
+        if (h >= 0 && !(*(volatile uint32_t*)(cnt + h) & L0_TRI)) {
+            atomicAdd(&cnt[h], 1u);
+            atomicAdd(&lcnt[list], 1);
+        }
+    }
+};
+
+__device__ __forceinline__ void warp_edge_l0(const PaperArgs& a, L0Ctx& cx, uint32_t t, int va, int* st, int lane) {
+    const int64_t e = a.e_first + (int64_t)t * a.e_stride;
+    const int i = a.esrc[e], j = a.edst[e];
+    const bool swapped = (va == j);                      // stream i's side, test j
+    cx.vb = swapped ? i : j;
+    cx.sb = a.rowptr[cx.vb];
+    cx.db = a.rowptr[cx.vb + 1] - cx.sb;
+    cx.qn = 0;
+    // pass 1 over the heads: common neighbours get their slot marked
+    int tri = 0;
+    uint32_t mbits = 0;
+    for (int p = lane, c = 0; p < cx.db; p += 32, ++c) {
+        const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+        bool in = false;
+        if ((int)m != va && bitmap_test(cx.bm, L0_BITS - 1, m)) {
+            const int h = ro_probe(cx.tab, cx.mask, cx.shift, m);
+            if (h >= 0) { cx.cnt[h] = L0_TRI; in = true; }
+        }
+        tri += in;
+        if (c < 32) mbits |= in ? (1u << c) : 0u;
+    }
+    tri = __reduce_add_sync(FULL, tri);
+    __syncwarp();
+    // pass 2: the lists of the pure heads
+    int sq_b = 0, g_b = 0;
+    for (int c0 = 0, c = 0; c0 < cx.db; c0 += 32, ++c) {
+        int mb = 0, md = 0;
+        if (c0 + lane < cx.db) {
+            const int m = a.colidx[cx.sb + c0 + lane];
+            const bool in = c < 32 ? ((mbits >> c) & 1u)
+                                   : (bitmap_test(cx.bm, L0_BITS - 1, (uint32_t)m) && ro_probe(cx.tab, cx.mask, cx.shift, (uint32_t)m) >= 0);
+            if (m != va && !in) {
+                mb = a.rowptr[m];
+                md = a.rowptr[m + 1] - mb;
+            }
+        }
+        warp_chunk(cx, mb, md, st, lane, sq_b, g_b);
+    }
+    sq_b = __reduce_add_sync(FULL, sq_b);
+    g_b = __reduce_max_sync(FULL, g_b);
+    // the collect: one sweep over the slot counters reads the matches of va's side and leaves them all zero
+    int sq_a = 0, g_a = 0;
+    if (sq_b > 0 || tri > 0) {
+        for (uint32_t s = lane; s <= cx.mask; s += 32) {
+            const uint32_t c = cx.cnt[s];
+            if (c) {
+                cx.cnt[s] = 0u;
+                if (!(c & L0_TRI)) { ++sq_a; g_a = max(g_a, (int)c); }
+            }
+        }
+        sq_a = __reduce_add_sync(FULL, sq_a);
+        g_a = __reduce_max_sync(FULL, g_a);
+    }
+    if (lane == 0) {
+        a.out_tri[t] = tri;
+        a.out_sq_i[t] = swapped ? sq_b : sq_a;
+        a.out_sq_j[t] = swapped ? sq_a : sq_b;
+        a.out_gamma[t] = (sq_b > 0 && sq_a > 0) ? max(g_a, g_b) : 0;
+    }
+    __syncwarp();
+}
+
+// L0 kernel: warp-private table, kept while consecutive edges (sorted by tested endpoint) share va.
+constexpr int L0_PER_WARP = WSTATE_INTS + Q_WORDS + L0_BITS / 32 + 2 * L0_SLOTS;
 __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_warp_kernel(PaperArgs a) {
     extern __shared__ uint32_t smem_dyn[];
-    constexpr int PER_WARP = WSTATE_INTS + L0_TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* base = smem_dyn + warp * PER_WARP;
+    uint32_t* base = smem_dyn + warp * L0_PER_WARP;
     int* st = (int*)base;
-    uint32_t* tb = base + WSTATE_INTS;
-    uint32_t* mh = tb + L0_TB_WORDS;
-    uint32_t* bm = mh + 2 * L0_CAP;
+    uint32_t* bm = base + WSTATE_INTS + Q_WORDS;
     uint32_t* tab = bm + L0_BITS / 32;
-    for (int p = lane; p < 2 * L0_CAP; p += 32) mh[p] = 0u;
-    if (lane == 0) st[WS_NDIST] = 0;
+    uint32_t* cnt = tab + L0_SLOTS;
+    for (int p = lane; p < L0_SLOTS; p += 32) cnt[p] = 0u;
     __syncwarp();
     const WorkSource ws = work_source(a, CL_L0);
     const uint32_t* ova = a.ova + a.plan->class_begin[CL_L0];
     int cur_va = -1;
-    Member<false> mem;
-    mem.tab = tab; mem.bm = bm; mem.bmask = L0_BITS - 1; mem.mask = 0; mem.shift = 0;
+    L0Ctx cx;
+    cx.colidx = a.colidx; cx.tab = tab; cx.bm = bm; cx.cnt = cnt; cx.mask = 0; cx.shift = 0;
+    cx.q = (uint2*)(base + WSTATE_INTS); cx.qn = 0; cx.lcnt = st + WS_LCNT;
     while (true) {
         unsigned int idx0 = 0;
         if (lane == 0) idx0 = atomicAdd(ws.next, (unsigned)DCR_L0_GRAB);
@@ -1083,23 +1234,23 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
             const int va = (int)ova[q];
             if (va != cur_va) {
                 const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
-                ro_geometry<L0_SLOTS, 2>(da, mem.mask, mem.shift);
-                for (uint32_t s = lane; s <= mem.mask; s += 32) tab[s] = EMPTY;
+                ro_geometry<L0_SLOTS, 2>(da, cx.mask, cx.shift);
+                for (uint32_t s = lane; s <= cx.mask; s += 32) tab[s] = EMPTY;
                 for (int s = lane; s < L0_BITS / 32; s += 32) bm[s] = 0u;
                 __syncwarp();
                 for (int p = lane; p < da; p += 32) {
                     const uint32_t k = (uint32_t)a.colidx[sa + p];
-                    ro_insert(tab, mem.mask, mem.shift, k);
-                    atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
+                    ro_insert(tab, cx.mask, cx.shift, k);
+                    atomicOr(&bm[(k & (L0_BITS - 1)) >> 5], 1u << (k & 31u));
                 }
                 __syncwarp();
                 cur_va = va;
             }
-            // d_a <= 128 distinct matches always fit the hash (L0_CAP * 3/4 = 192)
-            warp_edge<L0_CAP, L0_TB_WORDS, false, false>(a, mem, ws.order[q], va, st, tb, mh, lane);
+            warp_edge_l0(a, cx, ws.order[q], va, st, lane);
         }
     }
 }
+
 
 // One COOPERATIVE edge by the whole CTA (stream too long, or too many distinct matches, for one warp).  Rounds of
 // THREADS heads: every thread resolves one head, a CTA-wide prefix sum compacts the lists of the pure heads and lays
@@ -1113,7 +1264,7 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
 // CTA-wide hash goes to the global overflow list.
 template <int NWARPS, bool DENSE>
 __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st_all,
-                                      uint32_t* tb_all, uint32_t* hash_words, uint32_t hash_cap, int* s_acc,
+                                      uint32_t* tb_all, uint32_t* hash_words, uint32_t hash_cap, uint2* q_all, int* s_acc,
                                       unsigned long long* s_wtot, int part, int parts, SplitEdge* se) {
     constexpr int THREADS = NWARPS * 32, TBW = COOP_TB_WORDS, TM = DENSE ? TRI_DENSE : TRI_HASHED;
     static_assert(3 * THREADS + 1 <= NWARPS * WSTATE_INTS, "cooperative stream state must fit the warp scratch");
@@ -1127,6 +1278,7 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
     EdgeCtx<DENSE, TM> cx;
     cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb_all; cx.tb_mask = TBW - 1;
     cx.hash.init(hash_words, se ? &se->n_distinct : s_acc + 4, hash_cap);
+    cx.q = q_all + warp * Q_CAP; cx.qn = 0; cx.lcnt = lcnt;
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
@@ -1201,12 +1353,11 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
                 int l = lo;
                 while (f0 < f1) {
                     const int seg_end = min(f1, pre[l + 1]);
-                    int c = stream_segment(cx, a.colidx + beg[l] + (f0 - pre[l]) + lane, seg_end - f0, lane);
-                    c = __reduce_add_sync(FULL, c);
-                    if (lane == 0 && c) atomicAdd(&lcnt[l], c);
+                    stream_list(cx, a.colidx + beg[l] + (f0 - pre[l]) + lane, seg_end - f0, l, lane);
                     f0 = seg_end;
                     ++l;
                 }
+                if (cx.qn) q_flush(cx, lane);
             }
             __syncthreads();
             const int c = tid < nlists ? lcnt[tid] : 0;
@@ -1273,16 +1424,16 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
 // (2*ghash_cap words, ghash_cap >= 2 * max degree: it cannot fill up).  Ends with the CTA synchronised.
 template <int NWARPS, int CAP, bool DENSE>
 __device__ __forceinline__ void cta_edge_retry(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va,
-                                               int* st_all, uint32_t* tb_all, uint32_t* mh_all, int* s_acc,
+                                               int* st_all, uint32_t* tb_all, uint32_t* mh_all, uint2* q_all, int* s_acc,
                                                unsigned long long* s_wtot) {
-    cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, mh_all, NWARPS * CAP, s_acc, s_wtot, 0, 1, nullptr);
+    cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, mh_all, NWARPS * CAP, q_all, s_acc, s_wtot, 0, 1, nullptr);
     __syncthreads();
     if (s_acc[5]) {
         uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
         for (uint32_t p = threadIdx.x; p < 2 * a.ghash_cap; p += NWARPS * 32) gh[p] = 0u;
         __threadfence_block();
         __syncthreads();
-        cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, gh, a.ghash_cap, s_acc, s_wtot, 0, 1, nullptr);
+        cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, gh, a.ghash_cap, q_all, s_acc, s_wtot, 0, 1, nullptr);
         __syncthreads();
     }
 }
@@ -1322,7 +1473,8 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     uint32_t* tb_all = tb_coop + tb_coop_words;
     uint32_t* mh_all = tb_all + NWARPS * TB_WORDS;
     int* st_all = (int*)(mh_all + NWARPS * 2 * CAP);
-    uint32_t* tab = (uint32_t*)(st_all + NWARPS * WSTATE_INTS);
+    uint2* q_all = (uint2*)(st_all + NWARPS * WSTATE_INTS);          // per-warp candidate queues (8-byte aligned: all sizes even)
+    uint32_t* tab = (uint32_t*)(q_all + NWARPS * Q_CAP);
     uint32_t* bm = tab + (DENSE ? 0 : MAX_SLOTS);
     const int bm_words = DENSE ? dense_words : BITS / 32;
     int* st = st_all + warp * WSTATE_INTS;
@@ -1395,14 +1547,14 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
             const int va = edge_role(a, i, j, a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j]).va;
             build(va);
             cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, a.shash + (size_t)k * SHASH_WORDS + se->hash_off,
-                                    se->hash_cap, s_acc, s_wtot, part, se->parts, se);
+                                    se->hash_cap, q_all, s_acc, s_wtot, part, se->parts, se);
             __syncthreads();
             if (s_acc[8] && s_acc[5]) {                  // its hash filled up: once more, whole, with this CTA's big hash
                 uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
                 for (uint32_t p = tid; p < 2 * a.ghash_cap; p += THREADS) gh[p] = 0u;
                 __threadfence_block();
                 __syncthreads();
-                cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, gh, a.ghash_cap, s_acc, s_wtot, 0, 1, nullptr);
+                cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, gh, a.ghash_cap, q_all, s_acc, s_wtot, 0, 1, nullptr);
             }
             TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (3ull << 30) | t; })
         }
@@ -1417,7 +1569,7 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
         TRACE(const unsigned long long tr_a = gtimer();)
         const int va = (int)cova[idx];
         build(va);
-        cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, cws.order[idx], va, st_all, tb_coop, mh_all, s_acc, s_wtot);
+        cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, cws.order[idx], va, st_all, tb_coop, mh_all, q_all, s_acc, s_wtot);
         TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (1ull << 30) | cws.order[idx]; })
     }
     TRACE(const unsigned long long tr_t1 = gtimer();)
@@ -1440,13 +1592,13 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
             my = __shfl_sync(FULL, my, 0);
             if ((int)my >= q_end) break;
             const uint32_t t = ord[my];
-            if (!warp_edge<CAP, TB_WORDS, DENSE, true>(a, mem, t, va, st, tb, mh, lane) && lane == 0)
+            if (!warp_edge<CAP, TB_WORDS, DENSE, true>(a, mem, t, va, st, tb, mh, q_all + warp * Q_CAP, lane) && lane == 0)
                 s_defer[atomicAdd(&s_ndefer, 1)] = t;     // too many triangles / distinct matches for one warp: CTA path
         }
         __syncthreads();                                  // every warp is done with the run
         const int nd = s_ndefer;
         for (int d = 0; d < nd; ++d)
-            cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, s_acc, s_wtot);
+            cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, q_all, s_acc, s_wtot);
         if (nd > 0 && lane == 0) st[WS_NDIST] = 0;
         TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (2ull << 30) | ((unsigned long long)nd << 20) | s_idx; })
     }
@@ -1599,12 +1751,13 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     const int dev = current_device();
     bool& attr_done = attr_done_dev[dev];
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
-    const int dense_words = (n + 31) / 32;
+    const int dense_words = (n + 63) / 64 * 2;       // even: what follows the bitmaps in shared memory is 8-byte aligned
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
-    const int smem_l0 = L0_WARPS * (WSTATE_INTS + L0_TB_WORDS + 2 * L0_CAP + L0_BITS / 32 + L0_SLOTS) * (int)sizeof(uint32_t);
-    const int smem_g1 = (COOP_TB_WORDS + G1_SLOTS + G1_BITS / 32 + G1_WARPS * (TB_WORDS + 2 * G1_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
-    const int smem_g2 = (COOP_TB_WORDS + G2_SLOTS + G2_BITS / 32 + G2_WARPS * (TB_WORDS + 2 * G2_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
-    const int smem_gd = (2 * dense_words + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+    constexpr int WARP_WORDS = TB_WORDS + WSTATE_INTS + Q_WORDS;     // per warp of a group kernel, beside its match hash
+    const int smem_l0 = L0_WARPS * L0_PER_WARP * (int)sizeof(uint32_t);
+    const int smem_g1 = (COOP_TB_WORDS + G1_SLOTS + G1_BITS / 32 + G1_WARPS * (2 * G1_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+    const int smem_g2 = (COOP_TB_WORDS + G2_SLOTS + G2_BITS / 32 + G2_WARPS * (2 * G2_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+    const int smem_gd = (2 * dense_words + GD_WARPS * (2 * GD_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
     auto* k_g1 = paper_group_kernel<G1_WARPS, G1_SLOTS, G1_BITS, G1_CAP, G1_CTAS_PER_SM, false>;
     auto* k_g2 = paper_group_kernel<G2_WARPS, G2_SLOTS, G2_BITS, G2_CAP, 1, false>;
     auto* k_gd = paper_group_kernel<GD_WARPS, 64, 32, GD_CAP, GD_CTAS_PER_SM, true>;
@@ -1614,7 +1767,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_CUDA(cudaFuncSetAttribute(paper_light_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l0));
         DCR_CUDA(cudaFuncSetAttribute(k_g1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g1));
         DCR_CUDA(cudaFuncSetAttribute(k_g2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g2));
-        const int smem_gd_max = (2 * (DENSE_MAX_N / 32) + GD_WARPS * (TB_WORDS + 2 * GD_CAP + WSTATE_INTS)) * (int)sizeof(uint32_t);
+        const int smem_gd_max = (2 * (DENSE_MAX_N / 32) + GD_WARPS * (2 * GD_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
         DCR_CUDA(cudaFuncSetAttribute(k_gd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gd_max));
         attr_done = true;
     }

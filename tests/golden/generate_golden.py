@@ -143,6 +143,67 @@ def gen_paper(out):
     print("paper_kat:", len(graphs), "graphs")
 
 
+def _bfc_edge_with_locals(G, v1, v2):
+    """Run the UNMODIFIED ``bfc_edge`` and return ``(value, locals at return)`` — the integer quantities the paper
+    flavour must match bit-exactly (``len(triangles)``, ``len(squares_1)``, ``len(squares_2)``, ``gamma``) are locals
+    of that function, read from its frame by a profile hook."""
+    grabbed = {}
+    code = ref_naive.bfc_edge.__code__
+
+    def hook(frame, event, arg):
+        if event == "return" and frame.f_code is code:
+            grabbed.update(frame.f_locals)
+
+    sys.setprofile(hook)
+    try:
+        val = ref_naive.bfc_edge(G, v1, v2)
+    finally:
+        sys.setprofile(None)
+    return val, grabbed
+
+
+def gen_paper_ints(out):
+    """Integer fields of the paper flavour from the unmodified reference: per edge (deg1, deg2, #triangles, #squares_1,
+    #squares_2, gamma) with gamma = 0 where the reference never computes it (early returns at bfc_naive.py:18-19,30-32)."""
+    from dcr.synth import named_graph
+
+    graphs = {k: (sorted_symmetric_edge_index(g), g.number_of_nodes()) for k, g in toy_graphs().items()}
+    for seed in range(24):
+        n = 12 + seed
+        g = nx.gnp_random_graph(n, 0.12 + 0.015 * (seed % 12), seed=seed)
+        graphs[f"gnp{seed}"] = (sorted_symmetric_edge_index(g), n)
+    for seed in range(6):                       # denser graphs: every edge reaches the gamma branch
+        n = 30 + 4 * seed
+        g = nx.gnp_random_graph(n, 0.3 + 0.05 * seed, seed=300 + seed)
+        graphs[f"dense{seed}"] = (sorted_symmetric_edge_index(g), n)
+    for name in ("cornell", "wisconsin"):
+        graphs[name] = named_graph(name)
+    pack = {"names": np.array(sorted(graphs))}
+    n_gamma = 0
+    for name, (ei, n) in graphs.items():
+        G = graph_from_edge_index(ei, n)
+        m = ei[0] < ei[1]
+        edges = np.stack([ei[0][m], ei[1][m]], axis=1)
+        ints = np.zeros((edges.shape[0], 6), dtype=np.int64)
+        vals = np.zeros(edges.shape[0], dtype=np.float64)
+        for q, (a, b) in enumerate(edges):
+            val, loc = _bfc_edge_with_locals(G, int(a), int(b))
+            vals[q] = float(val)
+            ints[q, 0], ints[q, 1] = loc["deg1"], loc["deg2"]
+            if "triangles" in loc:
+                ints[q, 2:5] = len(loc["triangles"]), len(loc["squares_1"]), len(loc["squares_2"])
+            if "gamma" in loc:
+                ints[q, 5] = int(loc["gamma"])
+                n_gamma += 1
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/edges"] = edges
+        pack[f"{name}/ints"] = ints
+        pack[f"{name}/bfc"] = vals
+    np.savez_compressed(out, **pack)
+    print("paper_ints_kat:", len(graphs), "graphs,", n_gamma, "edges with gamma")
+
+
 def dense_from_edge_index(ei, n):
     A = torch.zeros(n, n)
     A[ei[0], ei[1]] = 1.0
@@ -299,7 +360,9 @@ def gen_sdrf_directed(out):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["paper", "cuda", "sdrf", "sdrf_directed"]
+    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed"]
+    if "paper_ints" in which:
+        gen_paper_ints(os.path.join(HERE, "paper_ints_kat.npz"))
     if "sdrf_directed" in which:
         gen_sdrf_directed(os.path.join(HERE, "sdrf_directed_seq.npz"))
     if "paper" in which:
