@@ -51,10 +51,10 @@ constexpr uint32_t KEYMASK = 0x3fffffffu;
 enum { CL_L0 = 0, CL_G1, CL_G2, CL_C1, CL_C2, CL_X, N_CLASSES };   // C1 / C2: the cooperative edges of G1 / G2
 constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
 #ifndef DCR_COOP_L0
-#define DCR_COOP_L0 8192
+#define DCR_COOP_L0 16384
 #endif
 #ifndef DCR_COOP_G
-#define DCR_COOP_G 24576
+#define DCR_COOP_G 16384
 #endif
 // stream length above which an edge is cooperative (one CTA per edge; L0 vertices hand such edges to C1).  Measured on
 // the arxiv shape at 1/1 and 1/8 of the edges per call: finer items (8192 / 4096) lose at both sizes — the CTA path
@@ -93,10 +93,6 @@ constexpr long long SIZE_B1 = 2048, SIZE_B2 = 512;
 #define DCR_RUN_EDGES 64
 #endif
 constexpr int RUN_EDGES = DCR_RUN_EDGES;
-#ifndef DCR_COOP_SLICE
-#define DCR_COOP_SLICE 512
-#endif
-constexpr int COOP_SLICE = DCR_COOP_SLICE;        // cooperative edges: flat-stream elements per work item of a warp
 __host__ __device__ inline int run_table_of(int cls) { return cls == CL_G2 ? 1 : 0; }
 __host__ __device__ inline int coop_class_of(int cls) { return cls == CL_G2 ? CL_C2 : CL_C1; }
 constexpr int BIG_SLOTS = 32768, BIG_THREADS = 1024;
@@ -129,12 +125,15 @@ constexpr int UNROLL = DCR_UNROLL;
 #define DCR_LONG_LIST 64
 #endif
 constexpr int LONG_LIST = DCR_LONG_LIST;     // lists at least this long are streamed one at a time by the whole warp
-constexpr int L0_SLOTS = 256, L0_BITS = 4096, L0_CAP = 256, L0_WARPS = 8, L0_CTAS_PER_SM = DCR_L0_CTAS;
+#ifndef DCR_L0_BITS
+#define DCR_L0_BITS 8192
+#endif
+constexpr int L0_SLOTS = 256, L0_BITS = DCR_L0_BITS, L0_WARPS = 8, L0_CTAS_PER_SM = DCR_L0_CTAS;
 constexpr int G1_SLOTS = 2048, G1_BITS = 32768, G1_CAP = 512, G1_WARPS = 8, G1_CTAS_PER_SM = DCR_G1_CTAS;
 constexpr int G2_SLOTS = 32768, G2_BITS = 131072, G2_CAP = 256, G2_WARPS = 16;
 // dense mode: exact bitmap of N(va) over all node ids; 8 warps and >= 4 CTAs per SM while n <= DENSE_MAX_N
 #ifndef DCR_GD_CTAS
-#define DCR_GD_CTAS 3
+#define DCR_GD_CTAS 4
 #endif
 #ifndef DCR_GD_WARPS
 #define DCR_GD_WARPS 8
@@ -152,14 +151,12 @@ constexpr int WS_BEG = 0, WS_LEN = 32, WS_LCNT = 64, WS_NDIST = 128, WSTATE_INTS
 constexpr int Q_FLUSH = 32, Q_CAP = Q_FLUSH + 32 * (DCR_UNROLL > DCR_FLAT_UNROLL ? DCR_UNROLL : DCR_FLAT_UNROLL);
 constexpr int Q_WORDS = 2 * Q_CAP;
 // Common neighbours T = N(va) ∩ N(vb) must not count as matches, and they are FREQUENT in the stream of a hub–hub
-// edge (hubs are each other's neighbours), so membership in T has to be exact and on chip:
-//   TRI_SET     warp path: exact open-addressing set of T in the warp's scratch (TB_WORDS slots, |T| <= TRI_DEFER in
-//               the group kernels — richer edges go to the CTA path; 256 slots in L0 where |T| <= d_a <= 128)
-//   TRI_DENSE   CTA path, dense mode: a second exact bitmap over all node ids
-//   TRI_HASHED  CTA path, hashed mode: 64K-bit hashed bitmap, positives confirmed by binary search in N(vb)
-enum { TRI_SET = 0, TRI_DENSE = 1, TRI_HASHED = 2 };
-constexpr int TB_WORDS = 64, L0_TB_WORDS = 256;
-constexpr int COOP_TB_WORDS = 2048;
+// edge (hubs are each other's neighbours), so membership in T has to be exact and on chip: an open-addressing set of T
+// — TB_WORDS slots in the warp's scratch on the warp path (edges with |T| > TRI_DEFER go to the CTA path), sized for
+// |T| on the CTA path (shared memory up to TSET_WORDS slots, this CTA's region of global memory beyond).  The d_a <=
+// 128 kernel marks the slots of T in its table of N(va) instead.
+enum { TRI_SET = 0 };
+constexpr int TB_WORDS = 64;
 constexpr int TRI_DEFER = 32;                // light edges with more triangles go to the CTA path
 
 struct PaperPlan {           // lives at the head of the scratch buffer
@@ -191,7 +188,7 @@ struct PaperArgs {
     uint32_t* ova;         // [count] tested endpoint of order[pos]
     uint32_t* va_cnt;      // [N_SLOTS][n] #edges per (cooperative | size bucket, tested endpoint); then: rank offset inside the group
     uint32_t* va_cur;      // [N_SLOTS][n] fill cursors
-    uint32_t* grp;         // [4][n] (start, count) of the vertex's light group and of its cooperative group in `order`
+    uint32_t* grp;         // [5][n] (start, count) of the vertex's light group and of its cooperative group in `order`, #runs
     uint2* runs;           // [2][max_runs] (first position, length) of the runs of the group classes
     uint32_t max_runs;
     int n;
@@ -200,6 +197,7 @@ struct PaperArgs {
     uint32_t gslots;
     uint32_t* ghash;       // last-resort match hashes in global memory: 2*ghash_cap words per CTA of a group kernel
     uint32_t ghash_cap;
+    uint32_t* gtri;        // the CTA path's triangle sets that do not fit shared memory: ghash_cap words per CTA of a group kernel
     uint32_t* shash;       // [2][SHASH_WORDS] pools of the split edges' match hashes (the used part is zeroed per call)
     uint32_t* split_item;  // [2][MAX_SPLIT * MAX_PARTS] work item -> split edge << 8 | part
 };
@@ -370,13 +368,13 @@ __global__ void plan_ranges_kernel(PaperArgs a) {
 }
 
 // position of rank s inside a group of `cnt` edges that starts at `gstart` (see RUN_EDGES)
-__device__ __forceinline__ unsigned int run_layout_pos(unsigned int gstart, unsigned int cnt, unsigned int s) {
-    const unsigned int R = (cnt + RUN_EDGES - 1) / RUN_EDGES, q = cnt / R, rem = cnt % R;
+__device__ __forceinline__ unsigned int run_layout_pos(unsigned int gstart, unsigned int cnt, unsigned int R, unsigned int s) {
+    const unsigned int q = cnt / R, rem = cnt % R;
     const unsigned int r = s % R;
     return gstart + r * q + min(r, rem) + s / R;
 }
-__device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned int gstart, unsigned int cnt) {
-    const unsigned int R = (cnt + RUN_EDGES - 1) / RUN_EDGES, q = cnt / R, rem = cnt % R;
+__device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned int gstart, unsigned int cnt, unsigned int R) {
+    const unsigned int q = cnt / R, rem = cnt % R;
     const int tbl = run_table_of(cls);
     const unsigned int base = atomicAdd(&a.plan->n_runs[tbl], R);
     for (unsigned int r = 0; r < R; ++r)
@@ -420,7 +418,12 @@ __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
         const unsigned int gstart = s_base[cls] + own_off;
         a.grp[v] = gstart;
         a.grp[(size_t)a.n + v] = own;
-        if (cls == CL_G1 || cls == CL_G2) emit_runs(a, cls, gstart, own);
+        if (cls == CL_G1 || cls == CL_G2) {
+            unsigned int R = (own + RUN_EDGES - 1) / RUN_EDGES;
+            R = max(1u, min(R, own));
+            a.grp[(size_t)4 * a.n + v] = R;
+            emit_runs(a, cls, gstart, own, R);
+        }
     }
     if (c[0]) {
         a.grp[(size_t)2 * a.n + v] = s_base[cc] + coop_off;
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
     const unsigned int s = a.va_cnt[slot] + atomicAdd(&a.va_cur[slot], 1u);
     const size_t g = (r.slot == 0 ? (size_t)2 * a.n : 0) + r.va;
     const unsigned int gstart = a.grp[g], cnt = a.grp[g + a.n];
-    const unsigned int pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, s) : gstart + s;
+    const unsigned int pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, a.grp[(size_t)4 * a.n + r.va], s) : gstart + s;
     a.order[pos] = (uint32_t)t;
     a.ova[pos] = (uint32_t)r.va;
 }
@@ -794,11 +797,33 @@ struct Member {
     __device__ __forceinline__ bool maybe(uint32_t k) const {      // cheap necessary condition (exact when DENSE)
         return DENSE ? ((bm[k >> 5] >> (k & 31u)) & 1u) : bitmap_test(bm, bmask, k);
     }
+    __device__ __forceinline__ uint32_t word(uint32_t k) const { return DENSE ? bm[k >> 5] : bm[(k & bmask) >> 5]; }
     __device__ __forceinline__ bool confirm(uint32_t k) const {    // after maybe(k)
         return DENSE ? true : (ro_probe(tab, mask, shift, k) >= 0);
     }
     __device__ __forceinline__ bool has(uint32_t k) const { return maybe(k) && confirm(k); }
 };
+
+// One out-of-line copy per kernel: the candidate path is cold next to the streaming loops, and the group kernels had
+// outgrown the instruction cache (stall_no_instructions was the top stall reason with everything inlined).
+__device__ __noinline__ bool match_hash_add(uint32_t* mh, int* n_distinct, uint32_t cap, int shift, uint32_t k) {
+    const uint32_t key = k + 1u;
+    uint32_t p = (key * 0x9E3779B1u) >> shift;
+    for (uint32_t tries = 0; tries < cap; ++tries) {
+        uint32_t v = *(volatile uint32_t*)(mh + p);
+        if (v == 0u) {
+            if (*(volatile int*)n_distinct >= (int)(cap / 4 * 3)) return false;
+            v = atomicCAS(&mh[p], 0u, key);
+            if (v == 0u) atomicAdd(n_distinct, 1);
+        }
+        if (v == 0u || v == key) {
+            atomicAdd(&mh[cap + p], 1u);
+            return true;
+        }
+        p = (p + 1) & (cap - 1);
+    }
+    return false;
+}
 
 // Match hash: keys[cap] (node id + 1) | counts[cap], cap a power of two; lives in shared memory (per warp, or the
 // per-warp hashes of a CTA taken together) or, as a last resort, in global memory.
@@ -811,24 +836,7 @@ struct MatchHash {
         mh = p; n_distinct = nd; cap = c; shift = __clz(c) + 1;
     }
     // false when the hash is (nearly) full
-    __device__ __forceinline__ bool add(uint32_t k) {
-        const uint32_t key = k + 1u;
-        uint32_t p = (key * 0x9E3779B1u) >> shift;
-        for (uint32_t tries = 0; tries < cap; ++tries) {
-            uint32_t v = *(volatile uint32_t*)(mh + p);
-            if (v == 0u) {
-                if (*(volatile int*)n_distinct >= (int)(cap / 4 * 3)) return false;
-                v = atomicCAS(&mh[p], 0u, key);
-                if (v == 0u) atomicAdd(n_distinct, 1);
-            }
-            if (v == 0u || v == key) {
-                atomicAdd(&mh[cap + p], 1u);
-                return true;
-            }
-            p = (p + 1) & (cap - 1);
-        }
-        return false;
-    }
+    __device__ __forceinline__ bool add(uint32_t k) { return match_hash_add(mh, n_distinct, cap, shift, k); }
     // (#distinct keys, largest count) of this thread's share of the hash; clears what it reads
     __device__ __forceinline__ void collect(int first, int stride, int& sq_a, int& g_a) {
         for (uint32_t p = first; p < cap; p += stride) {
@@ -849,39 +857,47 @@ template <bool DENSE, int TM>
 struct EdgeCtx {
     const int32_t* __restrict__ colidx;
     Member<DENSE> mem;
-    const uint32_t* tb;      // the structure that answers "k in T" (see TRI_*)
-    uint32_t tb_mask;        // TRI_SET: slots - 1; TRI_HASHED: words - 1
+    const uint32_t* tb;      // exact open-addressing set of T (per warp in shared memory, or the CTA's: shared / global)
+    uint32_t tb_mask;        // slots - 1 (0: the empty set)
+    int tb_shift;            // 32 - log2(slots)
+    bool tb_global;          // the set lives in global memory (filled with L2 atomics: read with ld.global.cg)
     MatchHash hash;
-    uint2* q;                // candidate queue (key, list)
+    uint32_t* q;             // candidate queue: (key, list) pairs, or key | list << 24 in one word when DENSE (n <= 2^18)
     int qn;                  // its length (warp-uniform)
+    static constexpr int Q_ENTRY_WORDS = DENSE ? 1 : 2;
+    __device__ __forceinline__ void q_store(int pos, uint32_t k, uint32_t list) {
+        if (DENSE) q[pos] = k | (list << 24);
+        else ((uint2*)q)[pos] = make_uint2(k, list);
+    }
+    __device__ __forceinline__ void q_load(int pos, uint32_t& k, uint32_t& list) const {
+        if (DENSE) { const uint32_t v = q[pos]; k = v & 0xffffffu; list = v >> 24; }
+        else { const uint2 v = ((const uint2*)q)[pos]; k = v.x; list = v.y; }
+    }
     int* lcnt;               // per-list match counters
-    int vb, sb, db;
+    int va, vb, sb, db;
     bool ovf;
+    __device__ __forceinline__ void set_ovf(const EdgeCtx& o) { ovf = o.ovf; }
     __device__ __forceinline__ bool in_triangle(uint32_t kk) const {
-        if (TM == TRI_DENSE) return (tb[kk >> 5] >> (kk & 31u)) & 1u;
-        if (TM == TRI_SET) {
-            uint32_t h = (kk * 2654435761u) >> 16 & tb_mask;
-            while (true) {
-                const uint32_t v = tb[h];
-                if (v == kk) return true;
-                if (v == EMPTY) return false;
-                h = (h + 1) & tb_mask;
-            }
+        uint32_t h = ((kk * 2654435761u) >> tb_shift) & tb_mask;
+        while (true) {
+            const uint32_t v = tb_global ? __ldcg(tb + h) : tb[h];
+            if (v == kk) return true;
+            if (v == EMPTY) return false;
+            h = (h + 1) & tb_mask;
         }
-        return ((tb[(kk >> 5) & tb_mask] >> (kk & 31u)) & 1u) && find_sorted(colidx, sb, db, (int)kk) >= 0;
     }
     // k in N(m), m a pure neighbour of vb: is (m,k) an edge of the bipartite graph M_b – M_a?  hit() is the per-element
     // filter of the streaming loops (one shared-memory load); handle() runs on queued candidates, 32 per pass.
-    __device__ __forceinline__ bool hit(int k) const { return mem.maybe((uint32_t)k) && k != vb; }
+    __device__ __forceinline__ uint32_t word(int k) const { return mem.word((uint32_t)k); }
     __device__ __forceinline__ void handle(uint32_t kk, uint32_t list) {
-        if (mem.confirm(kk) && !in_triangle(kk)) {     // k in N(va) and not a common neighbour
+        if ((int)kk != vb && mem.confirm(kk) && !in_triangle(kk)) {     // k in N(va) \ {vb} and not a common neighbour
             if (!hash.add(kk)) ovf = true;
             atomicAdd(&lcnt[list], 1);
         }
     }
 };
-__device__ __forceinline__ void tri_set_insert(uint32_t* ts, uint32_t mask, uint32_t kk) {
-    uint32_t h = (kk * 2654435761u) >> 16 & mask;
+__device__ __forceinline__ void tri_set_insert(uint32_t* ts, uint32_t mask, int shift, uint32_t kk) {
+    uint32_t h = ((kk * 2654435761u) >> shift) & mask;
     while (true) {
         const uint32_t v = atomicCAS(&ts[h], EMPTY, kk);
         if (v == EMPTY || v == kk) return;
@@ -898,67 +914,95 @@ __device__ __forceinline__ int pick(const int (&v)[N], int u) {
     return r;
 }
 
-// Append this window's candidates (bit u of hm: element k[u] of this lane passed the filter) to the warp's queue.
-// One pass per candidate of the busiest lane; all lanes take part in every ballot.
+// Append this window's candidates (bit u of hm: element k[u] of this lane passed the filter) to the warp's queue: one
+// ballot per element row, lanes that hold a candidate of the row store it behind the candidates of the lower lanes.
 template <class Ctx, int N>
 __device__ __forceinline__ void q_push(Ctx& cx, uint32_t hm, const int (&k)[N], const int (&own)[N], int lane) {
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t b = __ballot_sync(FULL, hm != 0u);
-    while (b) {
-        if (hm) {
-            const int u = __ffs(hm) - 1;
-            hm &= hm - 1;
-            cx.q[cx.qn + __popc(b & lt)] = make_uint2((uint32_t)pick(k, u), (uint32_t)pick(own, u));
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const bool mine = (hm >> u) & 1u;
+        const uint32_t b = __ballot_sync(FULL, mine);
+        if (b) {
+            if (mine) cx.q_store(cx.qn + __popc(b & lt), (uint32_t)k[u], (uint32_t)own[u]);
+            cx.qn += __popc(b);
         }
-        cx.qn += __popc(b);
-        b = __ballot_sync(FULL, hm != 0u);
     }
 }
 template <class Ctx>
 __device__ __forceinline__ void q_flush(Ctx& cx, int lane) {
     __syncwarp();
     for (int q = lane; q < cx.qn; q += 32) {
-        const uint2 e = cx.q[q];
-        cx.handle(e.x, e.y);
+        uint32_t k, list;
+        cx.q_load(q, k, list);
+        cx.handle(k, list);
     }
     cx.qn = 0;
     __syncwarp();
 }
 
+// The filter of one window: bit u of the result says that element k[u] of this lane may be a match.  The filter word of
+// element u is rotated so that the element's bit lands on bit u (one funnel shift) and merged with one and-or; with
+// VB_TEST the streamed endpoint itself — it sits in every streamed list and in N(va) — is dropped here, otherwise
+// handle() drops it.
+template <bool VB_TEST, class Ctx, int N>
+__device__ __forceinline__ uint32_t filter_window(const Ctx& cx, const int (&k)[N]) {
+    uint32_t w[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) w[u] = cx.word(k[u]);
+    uint32_t hm = 0;
+#pragma unroll
+    for (int u = 0; u < N; ++u) hm |= __funnelshift_r(w[u], w[u], (uint32_t)k[u] - (uint32_t)u) & (1u << u);
+    if (VB_TEST) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) if (k[u] == cx.vb) hm &= ~(1u << u);
+    }
+    return hm;
+}
+
 // `len` consecutive entries of ONE neighbour list, streamed by the whole warp (p already includes the lane offset);
 // candidates go to the queue with `owner` as their list.  Full windows carry no bounds test at all; lanes past the
-// end of the last window test vb, which never passes the filter.
-template <class Ctx>
-__device__ __forceinline__ void stream_list(Ctx& cx, const int32_t* __restrict__ p, int len, int owner, int lane) {
+// end of the last window test va, which is never a member of N(va).
+template <bool VB_TEST, class Ctx>
+__device__ __forceinline__ void stream_list_t(Ctx& cx, const int32_t* __restrict__ p, int len, int owner, int pad, int lane) {
     int own[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) own[u] = owner;
-    const int32_t* __restrict__ const p_full = p + (len & ~(32 * UNROLL - 1));
-    for (; p < p_full; p += 32 * UNROLL) {                  // all loads of a window are in flight before the first test
+    const int full = len & ~(32 * UNROLL - 1);
+    for (int F = 0; F < full; F += 32 * UNROLL) {           // all loads of a window are in flight before the first test
         int k[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) k[u] = __ldg(p + 32 * u);
-        uint32_t hm = 0;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        for (int u = 0; u < UNROLL; ++u) k[u] = __ldg(p + F + 32 * u);
+        const uint32_t hm = filter_window<VB_TEST>(cx, k);
         if (__any_sync(FULL, hm != 0u)) {
             q_push(cx, hm, k, own, lane);
             if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
         }
     }
-    const int rem = len & (32 * UNROLL - 1);
+    const int rem = len - full;
     if (rem) {
         int k[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) k[u] = (32 * u + lane < rem) ? __ldg(p + 32 * u) : cx.vb;
-        uint32_t hm = 0;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+        for (int u = 0; u < UNROLL; ++u) k[u] = (32 * u + lane < rem) ? __ldg(p + full + 32 * u) : pad;
+        const uint32_t hm = filter_window<VB_TEST>(cx, k);
         if (__any_sync(FULL, hm != 0u)) {
             q_push(cx, hm, k, own, lane);
             if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
         }
     }
+}
+template <class Ctx>
+__device__ __forceinline__ void stream_list(Ctx& cx, const int32_t* __restrict__ p, int len, int owner, int lane) {
+    stream_list_t<true>(cx, p, len, owner, cx.va, lane);
+}
+// (out-of-line copies work on a register copy of the context: through the reference every store to shared memory
+//  would force the context's fields to be re-read from the caller's stack frame)
+template <class Ctx>
+__device__ __noinline__ void stream_list_call(Ctx& cx_ref, const int32_t* __restrict__ p, int len, int owner, int lane) {
+    Ctx cx = cx_ref;
+    stream_list_t<true>(cx, p, len, owner, cx.va, lane);
+    cx_ref.qn = cx.qn;
+    cx_ref.set_ovf(cx);
 }
 
 // One chunk of 32 heads of N(vb) by one warp; lane l holds head l of the chunk: (mb, md) = (begin, length) of its
@@ -969,7 +1013,7 @@ __device__ __forceinline__ void stream_list(Ctx& cx, const int32_t* __restrict__
 // go through the queue; the chunk ends with the queue drained and the per-list counters folded into the lane-partial
 // sq_b (#lists with a match) and g_b (largest per-list count).
 template <class Ctx>
-__device__ __forceinline__ void warp_chunk(Ctx& cx, int mb, int md, int* st, int lane, int& sq_b, int& g_b) {
+__device__ __forceinline__ void warp_chunk_impl(Ctx& cx, int mb, int md, int* st, int lane, int& sq_b, int& g_b) {
     const int32_t* __restrict__ colidx = cx.colidx;
     const uint32_t lm0 = __ballot_sync(FULL, md >= LONG_LIST);
     const bool shortl = md > 1 && md < LONG_LIST;               // (a list that holds only vb cannot match)
@@ -1021,11 +1065,9 @@ __device__ __forceinline__ void warp_chunk(Ctx& cx, int mb, int md, int* st, int
                 below += __popc(starts);
                 const int bs = __shfl_sync(FULL, base_l, own[u]);
                 const int f = Fu + lane;
-                k[u] = f < total ? __ldg(colidx + bs + f) : cx.vb;
+                k[u] = f < total ? __ldg(colidx + bs + f) : cx.va;
             }
-            uint32_t hm = 0;
-#pragma unroll
-            for (int u = 0; u < FU; ++u) hm |= cx.hit(k[u]) ? (1u << u) : 0u;
+            const uint32_t hm = filter_window<true>(cx, k);
             if (__any_sync(FULL, hm != 0u)) {
                 q_push(cx, hm, k, own, lane);
                 if (cx.qn >= Q_FLUSH) q_flush(cx, lane);
@@ -1039,19 +1081,37 @@ __device__ __forceinline__ void warp_chunk(Ctx& cx, int mb, int md, int* st, int
     __syncwarp();
 }
 
+// the d_a <= 128 kernel inlines the chunk; the group kernels — several callers, much more code around — share ONE copy
+template <class Ctx>
+__device__ __forceinline__ void warp_chunk(Ctx& cx, int mb, int md, int* st, int lane, int& sq_b, int& g_b) {
+    warp_chunk_impl(cx, mb, md, st, lane, sq_b, g_b);
+}
+template <class Ctx>
+__device__ __noinline__ void warp_chunk_call(Ctx& cx_ref, int mb, int md, int* st, int lane, int& sq_b_ref, int& g_b_ref) {
+    Ctx cx = cx_ref;
+    int sq_b = sq_b_ref, g_b = g_b_ref;
+    warp_chunk_impl(cx, mb, md, st, lane, sq_b, g_b);
+    sq_b_ref = sq_b;
+    g_b_ref = g_b;
+    cx_ref.qn = cx.qn;
+    cx_ref.set_ovf(cx);
+}
+
 // One edge by one warp over the CTA-level membership structure (group kernels).  `st` = the warp's scratch, `tb` =
 // its exact triangle set (TSLOTS words), `mh` = its match hash (2*CAP words, all zero on entry and on exit), `q` = its
 // candidate queue.  Writes the four integer fields of local edge t and returns true, or returns false when the match
 // hash filled up or the edge has too many triangles for the warp's set (nothing written; the hash is clean again).
 template <int CAP, int TSLOTS, bool DENSE, bool CAN_DEFER>
 __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st,
-                                          uint32_t* tb, uint32_t* mh, uint2* q, int lane) {
+                                          uint32_t* tb, uint32_t* mh, uint32_t* q, int lane) {
     const int64_t e = a.e_first + (int64_t)t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const bool swapped = (va == j);                      // stream i's side, test j
     EdgeCtx<DENSE, TRI_SET> cx;
-    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.tb_mask = TSLOTS - 1; cx.hash.init(mh, st + WS_NDIST, CAP);
+    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb; cx.tb_mask = TSLOTS - 1; cx.tb_shift = 32 - ilog2_c(TSLOTS);
+    cx.tb_global = false; cx.hash.init(mh, st + WS_NDIST, CAP);
     cx.q = q; cx.qn = 0; cx.lcnt = st + WS_LCNT;
+    cx.va = va;
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
@@ -1075,7 +1135,7 @@ __device__ __forceinline__ bool warp_edge(const PaperArgs& a, const Member<DENSE
         for (int p = lane, c = 0; p < cx.db; p += 32, ++c) {
             if (c < 32 && !((mbits >> c) & 1u)) continue;
             const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-            if (c < 32 || ((int)m != va && mem.has(m))) tri_set_insert(tb, TSLOTS - 1, m);
+            if (c < 32 || ((int)m != va && mem.has(m))) tri_set_insert(tb, TSLOTS - 1, 32 - ilog2_c(TSLOTS), m);
         }
     } else if (lane == 0) {
         tb[0] = EMPTY;                                   // an empty set is recognised by its first probe ...
@@ -1130,11 +1190,24 @@ struct L0Ctx {
     uint32_t* cnt;
     uint32_t mask;
     int shift;
-    uint2* q;
+    uint32_t* q;
     int qn;
     int* lcnt;
-    int vb, sb, db;
-    __device__ __forceinline__ bool hit(int k) const { return bitmap_test(bm, L0_BITS - 1, (uint32_t)k) && k != vb; }
+    int va, vb, sb, db;
+    static constexpr int Q_ENTRY_WORDS = 2;
+    __device__ __forceinline__ void set_ovf(const L0Ctx&) {}
+    __device__ __forceinline__ void q_store(int pos, uint32_t k, uint32_t list) { ((uint2*)q)[pos] = make_uint2(k, list); }
+    __device__ __forceinline__ void q_load(int pos, uint32_t& k, uint32_t& list) const {
+        const uint2 v = ((const uint2*)q)[pos];
+        k = v.x; list = v.y;
+    }
+    uint32_t bm_off;          // byte offset of this warp's filter inside the CTA's filter block (a multiple of its size)
+    // one shift, one and-or, one load at a constant shared-memory base: the filters of the CTA's warps are contiguous
+    // at the start of dynamic shared memory and each is a power of two long
+    __device__ __forceinline__ uint32_t word(int k) const {
+        extern __shared__ uint32_t smem_dyn[];
+        return *(const uint32_t*)((const char*)smem_dyn + ((((uint32_t)k >> 3) & (L0_BITS / 8 - 4)) | bm_off));
+    }
     __device__ __forceinline__ void handle(uint32_t kk, uint32_t list) {
         const int h = ro_probe(tab, mask, shift, kk);
         if (h >= 0 && !(*(volatile uint32_t*)(cnt + h) & L0_TRI)) {
@@ -1152,6 +1225,9 @@ __device__ __forceinline__ void warp_edge_l0(const PaperArgs& a, L0Ctx& cx, uint
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
     cx.qn = 0;
+    cx.va = va;
+    // vb is in N(va) and in every streamed list, and never a match: its slot carries the mark of the common neighbours
+    if (lane == 0) cx.cnt[ro_probe(cx.tab, cx.mask, cx.shift, (uint32_t)cx.vb)] = L0_TRI;
     // pass 1 over the heads: common neighbours get their slot marked
     int tri = 0;
     uint32_t mbits = 0;
@@ -1186,7 +1262,7 @@ __device__ __forceinline__ void warp_edge_l0(const PaperArgs& a, L0Ctx& cx, uint
     g_b = __reduce_max_sync(FULL, g_b);
     // the collect: one sweep over the slot counters reads the matches of va's side and leaves them all zero
     int sq_a = 0, g_a = 0;
-    if (sq_b > 0 || tri > 0) {
+    {
         for (uint32_t s = lane; s <= cx.mask; s += 32) {
             const uint32_t c = cx.cnt[s];
             if (c) {
@@ -1207,14 +1283,15 @@ __device__ __forceinline__ void warp_edge_l0(const PaperArgs& a, L0Ctx& cx, uint
 }
 
 // L0 kernel: warp-private table, kept while consecutive edges (sorted by tested endpoint) share va.
-constexpr int L0_PER_WARP = WSTATE_INTS + Q_WORDS + L0_BITS / 32 + 2 * L0_SLOTS;
+constexpr int L0_PER_WARP = WSTATE_INTS + Q_WORDS + 2 * L0_SLOTS;      // beside the filter
 __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_warp_kernel(PaperArgs a) {
     extern __shared__ uint32_t smem_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* base = smem_dyn + warp * L0_PER_WARP;
+    // [filters of the 8 warps, contiguous][per warp: scratch | queue | table | slot counters]
+    uint32_t* bm = smem_dyn + warp * (L0_BITS / 32);
+    uint32_t* base = smem_dyn + L0_WARPS * (L0_BITS / 32) + warp * L0_PER_WARP;
     int* st = (int*)base;
-    uint32_t* bm = base + WSTATE_INTS + Q_WORDS;
-    uint32_t* tab = bm + L0_BITS / 32;
+    uint32_t* tab = base + WSTATE_INTS + Q_WORDS;
     uint32_t* cnt = tab + L0_SLOTS;
     for (int p = lane; p < L0_SLOTS; p += 32) cnt[p] = 0u;
     __syncwarp();
@@ -1223,7 +1300,8 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
     int cur_va = -1;
     L0Ctx cx;
     cx.colidx = a.colidx; cx.tab = tab; cx.bm = bm; cx.cnt = cnt; cx.mask = 0; cx.shift = 0;
-    cx.q = (uint2*)(base + WSTATE_INTS); cx.qn = 0; cx.lcnt = st + WS_LCNT;
+    cx.q = base + WSTATE_INTS; cx.qn = 0; cx.lcnt = st + WS_LCNT;
+    cx.bm_off = (uint32_t)warp * (L0_BITS / 8);
     while (true) {
         unsigned int idx0 = 0;
         if (lane == 0) idx0 = atomicAdd(ws.next, (unsigned)DCR_L0_GRAB);
@@ -1252,119 +1330,123 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
 }
 
 
-// One COOPERATIVE edge by the whole CTA (stream too long, or too many distinct matches, for one warp).  Rounds of
-// THREADS heads: every thread resolves one head, a CTA-wide prefix sum compacts the lists of the pure heads and lays
-// them out as one flat stream, and the warps pull slices of COOP_SLICE flat elements from a shared counter — a hub's
-// list next to twenty short ones does not serialise, and a slice that is dense in matches does not hold the others
-// up.  A warp walks the list segments inside its slice with the search-free segment loop.  The per-warp triangle
-// bitmaps and match hashes, contiguous in shared memory, act as ONE bitmap / ONE hash of NWARPS times the size; the
-// per-warp scratch blocks together hold pre[THREADS+1] | beg[THREADS] | lcnt[THREADS].
-// s_acc: [0] tri [1] sq_b [2] g_b [3] next slice [4] n_distinct [5] overflow [6] sq_a [7] g_a [11] #lists.  All
-// threads call it; the caller synchronises the CTA before the next use of s_acc.  An edge that overflows even the
-// CTA-wide hash goes to the global overflow list.
+// One COOPERATIVE edge by the whole CTA (stream too long, too many triangles or too many distinct matches for one
+// warp).  No rounds and no CTA-wide prefix sums: the warps pull CHUNKS of 32 heads from a shared counter and process
+// each exactly like the warp path does (warp_chunk: long lists one at a time, short lists as one flat stream,
+// candidates through the warp's queue) — the only CTA barriers are the ones around the triangle set at the start and
+// the reductions at the end.  What is shared by the CTA: the exact set of T (shared memory up to TSET_WORDS slots,
+// beyond that this CTA's region of `gtri` in global memory), the match hash (the per-warp hashes taken together, or a
+// hash in global memory) and the BIG lists: a list of at least BIG_LIST entries (hub neighbours) would hold one warp
+// long after the others ran out of chunks, so it is parked in s_big and, once the chunks are done, streamed by all
+// warps in slices of BIG_SLICE entries.
+// s_acc: [0] tri (this part) [1] sq_b [2] g_b [3] next chunk [4] n_distinct [5] overflow [6] sq_a [7] g_a [8] "this
+// part finalises its split edge" [9] |T| [10] #big lists.  All threads call it; the caller synchronises the CTA before
+// the next use of s_acc.
+constexpr int TSET_WORDS = 1024, BIG_LIST = 2048, BIG_SLICE = 1024, MAX_BIG = 32;
 template <int NWARPS, bool DENSE>
 __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st_all,
-                                      uint32_t* tb_all, uint32_t* hash_words, uint32_t hash_cap, uint2* q_all, int* s_acc,
-                                      unsigned long long* s_wtot, int part, int parts, SplitEdge* se) {
-    constexpr int THREADS = NWARPS * 32, TBW = COOP_TB_WORDS, TM = DENSE ? TRI_DENSE : TRI_HASHED;
-    static_assert(3 * THREADS + 1 <= NWARPS * WSTATE_INTS, "cooperative stream state must fit the warp scratch");
+                                      uint32_t* tset_sh, uint32_t* hash_words, uint32_t hash_cap, uint32_t* q_all, int* s_acc,
+                                      int* s_big, int part, int parts, SplitEdge* se) {
+    constexpr int THREADS = NWARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int* pre = st_all;                    // [THREADS + 1]
-    int* beg = pre + THREADS + 1;         // [THREADS]
-    int* lcnt = beg + THREADS;            // [THREADS]
+    int* st = st_all + warp * WSTATE_INTS;
     const int64_t e = a.e_first + (int64_t)t * a.e_stride;
     const int i = a.esrc[e], j = a.edst[e];
     const bool swapped = (va == j);
-    EdgeCtx<DENSE, TM> cx;
-    cx.colidx = a.colidx; cx.mem = mem; cx.tb = tb_all; cx.tb_mask = TBW - 1;
+    EdgeCtx<DENSE, TRI_SET> cx;
+    cx.colidx = a.colidx; cx.mem = mem;
     cx.hash.init(hash_words, se ? &se->n_distinct : s_acc + 4, hash_cap);
-    cx.q = q_all + warp * Q_CAP; cx.qn = 0; cx.lcnt = lcnt;
+    cx.q = q_all + warp * (Q_CAP * cx.Q_ENTRY_WORDS); cx.qn = 0; cx.lcnt = st + WS_LCNT;
+    cx.va = va;
     cx.vb = swapped ? i : j;
     cx.sb = a.rowptr[cx.vb];
     cx.db = a.rowptr[cx.vb + 1] - cx.sb;
     cx.ovf = false;
-    // a part of a split edge takes the heads [h_lo, h_hi) (the triangle structure always covers all heads)
+    // a part of a split edge takes the heads [h_lo, h_hi) (the triangle set always covers all heads)
     const int h_lo = (int)((long long)cx.db * part / parts), h_hi = (int)((long long)cx.db * (part + 1) / parts);
-    if (TM == TRI_HASHED) for (int s = tid; s < TBW; s += THREADS) tb_all[s] = 0u;   // (the dense one is kept clean)
-    if (tid < 8) s_acc[tid] = 0;
+    if (tid < 12) s_acc[tid] = 0;
     __syncthreads();
-    int tri = 0;
+    // the common neighbours: count, then build the exact set sized for them
+    int tri = 0, tri_all = 0;
     for (int p = tid; p < cx.db; p += THREADS) {
         const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-        if ((int)m != va && mem.has(m)) {
-            tri += (p >= h_lo && p < h_hi);
-            atomicOr(&tb_all[TM == TRI_DENSE ? (m >> 5) : ((m >> 5) & (TBW - 1))], 1u << (m & 31u));
-        }
+        const bool in = ((int)m != va && mem.has(m));
+        tri_all += in;
+        tri += in && p >= h_lo && p < h_hi;
     }
     tri = __reduce_add_sync(FULL, tri);
-    if (lane == 0 && tri) atomicAdd(&s_acc[0], tri);
+    tri_all = __reduce_add_sync(FULL, tri_all);
+    if (lane == 0 && tri_all) { atomicAdd(&s_acc[0], tri); atomicAdd(&s_acc[9], tri_all); }
     __syncthreads();
+    const int n_t = s_acc[9];
+    if (n_t == 0) {
+        cx.tb = tset_sh; cx.tb_mask = 0; cx.tb_shift = 31; cx.tb_global = false;
+        if (tid == 0) tset_sh[0] = EMPTY;
+    } else {
+        const int lg = max(6, 32 - __clz(2 * n_t - 1));            // >= 2 |T| slots
+        const uint32_t slots = 1u << lg;
+        cx.tb_global = slots > (uint32_t)TSET_WORDS;
+        uint32_t* ts = cx.tb_global ? a.gtri + (size_t)blockIdx.x * a.ghash_cap : tset_sh;   // ghash_cap >= pow2(2 * max degree)
+        cx.tb = ts; cx.tb_mask = slots - 1; cx.tb_shift = 32 - lg;
+        for (uint32_t s = tid; s < slots; s += THREADS) ts[s] = EMPTY;
+        __syncthreads();
+        for (int p = tid; p < cx.db; p += THREADS) {
+            const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
+            if ((int)m != va && mem.has(m)) tri_set_insert(ts, cx.tb_mask, cx.tb_shift, m);
+        }
+    }
+    __syncthreads();
+    // the chunks of the part's heads
     int sq_b = 0, g_b = 0;
-    for (int h0 = h_lo; h0 < h_hi; h0 += THREADS) {
+    const int nchunks = (h_hi - h_lo + 31) >> 5;
+    while (true) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&s_acc[3], 1);
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= nchunks) break;
+        const int p = h_lo + 32 * c + lane;
         int mb = 0, md = 0;
-        if (h0 + tid < h_hi) {
-            const int m = a.colidx[cx.sb + h0 + tid];
+        if (p < h_hi) {
+            const int m = a.colidx[cx.sb + p];
             if (m != va && !mem.has((uint32_t)m)) {
                 mb = a.rowptr[m];
                 md = a.rowptr[m + 1] - mb;
-                if (md <= 1) md = 0;                  // a list that holds only vb cannot match
             }
         }
-        // CTA-wide exclusive scan of (1 if the list is non-empty, its length), packed in 64 bits: the non-empty
-        // lists are compacted (rank -> pre/beg), so the walk below never steps over empty entries
-        unsigned long long inc = ((unsigned long long)(md > 0) << 40) | (unsigned long long)md;
-        const unsigned long long mine = inc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long up = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += up;
-        }
-        if (lane == 31) s_wtot[warp] = inc;
-        if (tid == 0) s_acc[3] = 0;                   // slice counter of this round
-        __syncthreads();
-        unsigned long long off = inc - mine;
-        for (int w = 0; w < warp; ++w) off += s_wtot[w];
-        const int rank = (int)(off >> 40), fpos = (int)(off & 0xffffffffffull);
-        if (md > 0) { pre[rank] = fpos; beg[rank] = mb; }
-        lcnt[tid] = 0;
-        if (tid == THREADS - 1) {
-            const unsigned long long tot = off + mine;
-            pre[(int)(tot >> 40)] = (int)(tot & 0xffffffffffull);
-            s_acc[11] = (int)(tot >> 40);             // number of non-empty lists
-        }
-        __syncthreads();
-        const int nlists = s_acc[11];
-        const int total = pre[nlists];
-        if (total > 0) {
-            // at least ~4 slices per warp, so that a short round does not leave most warps waiting at its barrier
-            const int slice = max(128, min(COOP_SLICE, ((total / (NWARPS * 4)) + 127) & ~127));
-            while (true) {                             // slices of the flat stream, pulled from a shared counter
-                int sl = 0;
-                if (lane == 0) sl = atomicAdd(&s_acc[3], 1);
-                sl = __shfl_sync(FULL, sl, 0);
-                int f0 = sl * slice;
-                if (f0 >= total) break;
-                const int f1 = min(total, f0 + slice);
-                int lo = 0, hi = nlists - 1;           // last l with pre[l] <= f0 (warp-uniform search)
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (pre[mid] <= f0) lo = mid; else hi = mid - 1;
-                }
-                int l = lo;
-                while (f0 < f1) {
-                    const int seg_end = min(f1, pre[l + 1]);
-                    stream_list(cx, a.colidx + beg[l] + (f0 - pre[l]) + lane, seg_end - f0, l, lane);
-                    f0 = seg_end;
-                    ++l;
-                }
-                if (cx.qn) q_flush(cx, lane);
+        const uint32_t bigm = __ballot_sync(FULL, md >= BIG_LIST);
+        if (bigm) {                                   // park the big lists (those that find no room stay with this warp)
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&s_acc[10], __popc(bigm));
+            slot = __shfl_sync(FULL, slot, 0) + __popc(bigm & ((1u << lane) - 1u));
+            if (md >= BIG_LIST && slot < MAX_BIG) {
+                s_big[slot] = mb;
+                s_big[MAX_BIG + slot] = md;
+                s_big[2 * MAX_BIG + slot] = 0;
+                mb = 0;
+                md = 0;
             }
-            __syncthreads();
-            const int c = tid < nlists ? lcnt[tid] : 0;
+        }
+        warp_chunk_call(cx, mb, md, st, lane, sq_b, g_b);
+    }
+    __syncthreads();
+    const int nbig = min(s_acc[10], MAX_BIG);
+    if (nbig) {
+        cx.lcnt = s_big + 2 * MAX_BIG;
+        int before = 0;                               // slices of the earlier lists: slice q of the edge goes to warp q mod NWARPS
+        for (int b = 0; b < nbig; ++b) {
+            const int beg = s_big[b], len = s_big[MAX_BIG + b];
+            const int ns = (len + BIG_SLICE - 1) / BIG_SLICE;
+            for (int s = ((warp - before) % NWARPS + NWARPS) % NWARPS; s < ns; s += NWARPS)
+                stream_list_call(cx, a.colidx + beg + s * BIG_SLICE + lane, min(BIG_SLICE, len - s * BIG_SLICE), b, lane);
+            before += ns;
+        }
+        if (cx.qn) q_flush(cx, lane);
+        __syncthreads();
+        if (tid < nbig) {
+            const int c = s_big[2 * MAX_BIG + tid];
             sq_b += c > 0;
             g_b = max(g_b, c);
         }
-        __syncthreads();
     }
     sq_b = __reduce_add_sync(FULL, sq_b);
     g_b = __reduce_max_sync(FULL, g_b);
@@ -1374,7 +1456,7 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
         if (ovf) s_acc[5] = 1;
     }
     __syncthreads();
-    int tri_all = s_acc[0], sq_b_all = s_acc[1], g_b_all = s_acc[2];
+    int tri_out = s_acc[0], sq_b_all = s_acc[1], g_b_all = s_acc[2];
     bool finalise = true;
     if (se) {     // publish this part; the part that finishes last collects the shared hash and writes the result
         if (tid == 0) {
@@ -1392,7 +1474,7 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
             __threadfence();
             if (tid == 0) s_acc[5] = *(volatile int*)&se->overflow;   // the caller redoes the edge on its own
             __syncthreads();
-            tri_all = *(volatile int*)&se->tri;
+            tri_out = *(volatile int*)&se->tri;
             sq_b_all = *(volatile int*)&se->sq_b;
             g_b_all = *(volatile int*)&se->g_b;
         }
@@ -1407,33 +1489,28 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
     }
     if (finalise && tid == 0 && !s_acc[5]) {
         const int sa_ = s_acc[6];
-        a.out_tri[t] = tri_all;
+        a.out_tri[t] = tri_out;
         a.out_sq_i[t] = swapped ? sq_b_all : sa_;
         a.out_sq_j[t] = swapped ? sa_ : sq_b_all;
         a.out_gamma[t] = (sq_b_all > 0 && sa_ > 0) ? max(g_b_all, s_acc[7]) : 0;
     }
-    if (TM == TRI_DENSE) {                               // un-set the triangle bits: the bitmap stays all zero between edges
-        for (int p = tid; p < cx.db; p += THREADS) {
-            const uint32_t m = (uint32_t)a.colidx[cx.sb + p];
-            if ((int)m != va && mem.has(m)) atomicAnd(&tb_all[m >> 5], ~(1u << (m & 31u)));
-        }
-    }
 }
+
 
 // cooperative edge with the CTA-wide shared hash; on overflow once more with this CTA's hash in global memory
 // (2*ghash_cap words, ghash_cap >= 2 * max degree: it cannot fill up).  Ends with the CTA synchronised.
 template <int NWARPS, int CAP, bool DENSE>
 __device__ __forceinline__ void cta_edge_retry(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va,
-                                               int* st_all, uint32_t* tb_all, uint32_t* mh_all, uint2* q_all, int* s_acc,
-                                               unsigned long long* s_wtot) {
-    cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, mh_all, NWARPS * CAP, q_all, s_acc, s_wtot, 0, 1, nullptr);
+                                               int* st_all, uint32_t* tset_sh, uint32_t* mh_all, uint32_t* q_all, int* s_acc,
+                                               int* s_big) {
+    cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tset_sh, mh_all, NWARPS * CAP, q_all, s_acc, s_big, 0, 1, nullptr);
     __syncthreads();
     if (s_acc[5]) {
         uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
         for (uint32_t p = threadIdx.x; p < 2 * a.ghash_cap; p += NWARPS * 32) gh[p] = 0u;
         __threadfence_block();
         __syncthreads();
-        cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_all, gh, a.ghash_cap, q_all, s_acc, s_wtot, 0, 1, nullptr);
+        cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tset_sh, gh, a.ghash_cap, q_all, s_acc, s_big, 0, 1, nullptr);
         __syncthreads();
     }
 }
@@ -1451,6 +1528,46 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TRACE(...)
 #endif
 
+// (Re)build the membership structures of N(va) for the CTA; all threads; ends synchronised.  One out-of-line copy (three
+// call sites in the group kernel).
+template <int NWARPS, int MAX_SLOTS, bool DENSE>
+__device__ __noinline__ void build_member(const PaperArgs& a, Member<DENSE>& mem, uint32_t* tab, uint32_t* bm, int bm_words,
+                                          int& prev_va, int va) {
+    constexpr int THREADS = NWARPS * 32;
+    const int tid = threadIdx.x;
+    if (prev_va == va) return;
+    const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
+    if (DENSE) {
+        if (prev_va >= 0) {                        // un-set the previous endpoint's bits (no full clear)
+            const int ps = a.rowptr[prev_va], pd = a.rowptr[prev_va + 1] - ps;
+#pragma unroll 1
+            for (int p = tid; p < pd; p += THREADS) {
+                const uint32_t k = (uint32_t)a.colidx[ps + p];
+                atomicAnd(&bm[k >> 5], ~(1u << (k & 31u)));
+            }
+        }
+    } else {
+        ro_geometry<MAX_SLOTS, 2>(da, mem.mask, mem.shift);
+#pragma unroll 1
+        for (uint32_t s = tid; s <= mem.mask; s += THREADS) tab[s] = EMPTY;
+#pragma unroll 1
+        for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int p = tid; p < da; p += THREADS) {
+        const uint32_t k = (uint32_t)a.colidx[sa + p];
+        if (DENSE) {
+            atomicOr(&bm[k >> 5], 1u << (k & 31u));
+        } else {
+            ro_insert(tab, mem.mask, mem.shift, k);
+            atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
+        }
+    }
+    prev_va = va;
+    __syncthreads();
+}
+
 // Group kernel: the CTA builds the membership structures of N(va) for a run of edges with the same tested endpoint.
 // The cooperative edges of the run (they come first) are processed by the whole CTA one at a time; then the warps
 // pull the remaining edges — ordered by size, heaviest first — from a shared counter, one warp per edge; edges whose
@@ -1463,18 +1580,19 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     __shared__ int s_ndefer;
     __shared__ uint32_t s_defer[RUN_EDGES];
     __shared__ int s_acc[12];      // [8]: "this part finalises its split edge"
-    __shared__ unsigned long long s_wtot[NWARPS];
+    __shared__ int s_big[3 * MAX_BIG];
     constexpr int THREADS = NWARPS * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // [CTA-path triangle structure: COOP_TB_WORDS | dense_words][per-warp triangle sets: NWARPS x TB_WORDS][match hashes: NWARPS x
+    // [CTA-path triangle set: TSET_WORDS][per-warp triangle sets: NWARPS x TB_WORDS][match hashes: NWARPS x
     // 2*CAP][warp scratch: NWARPS x WSTATE_INTS][table (hashed only)][bitmap: hashed BITS/32 words | dense dense_words]
-    uint32_t* tb_coop = smem_dyn;                          // dense: exact triangle bitmap, dense_words words, kept all zero
-    const int tb_coop_words = DENSE ? dense_words : COOP_TB_WORDS;
+    uint32_t* tb_coop = smem_dyn;                          // the CTA path's exact set of T (TSET_WORDS slots)
+    constexpr int tb_coop_words = TSET_WORDS;
     uint32_t* tb_all = tb_coop + tb_coop_words;
     uint32_t* mh_all = tb_all + NWARPS * TB_WORDS;
     int* st_all = (int*)(mh_all + NWARPS * 2 * CAP);
-    uint2* q_all = (uint2*)(st_all + NWARPS * WSTATE_INTS);          // per-warp candidate queues (8-byte aligned: all sizes even)
-    uint32_t* tab = (uint32_t*)(q_all + NWARPS * Q_CAP);
+    constexpr int QW = Q_CAP * (DENSE ? 1 : 2);                      // words per warp queue
+    uint32_t* q_all = (uint32_t*)(st_all + NWARPS * WSTATE_INTS);    // per-warp candidate queues (8-byte aligned: all sizes even)
+    uint32_t* tab = q_all + NWARPS * QW;
     uint32_t* bm = tab + (DENSE ? 0 : MAX_SLOTS);
     const int bm_words = DENSE ? dense_words : BITS / 32;
     int* st = st_all + warp * WSTATE_INTS;
@@ -1486,7 +1604,6 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     if (lane == 0) st[WS_NDIST] = 0;
     if (DENSE) {
         for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
-        for (int s = tid; s < tb_coop_words; s += THREADS) tb_coop[s] = 0u;
     }
     const uint2* runs = a.runs + (size_t)run_table_of(cls) * a.max_runs;
     const unsigned int n_runs = a.plan->n_runs[run_table_of(cls)];
@@ -1496,36 +1613,7 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
     Member<DENSE> mem;
     mem.tab = tab; mem.bm = bm; mem.bmask = BITS - 1; mem.mask = 0; mem.shift = 0;
     int prev_va = -1;
-    // (re)build the membership structures of N(va); all threads; ends synchronised
-    auto build = [&](int va) {
-        if (prev_va == va) return;
-        const int sa = a.rowptr[va], da = a.rowptr[va + 1] - sa;
-        if (DENSE) {
-            if (prev_va >= 0) {                        // un-set the previous endpoint's bits (no full clear)
-                const int ps = a.rowptr[prev_va], pd = a.rowptr[prev_va + 1] - ps;
-                for (int p = tid; p < pd; p += THREADS) {
-                    const uint32_t k = (uint32_t)a.colidx[ps + p];
-                    atomicAnd(&bm[k >> 5], ~(1u << (k & 31u)));
-                }
-            }
-        } else {
-            ro_geometry<MAX_SLOTS, 2>(da, mem.mask, mem.shift);
-            for (uint32_t s = tid; s <= mem.mask; s += THREADS) tab[s] = EMPTY;
-            for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
-        }
-        __syncthreads();
-        for (int p = tid; p < da; p += THREADS) {
-            const uint32_t k = (uint32_t)a.colidx[sa + p];
-            if (DENSE) {
-                atomicOr(&bm[k >> 5], 1u << (k & 31u));
-            } else {
-                ro_insert(tab, mem.mask, mem.shift, k);
-                atomicOr(&bm[(k & mem.bmask) >> 5], 1u << (k & 31u));
-            }
-        }
-        prev_va = va;
-        __syncthreads();
-    };
+    auto build = [&](int va) { build_member<NWARPS, MAX_SLOTS, DENSE>(a, mem, tab, bm, bm_words, prev_va, va); };
     TRACE(unsigned long long tr_t0 = gtimer(), tr_long = 0, tr_id = 0, tr_n = 0;)
     // phase 0: the parts of the split edges — by far the longest streams of the pass
     {
@@ -1547,14 +1635,14 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
             const int va = edge_role(a, i, j, a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j]).va;
             build(va);
             cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, a.shash + (size_t)k * SHASH_WORDS + se->hash_off,
-                                    se->hash_cap, q_all, s_acc, s_wtot, part, se->parts, se);
+                                    se->hash_cap, q_all, s_acc, s_big, part, se->parts, se);
             __syncthreads();
             if (s_acc[8] && s_acc[5]) {                  // its hash filled up: once more, whole, with this CTA's big hash
                 uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
                 for (uint32_t p = tid; p < 2 * a.ghash_cap; p += THREADS) gh[p] = 0u;
                 __threadfence_block();
                 __syncthreads();
-                cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, gh, a.ghash_cap, q_all, s_acc, s_wtot, 0, 1, nullptr);
+                cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tb_coop, gh, a.ghash_cap, q_all, s_acc, s_big, 0, 1, nullptr);
             }
             TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (3ull << 30) | t; })
         }
@@ -1569,7 +1657,7 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
         TRACE(const unsigned long long tr_a = gtimer();)
         const int va = (int)cova[idx];
         build(va);
-        cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, cws.order[idx], va, st_all, tb_coop, mh_all, q_all, s_acc, s_wtot);
+        cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, cws.order[idx], va, st_all, tb_coop, mh_all, q_all, s_acc, s_big);
         TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (1ull << 30) | cws.order[idx]; })
     }
     TRACE(const unsigned long long tr_t1 = gtimer();)
@@ -1592,13 +1680,13 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
             my = __shfl_sync(FULL, my, 0);
             if ((int)my >= q_end) break;
             const uint32_t t = ord[my];
-            if (!warp_edge<CAP, TB_WORDS, DENSE, true>(a, mem, t, va, st, tb, mh, q_all + warp * Q_CAP, lane) && lane == 0)
+            if (!warp_edge<CAP, TB_WORDS, DENSE, true>(a, mem, t, va, st, tb, mh, q_all + warp * QW, lane) && lane == 0)
                 s_defer[atomicAdd(&s_ndefer, 1)] = t;     // too many triangles / distinct matches for one warp: CTA path
         }
         __syncthreads();                                  // every warp is done with the run
         const int nd = s_ndefer;
         for (int d = 0; d < nd; ++d)
-            cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, q_all, s_acc, s_wtot);
+            cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, q_all, s_acc, s_big);
         if (nd > 0 && lane == 0) st[WS_NDIST] = 0;
         TRACE(const unsigned long long tr_d = gtimer() - tr_a; ++tr_n; if (tr_d > tr_long) { tr_long = tr_d; tr_id = (2ull << 30) | ((unsigned long long)nd << 20) | s_idx; })
     }
@@ -1638,7 +1726,7 @@ static bool use_dense_mode(int n) {
 }
 
 struct ScratchLayout {
-    size_t plan, node_s, bucket, order, ova, va_cnt, va_cur, grp, runs, gtables, ghash, shash, split_item, total;
+    size_t plan, node_s, bucket, order, ova, va_cnt, va_cur, grp, runs, gtables, ghash, gtri, shash, split_item, total;
     uint32_t max_runs;
     uint32_t gslots, ghash_cap;
     int g_ctas, group_ctas;
@@ -1654,7 +1742,7 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.ova = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
     L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
-    L.grp = off; off = align_up(off + (size_t)4 * n * sizeof(uint32_t), 256);
+    L.grp = off; off = align_up(off + (size_t)5 * n * sizeof(uint32_t), 256);
     // a light group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(n, count) light groups
     L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>((int64_t)n, count) + 1);
     L.runs = off; off = align_up(off + (size_t)2 * L.max_runs * sizeof(uint2), 256);
@@ -1671,6 +1759,7 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.ghash_cap = std::max<uint32_t>(4096u, next_pow2_u32((uint64_t)max_degree * 2));
     L.group_ctas = sm_count() * std::max(GD_CTAS_PER_SM, G1_CTAS_PER_SM);
     L.ghash = off; off = align_up(off + (size_t)L.group_ctas * 2 * L.ghash_cap * sizeof(uint32_t), 256);
+    L.gtri = off; off = align_up(off + (size_t)L.group_ctas * L.ghash_cap * sizeof(uint32_t), 256);
     L.shash = off; off = align_up(off + (size_t)2 * SHASH_WORDS * sizeof(uint32_t), 256);
     L.split_item = off; off = align_up(off + (size_t)2 * MAX_SPLIT * MAX_PARTS * sizeof(uint32_t), 256);
     L.total = off;
@@ -1721,6 +1810,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.gslots = L.gslots;
     a.ghash = (uint32_t*)(base + L.ghash);
     a.ghash_cap = L.ghash_cap;
+    a.gtri = (uint32_t*)(base + L.gtri);
     a.shash = (uint32_t*)(base + L.shash);
     a.split_item = (uint32_t*)(base + L.split_item);
 
@@ -1754,10 +1844,11 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     const int dense_words = (n + 63) / 64 * 2;       // even: what follows the bitmaps in shared memory is 8-byte aligned
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
     constexpr int WARP_WORDS = TB_WORDS + WSTATE_INTS + Q_WORDS;     // per warp of a group kernel, beside its match hash
-    const int smem_l0 = L0_WARPS * L0_PER_WARP * (int)sizeof(uint32_t);
-    const int smem_g1 = (COOP_TB_WORDS + G1_SLOTS + G1_BITS / 32 + G1_WARPS * (2 * G1_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
-    const int smem_g2 = (COOP_TB_WORDS + G2_SLOTS + G2_BITS / 32 + G2_WARPS * (2 * G2_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
-    const int smem_gd = (2 * dense_words + GD_WARPS * (2 * GD_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+    constexpr int WARP_WORDS_D = TB_WORDS + WSTATE_INTS + Q_CAP;     // dense mode: one-word queue entries
+    const int smem_l0 = L0_WARPS * (L0_BITS / 32 + L0_PER_WARP) * (int)sizeof(uint32_t);
+    const int smem_g1 = (TSET_WORDS + G1_SLOTS + G1_BITS / 32 + G1_WARPS * (2 * G1_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+    const int smem_g2 = (TSET_WORDS + G2_SLOTS + G2_BITS / 32 + G2_WARPS * (2 * G2_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+    const int smem_gd = (TSET_WORDS + dense_words + GD_WARPS * (2 * GD_CAP + WARP_WORDS_D)) * (int)sizeof(uint32_t);
     auto* k_g1 = paper_group_kernel<G1_WARPS, G1_SLOTS, G1_BITS, G1_CAP, G1_CTAS_PER_SM, false>;
     auto* k_g2 = paper_group_kernel<G2_WARPS, G2_SLOTS, G2_BITS, G2_CAP, 1, false>;
     auto* k_gd = paper_group_kernel<GD_WARPS, 64, 32, GD_CAP, GD_CTAS_PER_SM, true>;
@@ -1767,7 +1858,7 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_CUDA(cudaFuncSetAttribute(paper_light_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l0));
         DCR_CUDA(cudaFuncSetAttribute(k_g1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g1));
         DCR_CUDA(cudaFuncSetAttribute(k_g2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g2));
-        const int smem_gd_max = (2 * (DENSE_MAX_N / 32) + GD_WARPS * (2 * GD_CAP + WARP_WORDS)) * (int)sizeof(uint32_t);
+        const int smem_gd_max = (TSET_WORDS + DENSE_MAX_N / 32 + GD_WARPS * (2 * GD_CAP + WARP_WORDS_D)) * (int)sizeof(uint32_t);
         DCR_CUDA(cudaFuncSetAttribute(k_gd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gd_max));
         attr_done = true;
     }
