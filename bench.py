@@ -39,10 +39,15 @@ WORKLOADS = {
 }
 
 
-# DRAM traffic of the edge kernels of ONE pass over the arxiv-shaped graph, from the committed ncu capture
-# (17.64 + 22.60 + 26.82 MB read, 0.23 + 1.58 + 3.26 MB written): the CSR is L2-resident, so this is ~1000x below the
-# algorithmic gather bytes.
-NCU_DRAM_BYTES_PER_PASS = 78.37e6
+def load_profile_summary():
+    """Counters of the committed ncu capture of the two edge kernels (profiles/r02_edge_kernels_ncu.json, written by
+    profiles/summarize_r02.py from the .ncu-rep of `bench.py --steps 1`): DRAM bytes, executed warp instructions and
+    streamed entries per pass.  bench.py holds no measured literals of its own."""
+    path = os.path.join(REPO, "profiles", "r02_edge_kernels_ncu.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
 
 
 def load_peaks():
@@ -196,6 +201,16 @@ def cpu_bfc_rate(rowptr, col, esrc, edst, threads: int, budget_s: float, seed: i
     return m / dt, m, dt
 
 
+def base_config(workload: str, n: int, E: int, world: int) -> dict:
+    """The part of `config` that names the workload — identical in our arm and in the reference arm."""
+    return {"workload": WORKLOADS[workload], "nodes": int(n), "undirected_edges": int(E),
+            "sharding": ("graph replicated; contiguous edge ranges of equal estimated work, one per GPU; results "
+                         "all-gathered (our arm: fused into the closing kernel over NVLink peer memory)") if world > 1
+            else "single GPU",
+            "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
+            "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks"}
+
+
 def build_graph(workload: str):
     from dcr import graph
     from dcr.synth import named_graph
@@ -210,12 +225,38 @@ def build_graph(workload: str):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the CPU implementation of the path on the host cores
 # ------------------------------------------------------------------------------------------------------------
+def build_oracle_only():
+    """The reference arm needs the oracle's C library and nothing of ours: it never loads libdcr.so."""
+    mk = os.path.join(REPO, "oracle", "c", "Makefile")
+    if os.path.exists(mk):
+        subprocess.run(["make", "-s", "-C", os.path.dirname(mk)], check=True)
+
+
+def python_speed_rate(ei, n, esrc, edst, budget_s: float, seed: int = 0):
+    """Python-speed stand-in for the reference's own `bfc_naive.bfc` loop (curvature/bfc_naive.py:43-52; the reference
+    checkout is not on the GPU box): oracle/paper_flavour.py — the same set arithmetic per edge, one Python thread — on a
+    seeded uniform sample of the edges."""
+    from oracle.paper_flavour import adjacency_sets, bfc_edge_fields
+    adj = adjacency_sets(ei, n)
+    rng = np.random.default_rng(seed)
+    pick = rng.permutation(esrc.size)
+    t0 = time.perf_counter()
+    done = 0
+    for e in pick.tolist():
+        bfc_edge_fields(adj, int(esrc[e]), int(edst[e]))
+        done += 1
+        if done >= 64 and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import __graft_entry__
-    __graft_entry__.build()
+    build_oracle_only()
     ei, n, rowptr, col, esrc, edst = build_graph(args.workload)
     threads = host_threads()
     steps = max(1, args.steps)
@@ -230,12 +271,17 @@ def run_reference(args):
     value = tot_m / tot_t
     sample = (f"oracle C port of curvature/bfc_naive.py (oracle/c/bfc_paper_csr.c), {threads} pthreads, per step a "
               f"seeded uniform sample of {m} of the {esrc.size} undirected edges")
+    py_rate, py_m, py_dt = python_speed_rate(ei, n, esrc, edst, 8.0)
     line = {
         "impl": "reference", "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32 counts + f64 value", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "sample_edges_per_step": m},
+        "config": base_config(args.workload, n, esrc.size, world),
+        "sample_edges_per_step": m,
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "python_speed_baseline": {"value": py_rate, "unit": "edges/s", "cores": 1, "kind": "port",
+                                  "sample": f"oracle/paper_flavour.py (set arithmetic of bfc_naive.bfc_edge, one Python "
+                                            f"thread), {py_m} sampled edges, {py_dt:.1f} s"},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -298,6 +344,31 @@ def sdrf_bench(args, torch):
     out["prefix_matches_cpu"] = bool(same)
     if "iters_per_s" in out:
         out["speedup_vs_cpu"] = out["iters_per_s"] / out["cpu_baseline"]["value"]
+    # the squirrel shape with the reference's hyper-parameters (utils/hyperparams.py:72-81: 1396 iterations, tau 436,
+    # bound 5.88): hub candidate matrices of up to millions of cells; the first --sdrf-squirrel-loops iterations
+    try:
+        from dcr.synth import SDRF_PARAMS
+        sei, sn = named_graph("squirrel")
+        lp_full, stau, sbound = SDRF_PARAMS["squirrel"]
+        lp = min(lp_full, args.sdrf_squirrel_loops)
+        suni = np.random.RandomState(5).random_sample(lp)
+        srow, sorder = graph.networkx_order(sei, sn)
+        st = sdrf.SdrfState(srow, sorder, max_additions=lp)
+        u_dev = torch.from_numpy(suni).cuda()
+        slog = torch.empty((lp, 8), dtype=torch.int32, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sres, _ = st.run(lp, True, sbound, stau, u_dev, log=slog)
+        e1.record()
+        torch.cuda.synchronize()
+        st.close()
+        out["squirrel"] = {"workload": f"squirrel-shaped synthetic graph (N=5201, E=198000), first {lp} of the reference's "
+                                       f"{lp_full} iterations, tau={stau}, removal_bound={sbound}",
+                           "iters_per_s": sres["iterations_done"] / (e0.elapsed_time(e1) * 1e-3),
+                           "iterations": sres["iterations_done"], "ms_total": e0.elapsed_time(e1), "status": sres["status"]}
+    except Exception as exc:
+        out["squirrel"] = {"unavailable": repr(exc)[:300]}
     # The reference's OWN numba kernels on this GPU (oracle/_ref PTX, built from /root/reference by oracle/build_ref.py,
     # loaded with the driver API) driven the reference's way: two A@A + an N^2 x N kernel per iteration, one .item()
     # per candidate.  A reported baseline ("the repo's numba bfc_cuda on the same B200"), present when oracle/_ref is.
@@ -395,20 +466,25 @@ def run_ours(args):
         dist.barrier()
     from dcr import bfc
     from dcr import lib as L
-    from dcr.dist import ShardedPaperBFC
+    from dcr.dist import HostShardedPaperBFC, ShardedPaperBFC
     L.load()
 
     ei, n, rowptr, col, esrc, edst = build_graph(args.workload)
     E = int(esrc.size)
     per_edge_bytes, b_compulsory = algorithmic_bytes(rowptr, col, esrc, edst)
     b_gather_total = int(per_edge_bytes.sum())
-    b_gather_rank = int(per_edge_bytes[rank::world].sum())
     peak, peak_src = load_peaks()
 
     dev = torch.device("cuda", local)
     csr = bfc.DeviceCSR.from_host(rowptr, col, device=dev)
     csr._edges = (torch.from_numpy(esrc).to(dev), torch.from_numpy(edst).to(dev), None)
-    sh = ShardedPaperBFC(csr)
+    sh = ShardedPaperBFC(csr, mode=args.exchange)
+    if sh.mode == "peer":
+        b_gather_rank = int(per_edge_bytes[sh.lo:sh.hi].sum())
+        my_edges = sh.hi - sh.lo
+    else:
+        b_gather_rank = int(per_edge_bytes[rank::world].sum())
+        my_edges = sh.count
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -422,6 +498,13 @@ def run_ours(args):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def gather_floats(x):
+        if world == 1:
+            return [list(x)]
+        out = [None] * world
+        dist.all_gather_object(out, [float(v) for v in x])
+        return out
 
     def new_events(k):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -437,10 +520,6 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    # N > 1: 2-GPU runs intermittently showed one or two 7-120 ms all-gathers among the first timed steps (never at
-    # N = 1, never in the run without the clock probes).  Extra untimed steps and a host head start did not remove
-    # them; the only rank-asymmetric work inside the timed region was rank 0's in-band clock probe, so at N > 1 the
-    # probes now ride on the untimed batch of the same steps that is run right after (where NVML is polled too).
     settle = 5 if world > 1 else 0
     for _ in range(args.warmup + settle):
         flush.zero_()
@@ -458,10 +537,12 @@ def run_ours(args):
             sampler.probe()         # runs on a side stream while this step's kernels execute
     barrier()
     wall = time.perf_counter() - wall0
+    sh.check()
     step_ms = [a.elapsed_time(b) for a, b in step_ev]
     edge_ms = [a.elapsed_time(b) for a, b in edge_ev]
-    # where a step's time goes on this rank: planning (step begin -> first edge kernel), the edge kernels + value
-    # kernel, and what follows them (all-gather + re-interleave at N > 1)
+    # where a step's time goes on this rank: planning (step begin -> first edge kernel), the edge kernels + closing
+    # kernel (which is also the all-gather on the peer route), and what follows (waiting for the peers' results /
+    # NCCL all-gather + re-interleave)
     plan_ms = [s0.elapsed_time(e0) for (s0, _), (e0, _) in zip(step_ev, edge_ev)]
     tail_ms = [e1.elapsed_time(s1) for (_, s1), (_, e1) in zip(step_ev, edge_ev)]
 
@@ -469,12 +550,12 @@ def run_ours(args):
         flush.zero_()
         sh.run()
         if world > 1 and rank == 0 and not args.no_clocks:
-            sampler.probe()         # N > 1: SM-clock probes ride on the untimed batch of the same steps (see below)
+            sampler.probe()         # N > 1: SM-clock probes ride on the untimed batch of the same steps
 
     if world > 1:
         sampler.probe_where = ("during an untimed batch of the same steps run right after the timed region (at N > 1 the "
-                               "probe is kept out of the timed steps: it was the only rank-asymmetric work in them)")
-        n_untimed = max(args.steps, 16)              # every rank runs the same untimed batch (collectives inside)
+                               "probe is kept out of the timed steps: it would be the only rank-asymmetric work in them)")
+        n_untimed = max(args.steps, 16)              # every rank runs the same untimed batch (hand-shakes inside)
         if rank == 0 and not args.no_clocks:
             sampler.under_load(untimed_step, n_untimed, exact=True)
         else:
@@ -491,45 +572,9 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = E / (ms_per_step * 1e-3)
     edge_ms_avg = float(np.mean(edge_ms))
-
-    # ---- end to end: host CSR in (pinned), host results out, copies inside the timed region -------------------
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_rowptr, h_col, h_esrc, h_edst = pin(rowptr), pin(col), pin(esrc), pin(edst)
-    h_out = torch.empty(E * 24, dtype=torch.uint8).pin_memory()
-    d_rowptr = torch.empty_like(h_rowptr, device=dev)
-    d_col = torch.empty_like(h_col, device=dev)
-    d_esrc = torch.empty_like(h_esrc, device=dev)
-    d_edst = torch.empty_like(h_edst, device=dev)
-    csr2 = bfc.DeviceCSR(d_rowptr, d_col, n, csr.max_degree)
-    csr2._edges = (d_esrc, d_edst, None)
-    sh2 = ShardedPaperBFC(csr2)
-    h2d = sum(int(t.numel() * t.element_size()) for t in (h_rowptr, h_col, h_esrc, h_edst))
-    d2h = E * 24
-
-    def e2e_step():
-        d_rowptr.copy_(h_rowptr, non_blocking=True)
-        d_col.copy_(h_col, non_blocking=True)
-        d_esrc.copy_(h_esrc, non_blocking=True)
-        d_edst.copy_(h_edst, non_blocking=True)
-        r = sh2.run()
-        o = 0
-        for key in ("bfc", "tri", "sq_i", "sq_j", "gamma"):
-            src = r[key].view(torch.uint8)
-            h_out[o:o + src.numel()].copy_(src, non_blocking=True)
-            o += src.numel()
-
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    e2e_ev = new_events(args.steps)
-    barrier()
-    for k in range(args.steps):
-        flush.zero_()
-        e2e_ev[k][0].record()
-        e2e_step()
-        e2e_ev[k][1].record()
-    barrier()
-    e2e_total = max_over_ranks(float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])))
-    e2e_value = E / (e2e_total / args.steps * 1e-3)
+    all_step_ms = gather_floats(step_ms)
+    per_step_max = np.max(np.array(all_step_ms), axis=0)            # slowest rank of every step
+    all_edge_ms = gather_floats([edge_ms_avg, float(np.mean(plan_ms)), float(np.mean(tail_ms)), float(my_edges)])
 
     # parity spot check of what was just timed (full check lives in tests/): first 2000 edges vs the C oracle
     checked = None
@@ -538,41 +583,90 @@ def run_ours(args):
         k = min(E, 2000)
         ref = bfc_paper_c(rowptr, col, esrc[:k], edst[:k], 1)
         checked = all(np.array_equal(res[key][:k].cpu().numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
+    sh.close()
 
-    # kernels of one pass (dense mode, n <= 262144): degree, node_s, classify, split_zero, plan_ranges, plan_groups, order;
-    # paper_group_kernel + paper_light_warp_kernel; paper_value_kernel; unshard at N > 1
-    launches_per_step = 7 + 2 + 1 + (1 if world > 1 else 0)
+    # ---- end to end: host CSR in (pinned), host results out, copies inside the timed region -------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_in = (pin(rowptr.astype(np.int32)), pin(col), pin(esrc), pin(edst))
+    hs = HostShardedPaperBFC(n, int(col.size), E, csr.max_degree)
+    for _ in range(min(args.warmup, 3)):
+        hs.run(*h_in)
+    e2e_ev = new_events(args.steps)
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        e2e_ev[k][0].record()
+        hs.run(*h_in)
+        e2e_ev[k][1].record()
+    barrier()
+    e2e_total = max_over_ranks(float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])))
+    e2e_value = E / (e2e_total / args.steps * 1e-3)
+    h2d, d2h = hs.bytes_per_pass()
+    e2e_checked = None
+    if rank == 0:
+        hv = hs.host_views()
+        k = min(E, 2000)
+        e2e_checked = all(np.array_equal(hv[key][:k].numpy(), ref[key]) for key in ("tri", "sq_i", "sq_j", "gamma", "bfc"))
+    if world > 1:
+        io = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(io)
+        h2d, d2h = int(io[0]), int(io[1])
+    hs.close()
+
+    # kernels of one pass (dense mode, n <= 262144): node_s, classify, plan_groups, order; paper_group_kernel +
+    # paper_light_warp_kernel; the closing kernel (value + exchange); at N > 1 the ready / wait hand-shake kernels
+    launches_per_step = 4 + 2 + 1 + (2 if world > 1 else 0)
+    prof = load_profile_summary() if (world == 1 and args.workload == "arxiv") else None
+    clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0) * 1e6
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    roof = {
+        "bound": "hbm", "kernel": "paper_group_kernel + paper_light_warp_kernel (the two edge kernels of one step, concurrent)",
+        "achieved": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+        "traffic": prof["dram_bytes_per_pass"] if prof else None,
+        "traffic_source": prof["source"] if prof else None,
+        "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
+        "algorithmic_bytes_model": "model_upper_bound: SURVEY.md §8d B_gather of this rank's edges — BOTH endpoints' 2-hop "
+                                   "lists once per edge, no cross-edge reuse; the kernel streams only the cheaper side, out "
+                                   "of L2, so frac > 1 is expected and is not a DRAM claim",
+        "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
+    }
+    if prof:
+        # what actually bounds the kernels: instruction issue.  issue_slots_ms = executed warp instructions / (SMs x 4
+        # schedulers x SM clock) = the time the pass needs if every scheduler issued every cycle.
+        issue_ms = prof["warp_instructions_per_pass"] / (sms * 4 * clock_hz) * 1e3
+        roof.update({
+            "streamed_bytes": 4 * prof["streamed_entries_per_pass"],
+            "streamed_frac_of_hbm_peak": 4 * prof["streamed_entries_per_pass"] / (edge_ms_avg * 1e-3) / 1e9 / peak,
+            "dram_frac_of_hbm_peak": prof["dram_bytes_per_pass"] / (edge_ms_avg * 1e-3) / 1e9 / peak,
+            "warp_instructions": prof["warp_instructions_per_pass"], "issue_slots_ms": issue_ms,
+            "frac_issue": issue_ms / edge_ms_avg,
+            "note": "the pass is issue / latency bound, not DRAM bound: CSR and bitmaps are L2 / shared-memory resident "
+                    "(dram_frac_of_hbm_peak), frac_issue = share of the issue slots of 148 SMs x 4 schedulers the "
+                    "executed warp instructions fill during the edge kernels"})
+    cfg = base_config(args.workload, n, E, world)
     line = {
         "metric": "bfc_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32 counts + f64 value", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "nodes": n, "undirected_edges": E,
-                   "sharding": f"edge e -> rank e % {world}, graph replicated, one all-gather" if world > 1 else "single GPU",
-                   "l2": "256 MiB memset between steps (outside the per-step CUDA events)",
-                   "timing": "K steps enqueued back to back, per-step CUDA events, sum over steps, max over ranks", "wall_s_timed_region": wall,
-                   "parity_spot_check_vs_c_oracle": checked, "step_ms": [round(x, 3) for x in step_ms],
-                   "extra_untimed_steps_after_warmup": settle,
-                   "step_ms_median_rank0": round(float(np.median(step_ms)), 4),
-                   "phase_ms_rank0": {"plan": round(float(np.mean(plan_ms)), 4), "edge_kernels": round(edge_ms_avg, 4),
-                                      "gather_unshard": round(float(np.mean(tail_ms)), 4)}},
+        "config": cfg,
+        "exchange": sh.mode, "wall_s_timed_region": wall, "parity_spot_check_vs_c_oracle": checked,
+        "e2e_parity_spot_check_vs_c_oracle": e2e_checked,
+        "step_ms": [round(x, 3) for x in per_step_max.tolist()],
+        "step_ms_mean_over_median": round(float(np.mean(per_step_max) / np.median(per_step_max)), 4),
+        "extra_untimed_steps_after_warmup": settle,
+        "phase_ms_rank0": {"plan": round(float(np.mean(plan_ms)), 4), "edge_kernels_and_closing": round(edge_ms_avg, 4),
+                           "wait_for_peers" if sh.mode == "peer" else "gather_unshard": round(float(np.mean(tail_ms)), 4)},
+        "per_rank": [{"edge_kernels_ms": round(r[0], 4), "plan_ms": round(r[1], 4), "tail_ms": round(r[2], 4),
+                      "edges": int(r[3])} for r in all_edge_ms],
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / args.steps,
-                "what": "dcr.dist.ShardedPaperBFC.run on host (pinned) CSR + edge list; results copied back to pinned host memory"},
+                "what": "dcr.dist.HostShardedPaperBFC.run: pinned host CSR + edge list -> every rank uploads the graph, finds "
+                        "its work-balanced range on the device, computes it and copies its slice of the results into one "
+                        "host block shared by the ranks (bytes = sum over ranks)"},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {
-            "bound": "hbm", "kernel": "paper_group_kernel + paper_light_warp_kernel (the two edge kernels of one step, concurrent)",
-            "achieved": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": b_gather_rank / (edge_ms_avg * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-            "traffic": NCU_DRAM_BYTES_PER_PASS if (world == 1 and args.workload == "arxiv") else None,
-            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the two edge-kernel "
-                              "launches of one pass (profiles/r01_v20_ncu_full_edge_kernels.csv)",
-            "edge_kernels_ms": edge_ms_avg, "algorithmic_bytes": b_gather_rank,
-            "b_gather_total": b_gather_total, "b_compulsory": b_compulsory,
-            "note": "algorithmic bytes = SURVEY.md §8d B_gather of this rank's edges (every 2-hop list once per edge, "
-                    "no cross-edge reuse charged); the CSR is L2-resident so DRAM traffic is far below it — see "
-                    "profiles/ for dram__bytes and lts__t_bytes",
-        },
+        "roofline": roof,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         thr = host_threads()
@@ -580,6 +674,17 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "edges/s", "cores": thr, "kind": "port",
                                 "sample": f"oracle C port of curvature/bfc_naive.py (oracle/c/bfc_paper_csr.c), {thr} "
                                           f"pthreads, seeded uniform sample of {m} of {E} edges, {dt:.1f} s"}
+        py_rate, py_m, py_dt = python_speed_rate(ei, n, esrc, edst, 6.0)
+        line["python_speed_baseline"] = {
+            "value": py_rate, "unit": "edges/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/paper_flavour.py — the set arithmetic of bfc_naive.bfc_edge at Python speed, the stand-in for "
+                      f"the reference's own bfc_naive.bfc loop (the checkout is not on the GPU box); {py_m} sampled edges, "
+                      f"{py_dt:.1f} s"}
+    if rank == 0 and world == 1 and not args.no_dense:
+        try:
+            line["dense"] = dense_bench(args, torch)
+        except Exception as exc:
+            line["dense"] = {"unavailable": repr(exc)[:300]}
     if rank == 0 and not args.no_sdrf:
         line["sdrf"] = sdrf_bench(args, torch)
     if rank == 0:
@@ -608,15 +713,9 @@ def emit(line: dict):
     out.flush()
 
 
-def run_dense(args):
-    """Config 4: the dense-regime tensor path (1 GPU).  value = undirected edges/s of the full cuda-flavour pass."""
-    import torch
-
-    import __graft_entry__
-    __graft_entry__.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device")
-    torch.cuda.set_device(0)
+def dense_bench(args, torch) -> dict:
+    """Config 4: the dense-regime tensor path on the squirrel-shaped graph (1 GPU): supports A2[i,j] on the edges via the
+    hand-written tcgen05 int8 A·A kernel, the full cuda-flavour pass through it, and the sorted-list route beside it."""
     from dcr import bfc
     ei, n, rowptr, col, esrc, edst = build_graph("squirrel")
     E = int(esrc.size)
@@ -625,8 +724,9 @@ def run_dense(args):
     ws = torch.empty(int(bfc.L.load().dcr_bfc_support_tc_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
     tri = torch.empty(csr.nnz, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    steps, warmup = max(5, min(args.steps, 20)), 3
 
-    def timed(fn, steps, warmup):
+    def timed(fn):
         for _ in range(warmup):
             fn()
         out = []
@@ -640,40 +740,73 @@ def run_dense(args):
             out.append(e0.elapsed_time(e1))
         return float(np.mean(out))
 
-    sampler = ClockSampler(0)
-    sampler.start()
-    timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), 1, args.warmup)
-    for _ in range(4):
-        sampler.probe()
-        bfc.support_tc(csr, out=tri, workspace=ws)
-    ms_tc = timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws), args.steps, args.warmup)
+    ms_tc = timed(lambda: bfc.support_tc(csr, out=tri, workspace=ws))
     ws2 = torch.empty(int(bfc.L.load().dcr_bfc_cuda_flavour_tc_workspace_bytes(n, csr.nnz)), dtype=torch.uint8,
                       device="cuda")
-    ms_full = timed(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2), args.steps, args.warmup)
-    sampler.under_load(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2), args.steps)
-    clocks = sampler.result()
-    ms_sparse = timed(lambda: bfc.support(csr, out=tri), args.steps, args.warmup)
-    ms_full_sparse = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr, out=tri)),
-                           args.steps, args.warmup)
+    ms_full = timed(lambda: bfc.cuda_flavour_tc(csr, want_fields=False, workspace=ws2))
+    ms_sparse = timed(lambda: bfc.support(csr, out=tri))
+    ms_full_sparse = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr, out=tri)))
     same = bool(torch.equal(bfc.support_tc(csr), bfc.support(csr)))
     c_tc = bfc.cuda_flavour_tc(csr, want_fields=False)["c32"]
     c_sp = bfc.cuda_flavour(csr, want_fields=False)["c32"]
     same = same and bool(torch.equal(c_tc.view(torch.int32), c_sp.view(torch.int32)))
     ops = 2.0 * n_pad ** 3
-    line = {
-        "metric": "bfc_edges_per_sec", "value": E / (ms_full * 1e-3), "unit": "edges/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), f64 closing formula",
-        "data": "synthetic", "config": {"workload": DENSE_WORKLOAD, "nodes": n, "undirected_edges": E, "n_pad": n_pad,
-                                        "l2": "256 MiB memset between steps", "outputs_bit_identical_to_sparse_path": same},
-        "clocks": clocks, "gpu_launches": 5 * args.steps,   # fill, GEMM, fill_q, GEMM, closing (+ one memset)
-        "roofline": {"bound": "tensor", "kernel": "tc_support_kernel (+ memset and tc_fill_kernel of the same call)",
-                     "achieved": ops / (ms_tc * 1e-3) / 1e12, "peak": 4500.0, "unit": "TOP/s (int8)",
-                     "frac": ops / (ms_tc * 1e-3) / 1e12 / 4500.0,
-                     "peak_source": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)",
+    peak_i8, peak_src = int8_peak(torch)
+    return {
+        "workload": DENSE_WORKLOAD, "nodes": n, "undirected_edges": E, "n_pad": n_pad,
+        "value": E / (ms_full * 1e-3), "unit": "edges/s", "ms_per_step": ms_full, "steps": steps,
+        "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), f64 closing formula",
+        "outputs_bit_identical_to_sparse_path": same,
+        "roofline": {"bound": "tensor", "kernel": "tc_support_kernel (+ the operand fill of the same call)",
+                     "achieved": ops / (ms_tc * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s (int8)",
+                     "frac": ops / (ms_tc * 1e-3) / 1e12 / peak_i8, "peak_source": peak_src,
                      "traffic": None, "support_tc_ms": ms_tc, "ops": ops},
         "sparse_path": {"support_ms": ms_sparse, "full_ms": ms_full_sparse,
                         "note": "sorted-list intersection kernels on the same CSR (dcr_bfc_support + dcr_bfc_cuda_flavour)"},
+    }
+
+
+def int8_peak(torch):
+    """Dense int8 tensor peak to hold the tcgen05 path against: measured on this GPU with the library's own
+    resident-tile tcgen05 kind::i8 loop when it exports one, else the nominal figure (labelled)."""
+    from dcr import lib as L
+    lib = L.load()
+    if hasattr(lib, "dcr_tc_int8_peak"):
+        import ctypes as C
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        fn = lib.dcr_tc_int8_peak
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p]
+        best = 0.0
+        for _ in range(3):
+            if fn(out.data_ptr(), L.current_stream()) != 0:
+                best = 0.0
+                break
+            torch.cuda.synchronize()
+            best = max(best, float(out.item()))
+        if best > 0:
+            return best, "measured: resident-tile tcgen05 kind::i8 loop of libdcr (dcr_tc_int8_peak), best of 3"
+    return 4500.0, "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)"
+
+
+def run_dense(args):
+    """`--workload squirrel-dense`: config 4 as a line of its own."""
+    import torch
+
+    import __graft_entry__
+    __graft_entry__.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(0)
+    d = dense_bench(args, torch)
+    line = {
+        "metric": "bfc_edges_per_sec", "value": d["value"], "unit": "edges/s", "n_gpus": 1,
+        "steps": d["steps"], "warmup": 3, "ms_per_step": d["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": d["dtype"], "data": "synthetic",
+        "config": {"workload": DENSE_WORKLOAD, "nodes": d["nodes"], "undirected_edges": d["undirected_edges"],
+                   "n_pad": d["n_pad"], "l2": "256 MiB memset between steps"},
+        "outputs_bit_identical_to_sparse_path": d["outputs_bit_identical_to_sparse_path"],
+        "gpu_launches": 5 * d["steps"], "roofline": d["roofline"], "sparse_path": d["sparse_path"],
     }
     emit(line)
 
@@ -688,7 +821,11 @@ def main():
     ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS) + ["squirrel-dense"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--sdrf-loops", type=int, default=1000)
-    ap.add_argument("--sdrf-cpu-iters", type=int, default=3)
+    ap.add_argument("--sdrf-cpu-iters", type=int, default=20)
+    ap.add_argument("--sdrf-squirrel-loops", type=int, default=200)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU exchange: fused peer-memory closing kernel (default) or NCCL all-gather")
+    ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sdrf", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks")

@@ -30,6 +30,7 @@
 // L2-resident, so the kernel is bound by instruction issue / L1 gathers / shared-memory probes, not by DRAM.
 // Grids are persistent (multiples of the SM count) and pull work from global counters.
 #include <algorithm>
+#include <mutex>
 #include <stdlib.h>
 
 #include "dcr_common.cuh"
@@ -256,20 +257,18 @@ __device__ __forceinline__ double paper_value(int d1, int d2, int tri, int sq1, 
 // ------------------------------------------------------------------------------------------------------------
 // planning kernels: S_v, per-edge class/bucket, bucket offsets, order
 // ------------------------------------------------------------------------------------------------------------
-// S_v = sum of the degrees of v's neighbours, via a degree array (one 4-byte gather per entry instead of two
-// dependent row-offset loads).
-__global__ void degree_kernel(const int32_t* __restrict__ rowptr, int n, int32_t* __restrict__ deg) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < n) deg[v] = rowptr[v + 1] - rowptr[v];
-}
-__global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                              const int32_t* __restrict__ deg, int n, int64_t* __restrict__ node_s) {
+// S_v = sum of the degrees of v's neighbours (the two row offsets of a neighbour share a sector).
+__global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                              int64_t* __restrict__ node_s) {
     const int lane = threadIdx.x & 31;
     const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (v >= n) return;
     const int b = rowptr[v], e = rowptr[v + 1];
     int64_t s = 0;
-    for (int p = b + lane; p < e; p += 32) s += deg[colidx[p]];
+    for (int p = b + lane; p < e; p += 32) {
+        const int k = colidx[p];
+        s += rowptr[k + 1] - rowptr[k];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if (lane == 0) node_s[v] = s;
@@ -347,26 +346,6 @@ __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
     if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
 }
 
-// zero the handed-out part of the split edges' hash pools
-__global__ void __launch_bounds__(256) split_zero_kernel(PaperArgs a) {
-    for (int k = 0; k < 2; ++k) {
-        const size_t used = (size_t)min(a.plan->shash_used[k], (unsigned long long)SHASH_WORDS);
-        uint4* p = (uint4*)(a.shash + (size_t)k * SHASH_WORDS);
-        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < used / 4; q += (size_t)gridDim.x * blockDim.x)
-            p[q] = make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
-// Class ranges (one thread).
-__global__ void plan_ranges_kernel(PaperArgs a) {
-    PaperPlan* plan = a.plan;
-    if (threadIdx.x == 0) {
-        unsigned int acc = 0;
-        for (int c = 0; c < N_CLASSES; ++c) { plan->class_begin[c] = acc; acc += plan->grouped[c]; }
-        plan->class_begin[N_CLASSES] = acc;
-    }
-}
-
 // position of rank s inside a group of `cnt` edges that starts at `gstart` (see RUN_EDGES)
 __device__ __forceinline__ unsigned int run_layout_pos(unsigned int gstart, unsigned int cnt, unsigned int R, unsigned int s) {
     const unsigned int q = cnt / R, rem = cnt % R;
@@ -389,8 +368,22 @@ __device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned 
 __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
     // ranges are reserved per block (shared-memory counters, then ONE global atomic per class and block): one global
     // atomic per vertex would serialise ~n operations on a handful of addresses
-    __shared__ unsigned int s_cnt[N_CLASSES], s_base[N_CLASSES];
+    __shared__ unsigned int s_cnt[N_CLASSES], s_base[N_CLASSES], s_begin[N_CLASSES + 1];
     if (threadIdx.x < N_CLASSES) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {                       // class ranges: every block derives them; block 0 publishes them
+        unsigned int acc = 0;
+        for (int c = 0; c < N_CLASSES; ++c) { s_begin[c] = acc; acc += a.plan->grouped[c]; }
+        s_begin[N_CLASSES] = acc;
+        if (blockIdx.x == 0)
+            for (int c = 0; c <= N_CLASSES; ++c) a.plan->class_begin[c] = s_begin[c];
+    }
+    // zero the handed-out part of the split edges' hash pools (grid-stride; nothing for most calls)
+    for (int k = 0; k < 2; ++k) {
+        const size_t used = (size_t)min(a.plan->shash_used[k], (unsigned long long)SHASH_WORDS);
+        uint4* pz = (uint4*)(a.shash + (size_t)k * SHASH_WORDS);
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < used / 4; q += (size_t)gridDim.x * blockDim.x)
+            pz[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int c[N_SLOTS] = {0, 0, 0, 0}, own = 0, own_off = 0, coop_off = 0;
@@ -412,7 +405,7 @@ __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
     }
     __syncthreads();
     if (threadIdx.x < N_CLASSES && s_cnt[threadIdx.x])
-        s_base[threadIdx.x] = a.plan->class_begin[threadIdx.x] + atomicAdd(&a.plan->group_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+        s_base[threadIdx.x] = s_begin[threadIdx.x] + atomicAdd(&a.plan->group_cursor[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
     if (own) {
         const unsigned int gstart = s_base[cls] + own_off;
@@ -1717,16 +1710,23 @@ static inline uint32_t next_pow2_u32(uint64_t v) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// DCR_PAPER_MODE=hashed forces the hashed-table kernels (the path of graphs with more than DENSE_MAX_N nodes) on a
-// small graph — used by the parity tests to cover both paths.
-static bool use_dense_mode(int n) {
+// Membership mode: 0 = automatic (exact shared-memory bitmap up to DENSE_MAX_N nodes), 1 = force the hashed-table
+// kernels (the path of graphs with more than DENSE_MAX_N nodes) — used by the parity tests to cover both paths on
+// small graphs.  The initial value comes from the environment variable DCR_PAPER_MODE=hashed, read ONCE at load;
+// dcr_bfc_paper_set_mode() changes it (process-wide; call it between passes, not concurrently with one).
+static int g_paper_mode = []() {
     const char* m = getenv("DCR_PAPER_MODE");
-    if (m && m[0] == 'h') return false;
-    return n <= DENSE_MAX_N;
+    return (m && m[0] == 'h') ? 1 : 0;
+}();
+extern "C" int dcr_bfc_paper_set_mode(int mode) {
+    const int old = g_paper_mode;
+    g_paper_mode = mode ? 1 : 0;
+    return old;
 }
+static bool use_dense_mode(int n) { return g_paper_mode == 0 && n <= DENSE_MAX_N; }
 
 struct ScratchLayout {
-    size_t plan, node_s, bucket, order, ova, va_cnt, va_cur, grp, runs, gtables, ghash, gtri, shash, split_item, total;
+    size_t plan, node_s, bucket, order, ova, va_cnt, va_cur, grp, runs, gtables, ghash, gtri, shash, split_item, zero_bytes, total;
     uint32_t max_runs;
     uint32_t gslots, ghash_cap;
     int g_ctas, group_ctas;
@@ -1735,13 +1735,15 @@ struct ScratchLayout {
 static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     ScratchLayout L;
     size_t off = 0;
+    // plan | va_cnt | va_cur are adjacent: one memset clears the three of them
     L.plan = off; off = align_up(off + sizeof(PaperPlan), 256);
+    L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
+    L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
+    L.zero_bytes = off;
     L.node_s = off; off = align_up(off + (size_t)n * sizeof(int64_t), 256);
     L.bucket = off; off = align_up(off + (size_t)count, 256);
     L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.ova = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
-    L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
-    L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
     L.grp = off; off = align_up(off + (size_t)5 * n * sizeof(uint32_t), 256);
     // a light group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(n, count) light groups
     L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>((int64_t)n, count) + 1);
@@ -1770,11 +1772,22 @@ extern "C" int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t co
     return (int64_t)scratch_layout(n, max_degree, count).total;
 }
 
-extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
-                             const int32_t* esrc, const int32_t* edst, int64_t e_first, int64_t e_stride,
-                             int64_t count, int32_t* out_tri, int32_t* out_sq_i, int32_t* out_sq_j,
-                             int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
-                             void* ev_edge_begin, void* ev_edge_end, void* stream) {
+// per-device fork/join streams and events of the pass.  One pass at a time per device may use them: the section
+// that records / waits on them is serialised by the device's mutex (two host threads driving the same device with
+// different streams would otherwise re-record each other's fork event).
+struct PaperAux {
+    std::mutex mu;
+    bool ready = false, attr_done = false;
+    cudaStream_t aux[3] = {};
+    cudaEvent_t fork = nullptr, join[3] = {};
+};
+static PaperAux g_aux[MAX_DEVICES];
+
+static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
+                      const int32_t* esrc, const int32_t* edst, int64_t e_first, int64_t e_stride,
+                      int64_t count, int32_t* out_tri, int32_t* out_sq_i, int32_t* out_sq_j,
+                      int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
+                      void* ev_edge_begin, void* ev_edge_end, void* stream, bool value_kernel) {
     if (count <= 0 || n <= 0) return 0;
     if (count > 0xfffffff0LL) { set_error("dcr_bfc_paper: more than 2^32 edges per call"); return 1; }
     if (n >= (1 << 30) - 1) { set_error("dcr_bfc_paper: node ids must fit 30 bits (table keys carry 2 tag bits)"); return 1; }
@@ -1814,22 +1827,13 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     a.shash = (uint32_t*)(base + L.shash);
     a.split_item = (uint32_t*)(base + L.split_item);
 
-    DCR_CUDA(cudaMemsetAsync(a.plan, 0, sizeof(PaperPlan), st));
-    DCR_CUDA(cudaMemsetAsync(a.va_cnt, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
-    int32_t* deg = (int32_t*)a.va_cur;     // va_cur is not used before order_kernel; cleared again below
-    degree_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr, n, deg);
+    DCR_CUDA(cudaMemsetAsync(base + L.plan, 0, L.zero_bytes - L.plan, st));      // plan, va_cnt, va_cur
+    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s);
     DCR_LAUNCH_CHECK();
-    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, deg, n, node_s);
-    DCR_LAUNCH_CHECK();
-    DCR_CUDA(cudaMemsetAsync(a.va_cur, 0, (size_t)N_SLOTS * n * sizeof(uint32_t), st));
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
-    split_zero_kernel<<<sm_count() * 4, 256, 0, st>>>(a);
-    DCR_LAUNCH_CHECK();
-    plan_ranges_kernel<<<1, 32, 0, st>>>(a);
-    DCR_LAUNCH_CHECK();
-    plan_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    plan_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);     // + class ranges, + zeroing of the split hashes
     DCR_LAUNCH_CHECK();
     order_kernel<<<tb, 256, 0, st>>>(a);
     DCR_LAUNCH_CHECK();
@@ -1837,9 +1841,10 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     const int sms = sm_count();
     if (ev_edge_begin) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_begin, st));
     // Persistent grids = SM count x resident CTAs per SM.
-    static bool attr_done_dev[MAX_DEVICES] = {false};
     const int dev = current_device();
-    bool& attr_done = attr_done_dev[dev];
+    PaperAux& ax = g_aux[dev];
+    std::lock_guard<std::mutex> guard(ax.mu);
+    bool& attr_done = ax.attr_done;
     constexpr int big_stream = 3 * heads_per_thread(BIG_THREADS) * BIG_THREADS + 8;
     const int dense_words = (n + 63) / 64 * 2;       // even: what follows the bitmaps in shared memory is 8-byte aligned
     const int smem_x = (big_stream + GLOBAL_BITS / 32) * (int)sizeof(int);
@@ -1866,17 +1871,16 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
     // from `st` so that, as the persistent CTAs of one class run out of work, CTAs of another class take over the
     // freed SMs instead of waiting for the slowest CTA.
     constexpr int N_AUX = 3;
-    static cudaStream_t aux_dev[MAX_DEVICES][N_AUX] = {};
-    static cudaEvent_t fork_dev[MAX_DEVICES] = {}, join_dev[MAX_DEVICES][N_AUX] = {};
-    cudaStream_t* aux = aux_dev[dev];
-    cudaEvent_t& ev_fork = fork_dev[dev];
-    cudaEvent_t* ev_join = join_dev[dev];
-    if (!aux[0]) {
+    cudaStream_t* aux = ax.aux;
+    cudaEvent_t& ev_fork = ax.fork;
+    cudaEvent_t* ev_join = ax.join;
+    if (!ax.ready) {
         for (int q = 0; q < N_AUX; ++q) {
             DCR_CUDA(cudaStreamCreateWithFlags(&aux[q], cudaStreamNonBlocking));
             DCR_CUDA(cudaEventCreateWithFlags(&ev_join[q], cudaEventDisableTiming));
         }
         DCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        ax.ready = true;
     }
     DCR_CUDA(cudaEventRecord(ev_fork, st));
     const int n_aux = a.dense ? 1 : N_AUX;
@@ -1900,10 +1904,21 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
         DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));
         DCR_CUDA(cudaStreamWaitEvent(st, ev_join[q], 0));
     }
-    paper_value_kernel<<<tb, 256, 0, st>>>(a);
-    DCR_LAUNCH_CHECK();
+    if (value_kernel) {
+        paper_value_kernel<<<tb, 256, 0, st>>>(a);
+        DCR_LAUNCH_CHECK();
+    }
     if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
     return 0;
+}
+
+extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
+                             const int32_t* esrc, const int32_t* edst, int64_t e_first, int64_t e_stride,
+                             int64_t count, int32_t* out_tri, int32_t* out_sq_i, int32_t* out_sq_j,
+                             int32_t* out_gamma, double* out_bfc, void* scratch, int64_t scratch_bytes,
+                             void* ev_edge_begin, void* ev_edge_end, void* stream) {
+    return paper_pass(rowptr, colidx, n, max_degree, esrc, edst, e_first, e_stride, count, out_tri, out_sq_i, out_sq_j,
+                      out_gamma, out_bfc, scratch, scratch_bytes, ev_edge_begin, ev_edge_end, stream, true);
 }
 
 #ifdef DCR_PAPER_TRACE
@@ -1943,6 +1958,264 @@ extern "C" int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t ch
     const int ctas = (int)std::min<int64_t>((n_edges + 255) / 256, (int64_t)sm_count() * 8);
     unshard_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)gathered, world, chunk, n_edges,
                                                           out_tri, out_sq_i, out_sq_j, out_gamma, out_bfc);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU, contiguous edge ranges: the value kernel of a rank doubles as the all-gather.  Every rank owns the
+// FULL result arrays (indexed by edge id) in a buffer its peers can write (CUDA IPC over NVLink / NVSwitch); rank r
+// computes the edges [e_lo, e_lo + count) and its closing kernel stores each edge's five results at the edge's own
+// position in EVERY rank's buffer — no staging block, no collective call, no re-interleave pass.  Two small flag
+// arrays per buffer carry the hand-shake: ready[p] = "rank p has passed the start of pass k" (its consumers of the
+// previous pass are done: its buffer may be overwritten), done[p] = "all of rank p's results of pass k have landed".
+// ------------------------------------------------------------------------------------------------------------
+constexpr int COMM_MAX_WORLD = 32;
+struct CommFlags {
+    unsigned int ready[COMM_MAX_WORLD];
+    unsigned int done[COMM_MAX_WORLD];
+    unsigned int blocks_done;        // last-block detection of the closing kernel
+    unsigned int error;              // a wait timed out (the peers never arrived)
+};
+struct dcr_comm {
+    int rank, world, device;
+    int64_t n_edges, chunk;          // arrays are `chunk` entries long (n_edges rounded up to 4)
+    size_t bytes, flag_off;
+    unsigned char* local;
+    unsigned char* peer[COMM_MAX_WORLD];
+    unsigned char** d_peers;         // the same pointers on the device
+    unsigned int epoch;
+    bool connected;
+};
+
+namespace dcr {
+
+struct CommView {
+    unsigned char* const* peers;     // [world] buffers
+    int rank, world;
+    int64_t chunk;
+    size_t flag_off;
+    unsigned int epoch;
+};
+__device__ __forceinline__ CommFlags* comm_flags(unsigned char* buf, size_t flag_off) { return (CommFlags*)(buf + flag_off); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long comm_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long COMM_TIMEOUT_NS = 4000000000ull;     // a peer that has not arrived after 4 s never will
+
+// start of a pass: tell every peer that this rank's buffer may be overwritten
+__global__ void comm_ready_kernel(CommView c) {
+    const int p = threadIdx.x;
+    if (p < c.world && p != c.rank) st_release_sys(&comm_flags(c.peers[p], c.flag_off)->ready[c.rank], c.epoch);
+}
+
+// bfc_naive.py:31-32 / :39-40 for the edges [e_lo, e_lo + count) + the fused all-gather (see above)
+__global__ void __launch_bounds__(256) paper_value_exchange_kernel(PaperArgs a, CommView c) {
+    __shared__ int s_last;
+    unsigned char* mine = c.peers[c.rank];
+    CommFlags* fl = comm_flags(mine, c.flag_off);
+    if (threadIdx.x < c.world && threadIdx.x != c.rank) {           // the peers' buffers are free to take pass `epoch`
+        const unsigned long long t0 = comm_now();
+        while ((int)(ld_acquire_sys(&fl->ready[threadIdx.x]) - c.epoch) < 0) {
+            if (comm_now() - t0 > COMM_TIMEOUT_NS) { fl->error = 1u; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.count) {
+        const int64_t e = a.e_first + t;
+        const int i = a.esrc[e], j = a.edst[e];
+        const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
+        const int tri = a.out_tri[t], sq_i = a.out_sq_i[t], sq_j = a.out_sq_j[t], gamma = a.out_gamma[t];
+        const double v = min(di, dj) <= 1 ? 0.0 : paper_value(di, dj, tri, sq_i, sq_j, gamma);   // :18-19 -> 0
+        a.out_bfc[t] = v;
+        for (int q = 1; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;                    // every rank starts with a different peer
+            unsigned char* buf = c.peers[p];
+            ((double*)buf)[e] = v;
+            int32_t* ints = (int32_t*)(buf + c.chunk * 8);
+            ints[e] = tri;
+            ints[c.chunk + e] = sq_i;
+            ints[2 * c.chunk + e] = sq_j;
+            ints[3 * c.chunk + e] = gamma;
+        }
+    }
+    if (c.world == 1) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&fl->blocks_done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {                                                    // everything this rank had to deliver is on its way
+        __threadfence_system();
+        if (threadIdx.x == 0) fl->blocks_done = 0u;
+        if (threadIdx.x < c.world && threadIdx.x != c.rank)
+            st_release_sys(&comm_flags(c.peers[threadIdx.x], c.flag_off)->done[c.rank], c.epoch);
+    }
+}
+
+// end of a pass: the peers' results have landed in this rank's buffer
+__global__ void comm_wait_kernel(CommView c) {
+    CommFlags* fl = comm_flags(c.peers[c.rank], c.flag_off);
+    const int p = threadIdx.x;
+    if (p < c.world && p != c.rank) {
+        const unsigned long long t0 = comm_now();
+        while ((int)(ld_acquire_sys(&fl->done[p]) - c.epoch) < 0) {
+            if (comm_now() - t0 > COMM_TIMEOUT_NS) { fl->error = 1u; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+}  // namespace dcr
+
+extern "C" int dcr_comm_create(int rank, int world, int64_t n_edges, dcr_comm** out) {
+    if (!out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || n_edges < 0) {
+        set_error("dcr_comm_create: bad arguments (world <= %d)", COMM_MAX_WORLD);
+        return 1;
+    }
+    dcr_comm* c = new dcr_comm();
+    c->rank = rank; c->world = world; c->device = current_device();
+    c->n_edges = n_edges;
+    c->chunk = std::max<int64_t>(4, (n_edges + 3) / 4 * 4);
+    c->flag_off = align_up((size_t)c->chunk * 24, 256);
+    c->bytes = c->flag_off + align_up(sizeof(CommFlags), 256);
+    c->epoch = 0;
+    c->connected = (world == 1);
+    c->local = nullptr; c->d_peers = nullptr;
+    for (int p = 0; p < COMM_MAX_WORLD; ++p) c->peer[p] = nullptr;
+    cudaError_t e = cudaMalloc((void**)&c->local, c->bytes);            // plain cudaMalloc: exportable through CUDA IPC
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, c->bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_peers, sizeof(unsigned char*) * COMM_MAX_WORLD);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "dcr_comm_create", __FILE__, __LINE__); }
+    c->peer[rank] = c->local;
+    e = cudaMemcpy(c->d_peers, c->peer, sizeof(unsigned char*) * COMM_MAX_WORLD, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "dcr_comm_create", __FILE__, __LINE__); }
+    *out = c;
+    return 0;
+}
+
+extern "C" int dcr_comm_handle(dcr_comm* c, void* handle64_host) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!c || !handle64_host) { set_error("dcr_comm_handle: NULL argument"); return 1; }
+    DCR_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_host, c->local));
+    return 0;
+}
+
+extern "C" int dcr_comm_connect(dcr_comm* c, const void* handles_host) {
+    if (!c || !handles_host) { set_error("dcr_comm_connect: NULL argument"); return 1; }
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles_host;
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) continue;
+        void* ptr = nullptr;
+        DCR_CUDA(cudaIpcOpenMemHandle(&ptr, h[p], cudaIpcMemLazyEnablePeerAccess));
+        c->peer[p] = (unsigned char*)ptr;
+    }
+    DCR_CUDA(cudaMemcpy(c->d_peers, c->peer, sizeof(unsigned char*) * COMM_MAX_WORLD, cudaMemcpyHostToDevice));
+    c->connected = true;
+    return 0;
+}
+
+extern "C" void* dcr_comm_buffer(dcr_comm* c) { return c ? c->local : nullptr; }
+extern "C" int64_t dcr_comm_chunk(dcr_comm* c) { return c ? c->chunk : 0; }
+
+extern "C" int dcr_comm_error(dcr_comm* c) {                               // synchronises
+    if (!c) return 1;
+    unsigned int err = 0;
+    if (cudaMemcpy(&err, c->local + c->flag_off + offsetof(CommFlags, error), sizeof(err), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 1;
+    return (int)err;
+}
+
+extern "C" int dcr_comm_destroy(dcr_comm* c) {
+    if (!c) return 0;
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world; ++p)
+        if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    if (c->d_peers) cudaFree(c->d_peers);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return 0;
+}
+
+extern "C" int dcr_bfc_paper_sharded(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
+                                     const int32_t* esrc, const int32_t* edst, int64_t e_lo, int64_t count,
+                                     dcr_comm* c, void* scratch, int64_t scratch_bytes, void* ev_edge_begin,
+                                     void* ev_edge_end, void* stream) {
+    if (!c) { set_error("dcr_bfc_paper_sharded: comm is NULL"); return 1; }
+    if (!c->connected) { set_error("dcr_bfc_paper_sharded: dcr_comm_connect has not been called"); return 1; }
+    if (e_lo < 0 || count < 0 || e_lo + count > c->n_edges) { set_error("dcr_bfc_paper_sharded: edge range outside [0, n_edges)"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CommView v;
+    v.peers = c->d_peers; v.rank = c->rank; v.world = c->world; v.chunk = c->chunk; v.flag_off = c->flag_off;
+    v.epoch = ++c->epoch;
+    if (c->world > 1) {
+        comm_ready_kernel<<<1, COMM_MAX_WORLD, 0, st>>>(v);
+        DCR_LAUNCH_CHECK();
+    }
+    double* bfc = (double*)c->local + e_lo;
+    int32_t* ints = (int32_t*)(c->local + c->chunk * 8);
+    int32_t *tri = ints + e_lo, *sq_i = ints + c->chunk + e_lo, *sq_j = ints + 2 * c->chunk + e_lo, *gamma = ints + 3 * c->chunk + e_lo;
+    if (count > 0) {
+        const int rc = paper_pass(rowptr, colidx, n, max_degree, esrc, edst, e_lo, 1, count, tri, sq_i, sq_j, gamma, bfc,
+                                  scratch, scratch_bytes, ev_edge_begin, nullptr, stream, false);
+        if (rc) return rc;
+    }
+    PaperArgs a;
+    a.rowptr = rowptr; a.colidx = colidx; a.esrc = esrc; a.edst = edst;
+    a.e_first = e_lo; a.e_stride = 1; a.count = count;
+    a.out_tri = tri; a.out_sq_i = sq_i; a.out_sq_j = sq_j; a.out_gamma = gamma; a.out_bfc = bfc;
+    // (an empty range still takes part in the hand-shake: one block that only signals)
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, (count + 255) / 256);
+    paper_value_exchange_kernel<<<blocks, 256, 0, st>>>(a, v);
+    DCR_LAUNCH_CHECK();
+    if (ev_edge_end) DCR_CUDA(cudaEventRecord((cudaEvent_t)ev_edge_end, st));
+    if (c->world > 1) {
+        comm_wait_kernel<<<1, COMM_MAX_WORLD, 0, st>>>(v);
+        DCR_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// work estimate per undirected edge, for cutting the edge list into contiguous ranges of equal WORK:
+// the entries the pass streams for the edge (the cheaper side's 2-hop lists) plus a per-head and a per-edge term.
+// ------------------------------------------------------------------------------------------------------------
+namespace dcr {
+__global__ void edge_cost_kernel(const int32_t* __restrict__ rowptr, const int64_t* __restrict__ node_s,
+                                 const int32_t* __restrict__ esrc, const int32_t* __restrict__ edst, int64_t n_edges,
+                                 int64_t* __restrict__ cost) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int i = esrc[e], j = edst[e];
+    const int64_t di = rowptr[i + 1] - rowptr[i], dj = rowptr[j + 1] - rowptr[j];
+    if (min(di, dj) <= 1) { cost[e] = 2; return; }
+    const int64_t ca = node_s[j] - di, cb = node_s[i] - dj;
+    const bool swapped = cb < ca;                    // stream i's side
+    const int64_t stream = swapped ? cb : ca, heads = swapped ? di : dj;
+    cost[e] = stream + 24 * heads + 160;
+}
+}  // namespace dcr
+
+extern "C" int dcr_bfc_paper_edge_cost(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc,
+                                       const int32_t* edst, int64_t n_edges, int64_t* out_cost, int64_t* node_s_scratch,
+                                       void* stream) {
+    if (n <= 0 || n_edges <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s_scratch);
+    DCR_LAUNCH_CHECK();
+    edge_cost_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(rowptr, node_s_scratch, esrc, edst, n_edges, out_cost);
     DCR_LAUNCH_CHECK();
     return 0;
 }

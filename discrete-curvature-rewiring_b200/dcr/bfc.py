@@ -211,22 +211,30 @@ def paper_flavour(csr: DeviceCSR, rank: int = 0, world: int = 1, ws: PaperWorksp
             "sq_j": ws.sq_j[:count], "gamma": ws.gamma[:count], "bfc": ws.bfc[:count], "ws": ws}
 
 
-def unshard(gathered: torch.Tensor, world: int, chunk: int, n_edges: int, out: PaperWorkspace | None = None,
-            csr: DeviceCSR | None = None) -> dict:
-    """Full-graph arrays (indexed by edge id) from the all-gathered per-rank blocks."""
+def unshard_outputs(n_edges: int, device) -> dict:
+    """Pre-allocated full-graph arrays for :func:`unshard` (one allocation per graph, not per pass)."""
+    c = max(int(n_edges), 1)
+    return {"tri": torch.empty(c, dtype=torch.int32, device=device), "sq_i": torch.empty(c, dtype=torch.int32, device=device),
+            "sq_j": torch.empty(c, dtype=torch.int32, device=device), "gamma": torch.empty(c, dtype=torch.int32, device=device),
+            "bfc": torch.empty(c, dtype=torch.float64, device=device)}
+
+
+def unshard(gathered: torch.Tensor, world: int, chunk: int, n_edges: int, out: dict | None = None) -> dict:
+    """Full-graph arrays (indexed by edge id) from the all-gathered per-rank blocks of the strided NCCL route."""
     lib = L.load()
-    dev = gathered.device
-    c = max(n_edges, 1)
-    tri = torch.empty(c, dtype=torch.int32, device=dev)
-    sq_i = torch.empty(c, dtype=torch.int32, device=dev)
-    sq_j = torch.empty(c, dtype=torch.int32, device=dev)
-    gamma = torch.empty(c, dtype=torch.int32, device=dev)
-    val = torch.empty(c, dtype=torch.float64, device=dev)
-    L.check(lib.dcr_bfc_paper_unshard(gathered.data_ptr(), int(world), int(chunk), int(n_edges), tri.data_ptr(),
-                                      sq_i.data_ptr(), sq_j.data_ptr(), gamma.data_ptr(), val.data_ptr(),
+    o = out if out is not None else unshard_outputs(n_edges, gathered.device)
+    L.check(lib.dcr_bfc_paper_unshard(gathered.data_ptr(), int(world), int(chunk), int(n_edges), o["tri"].data_ptr(),
+                                      o["sq_i"].data_ptr(), o["sq_j"].data_ptr(), o["gamma"].data_ptr(), o["bfc"].data_ptr(),
                                       L.current_stream()), "dcr_bfc_paper_unshard")
-    return {"tri": tri[:n_edges], "sq_i": sq_i[:n_edges], "sq_j": sq_j[:n_edges], "gamma": gamma[:n_edges],
-            "bfc": val[:n_edges]}
+    return {k: o[k][:n_edges] for k in ("tri", "sq_i", "sq_j", "gamma", "bfc")}
+
+
+def set_paper_mode(mode: str) -> str:
+    """Membership structures of the paper-flavour kernels: ``"auto"`` (exact shared-memory bitmap up to 262144 nodes) or
+    ``"hashed"`` (always the hashed bitmap + table of larger graphs — what the parity tests use to cover both paths).
+    Returns the previous mode."""
+    old = L.load().dcr_bfc_paper_set_mode(1 if mode == "hashed" else 0)
+    return "hashed" if old else "auto"
 
 
 def scatter_dense(csr: DeviceCSR, vals: torch.Tensor, C: torch.Tensor) -> torch.Tensor:

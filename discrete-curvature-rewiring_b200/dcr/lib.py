@@ -47,6 +47,16 @@ SIGNATURES = {
     "dcr_bfc_paper_scratch_bytes": (_L, [_I, _I, _L]),
     "dcr_bfc_paper": (_I, [_P, _P, _I, _I, _P, _P, _L, _L, _L, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "dcr_bfc_paper_unshard": (_I, [_P, _I, _L, _L, _P, _P, _P, _P, _P, _P]),
+    "dcr_bfc_paper_set_mode": (_I, [_I]),
+    "dcr_bfc_paper_edge_cost": (_I, [_P, _P, _I, _P, _P, _L, _P, _P, _P]),
+    "dcr_comm_create": (_I, [_I, _I, _L, C.POINTER(_P)]),
+    "dcr_comm_handle": (_I, [_P, _P]),
+    "dcr_comm_connect": (_I, [_P, _P]),
+    "dcr_comm_buffer": (_P, [_P]),
+    "dcr_comm_chunk": (_L, [_P]),
+    "dcr_comm_error": (_I, [_P]),
+    "dcr_comm_destroy": (_I, [_P]),
+    "dcr_bfc_paper_sharded": (_I, [_P, _P, _I, _I, _P, _P, _L, _L, _P, _P, _L, _P, _P, _P]),
     "dcr_post_delta": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P]),
     "dcr_sdrf_create": (_I, [_I, _P, _P, _L, C.POINTER(_P)]),
     "dcr_sdrf_destroy": (None, [_P]),

@@ -112,8 +112,9 @@ int dcr_bfc_cuda_dense_small(const float* A, int n, float* C, int32_t* flags, vo
  * run tables, and the global-memory match hashes: a few hundred MB for the benchmark graphs; contents need not be
  * preserved or initialised between calls); max_degree = the largest row length of the CSR.
  * Graphs of up to 262144 nodes use an exact shared-memory bitmap of the tested endpoint's neighbours, larger ones a
- * hashed bitmap + table; the environment variable DCR_PAPER_MODE=hashed (read on every call) forces the latter —
- * results are identical, the parity tests run both.
+ * hashed bitmap + table (dcr_bfc_paper_set_mode forces the latter; results are identical, the parity tests run both).
+ * Threading: passes on the same device are serialised while they enqueue (a per-device mutex guards the fork/join
+ * streams of the pass); passes on different devices are independent.
  * ---------------------------------------------------------------------------------------------------------- */
 int64_t dcr_bfc_paper_scratch_bytes(int n, int max_degree, int64_t count);
 int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree, const int32_t* esrc,
@@ -123,7 +124,44 @@ int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n, int max_d
 /* ev_edge_begin / ev_edge_end: optional cudaEvent_t (NULL = none) recorded on `stream` around the edge kernels
  * (the gather-bound part; the planning kernels before them are O(E)) — used by bench.py for the roofline. */
 
-/* Multi-GPU epilogue: `gathered` = the all-gathered per-rank result blocks, rank r's block at byte offset
+/* Membership mode of dcr_bfc_paper: 0 = automatic (exact shared-memory bitmap of the tested endpoint's neighbours for
+ * graphs of up to 262144 nodes, hashed bitmap + table beyond), 1 = always the hashed structures.  Results are identical;
+ * the parity tests run both.  Process-wide; returns the previous mode.  The initial mode is 0 unless the environment
+ * variable DCR_PAPER_MODE=hashed was set when the library was loaded. */
+int dcr_bfc_paper_set_mode(int mode);
+
+/* Work estimate per undirected edge (entries streamed + per-head + per-edge terms) for cutting the edge list into
+ * contiguous ranges of equal work (one range per GPU).  node_s_scratch: n int64 of device scratch. */
+int dcr_bfc_paper_edge_cost(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc, const int32_t* edst,
+                            int64_t n_edges, int64_t* out_cost, int64_t* node_s_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU full-graph BFC over contiguous edge ranges (north_star: "shards naturally by edge
+ * range ... curvature shards all-gathered over NVLink").  The reference has no multi-GPU path; this replaces what a
+ * caller would otherwise do with bfc_naive.bfc (curvature/bfc_naive.py:43-52) per shard plus an all-gather.
+ * A dcr_comm owns, on this rank's GPU, the FULL result arrays indexed by edge id — bfc f64[chunk] | tri | sq_i | sq_j |
+ * gamma int32[chunk], chunk = dcr_comm_chunk() >= n_edges — in one cudaMalloc'ed buffer that the peer ranks map through
+ * CUDA IPC (NVLink / NVSwitch peer memory).  dcr_bfc_paper_sharded computes the edges [e_lo, e_lo + count) and its
+ * closing kernel stores every result at the edge's position in EVERY rank's buffer (compute + all-gather fused, no
+ * staging copy, no re-interleave); device-side flags order it against the peers (no host synchronisation).  When the
+ * work enqueued by the call has run, the local buffer holds the results of ALL ranks' ranges for this pass.  Every rank
+ * must make the same sequence of calls.  world == 1 needs no connect.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dcr_comm dcr_comm;
+int dcr_comm_create(int rank, int world, int64_t n_edges, dcr_comm** out);
+/* 64-byte CUDA IPC handle of this rank's buffer (host memory) — exchange them with any host-side all-gather */
+int dcr_comm_handle(dcr_comm* comm, void* handle64_host);
+/* handles_host: world x 64 bytes, rank r's handle at offset 64*r; maps the peers' buffers */
+int dcr_comm_connect(dcr_comm* comm, const void* handles_host);
+void* dcr_comm_buffer(dcr_comm* comm);          /* device pointer of the local result buffer */
+int64_t dcr_comm_chunk(dcr_comm* comm);         /* entries per array inside the buffer */
+int dcr_comm_error(dcr_comm* comm);             /* synchronises; non-zero if a hand-shake timed out (a peer never arrived) */
+int dcr_comm_destroy(dcr_comm* comm);
+int dcr_bfc_paper_sharded(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree, const int32_t* esrc,
+                          const int32_t* edst, int64_t e_lo, int64_t count, dcr_comm* comm, void* scratch,
+                          int64_t scratch_bytes, void* ev_edge_begin, void* ev_edge_end, void* stream);
+
+/* Multi-GPU epilogue of the NCCL route (strided shards): `gathered` = the all-gathered per-rank result blocks, rank r's block at byte offset
  * r*chunk*24 laid out as bfc[chunk] f64 | tri[chunk] | sq_i[chunk] | sq_j[chunk] | gamma[chunk] int32, where
  * local index t of rank r is edge e = r + t*world.  Writes the full-graph arrays indexed by edge id. */
 int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t chunk, int64_t n_edges, int32_t* out_tri,

@@ -94,3 +94,81 @@ def test_shard_geometry_covers_every_edge_once():
             if n_edges <= 295:
                 blocks = [list(range(r, n_edges, world)) for r in range(world)]
                 assert interleave_reference(blocks, n_edges) == list(range(n_edges))
+
+
+# ---- contiguous work-balanced ranges (the peer-memory route): host logic over gloo --------------------------------
+def _edge_cost_host(rowptr, col, esrc, edst):
+    """numpy restatement of edge_cost_kernel (dcr_bfc_paper.cu)."""
+    deg = np.diff(rowptr.astype(np.int64))
+    rows = np.repeat(np.arange(deg.size), deg)
+    S = np.bincount(rows, weights=deg[col].astype(np.float64), minlength=deg.size).astype(np.int64)
+    di, dj = deg[esrc], deg[edst]
+    ca, cb = S[edst] - di, S[esrc] - dj
+    sw = cb < ca
+    cost = np.where(sw, cb, ca) + 24 * np.where(sw, di, dj) + 160
+    return np.where(np.minimum(di, dj) <= 1, 2, cost).astype(np.int64)
+
+
+def _range_worker(rank, world, port, out_path):
+    for p in (PKG, REPO):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dcr import graph
+        from dcr.dist import balanced_bounds
+        from dcr.synth import named_graph
+        from oracle.paper_flavour import bfc_paper
+        ei, n = named_graph("wisconsin")
+        rowptr, col = graph.undirected_csr(ei, n)
+        m = ei[0] < ei[1]
+        esrc, edst = ei[0][m], ei[1][m]
+        cost = _edge_cost_host(rowptr, col, esrc, edst)
+        b = balanced_bounds(np.cumsum(cost), world)
+        # every rank derives the same cuts
+        got = [None] * world
+        dist.all_gather_object(got, b)
+        assert all(g == b for g in got)
+        lo, hi = b[rank], b[rank + 1]
+        # each rank computes its contiguous range with the oracle and writes it at the edges' own positions of a full
+        # block (what the closing kernel does through peer memory); summing the blocks = the gather
+        ref = bfc_paper(ei, n)
+        E = len(ref["bfc"])
+        full = torch.zeros(E, dtype=torch.float64)
+        full[lo:hi] = torch.from_numpy(ref["bfc"][lo:hi])
+        owner = torch.zeros(E, dtype=torch.int32)
+        owner[lo:hi] = 1
+        dist.all_reduce(full)
+        dist.all_reduce(owner)
+        assert bool((owner == 1).all())                    # the ranges tile [0, E) exactly once
+        assert np.array_equal(full.numpy(), ref["bfc"])
+        if rank == 0:
+            work = [int(cost[b[r]:b[r + 1]].sum()) for r in range(world)]
+            np.save(out_path, np.array(work))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_contiguous_ranges_world2_gloo(tmp_path):
+    out = str(tmp_path / "work.npy")
+    mp.spawn(_range_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    work = np.load(out)
+    assert work.min() > 0 and work.max() / work.sum() < 0.6          # two ranks: neither holds more than 60 % of the work
+
+
+def test_balanced_bounds_properties():
+    sys.path.insert(0, PKG)
+    from dcr.dist import balanced_bounds
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        cost = rng.integers(1, 1000, size=5000).astype(np.int64)
+        cost[rng.integers(0, 5000, size=20)] = 200000                # hubs
+        pre = np.cumsum(cost)
+        b = balanced_bounds(pre, world)
+        assert b[0] == 0 and b[-1] == 5000 and all(b[k] <= b[k + 1] for k in range(world))
+        work = np.array([cost[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert work.max() <= pre[-1] / world + cost.max()             # no range exceeds its share by more than one edge
+        assert balanced_bounds(torch.from_numpy(pre), world) == b     # torch and numpy inputs agree
+    assert balanced_bounds(np.zeros(0, dtype=np.int64), 4) == [0, 0, 0, 0, 0]

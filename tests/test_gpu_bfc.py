@@ -12,15 +12,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(params=["auto", "hashed"])
-def paper_mode(request, monkeypatch):
+def paper_mode(request):
     """Both membership structures of the paper-flavour kernels: ``auto`` picks the exact shared-memory bitmap of
     N(a) (every graph here has n <= DENSE_MAX_N), ``hashed`` forces the hashed-bitmap + table kernels that graphs
-    with more nodes take (dcr_bfc_paper.cu reads DCR_PAPER_MODE on every call)."""
-    if request.param == "hashed":
-        monkeypatch.setenv("DCR_PAPER_MODE", "hashed")
-    else:
-        monkeypatch.delenv("DCR_PAPER_MODE", raising=False)
-    return request.param
+    with more nodes take (``dcr_bfc_paper_set_mode``, per call — no environment variable involved)."""
+    from dcr import bfc
+    old = bfc.set_paper_mode(request.param)
+    yield request.param
+    bfc.set_paper_mode(old)
 
 
 def _csr(ei, n):
@@ -286,6 +285,65 @@ def test_dense_roundtrip_and_validation():
         bfc.DeviceCSR.from_dense(B)
 
 
+def test_full_size_squirrel_shape_every_edge_against_c_oracle(paper_mode):
+    """Config-4 size: all 198,000 edges against the plain-C restatement of bfc_naive.py, both membership modes."""
+    import os
+    from dcr import bfc, graph
+    from dcr.synth import named_graph
+    from oracle.c_port import bfc_paper_c
+    ei, n = named_graph("squirrel")
+    rowptr, col = graph.undirected_csr(ei, n)
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    out = bfc.paper_flavour(csr)
+    es, ed = out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4
+    ref = bfc_paper_c(rowptr, col, es, ed, threads=threads)
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        got = out[k].cpu().numpy()
+        assert np.array_equal(got, ref[k]), (k, int((got != ref[k]).sum()))
+
+
+def test_global_table_class_every_edge_against_c_oracle(paper_mode):
+    """The graph of the CTA-team test (a hub of degree ~17000: hashed mode takes the global-table kernel, class X): every
+    edge against the C oracle, not a sample."""
+    import os
+    from dcr import bfc, graph
+    from oracle.c_port import bfc_paper_c
+    rng = np.random.default_rng(5)
+    n = 20000
+    pairs = [(0, i) for i in range(1, 17000)] + [(1, i) for i in range(2, 9000)]
+    extra = rng.integers(0, n, size=(30000, 2))
+    ei = sym_edge_index(pairs + [tuple(p) for p in extra.tolist()], n)
+    rowptr, col = graph.undirected_csr(ei, n)
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    out = bfc.paper_flavour(csr)
+    es, ed = out["esrc"].cpu().numpy(), out["edst"].cpu().numpy()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4
+    ref = bfc_paper_c(rowptr, col, es, ed, threads=threads)
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        got = out[k].cpu().numpy()
+        assert np.array_equal(got, ref[k]), (k, int((got != ref[k]).sum()))
+
+
+def test_paper_flavour_golden_integer_fields(paper_mode):
+    """deg, #triangles, #squares_1, #squares_2, gamma read from the locals of the UNMODIFIED bfc_naive.bfc_edge
+    (tests/golden/generate_golden.py::gen_paper_ints) — the integer fields pinned by the reference itself, not only
+    through the oracle."""
+    z = golden("paper_ints_kat.npz")
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        if ei.shape[1] == 0:
+            continue
+        got = _paper_gpu(ei, n)
+        assert np.array_equal(got["edges"], z[f"{name}/edges"]), name
+        ints = z[f"{name}/ints"]
+        assert np.array_equal(got["tri"], ints[:, 2]), name
+        assert np.array_equal(got["sq_i"], ints[:, 3]), name
+        assert np.array_equal(got["sq_j"], ints[:, 4]), name
+        assert np.array_equal(got["gamma"], ints[:, 5]), name
+        assert np.array_equal(got["bfc"], z[f"{name}/bfc"]), name
+
+
 def test_full_size_properties_squirrel_shape():
     """Config-4 size: size-independent properties + oracle spot checks (the dense oracle is too slow here)."""
     from dcr import bfc
@@ -314,7 +372,7 @@ def test_full_size_properties_squirrel_shape():
 
 
 def test_sharded_path_single_process_matches_full():
-    """The N>1 code path (shared result block, gather buffer, unshard kernel) run as W emulated ranks on one GPU."""
+    """The NCCL-route code path (shared result block, gather buffer, unshard kernel) run as W emulated ranks on one GPU."""
     import torch
     from dcr import bfc
     from dcr.dist import chunk_size
@@ -330,9 +388,93 @@ def test_sharded_path_single_process_matches_full():
             ws = bfc.PaperWorkspace(csr, bfc.shard_count(E, r, world), chunk=chunk)
             bfc.paper_flavour(csr, rank=r, world=world, ws=ws)
             gathered[r * chunk * 24:(r + 1) * chunk * 24] = ws.block
-        out = bfc.unshard(gathered, world, chunk, E)
+        out = bfc.unshard(gathered, world, chunk, E, out=bfc.unshard_outputs(E, "cuda"))
         for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
             assert torch.equal(out[k], full[k]), (world, k)
+
+
+def test_contiguous_ranges_through_the_sharded_entry_point(paper_mode):
+    """dcr_bfc_paper_sharded over work-balanced contiguous ranges (the peer-memory route with the peers left out: W
+    emulated ranks, one after the other, each writing its range at the edges' own positions of ONE result buffer) ==
+    the single pass; also an empty range and the ShardedPaperBFC wrapper at world size 1."""
+    import torch
+    from dcr import bfc, dist as ddist
+    from dcr import lib as L
+    from dcr.synth import named_graph
+    for name in ("cora", "squirrel"):
+        ei, n = named_graph(name)
+        csr = _csr(ei, n)
+        full = bfc.paper_flavour(csr)
+        esrc, edst, _ = csr.undirected_edges()
+        E = full["count"]
+        cost = ddist.edge_cost(csr, esrc, edst)
+        lib = L.load()
+        for world in (3, 8):
+            b = ddist.balanced_bounds(torch.cumsum(cost, 0), world)
+            assert b[0] == 0 and b[-1] == E
+            work = [int(cost[b[r]:b[r + 1]].sum()) for r in range(world)]
+            assert max(work) <= sum(work) / world + int(cost.max())
+            comm = ddist.PeerComm(E, 0, 1)
+            nbytes = int(lib.dcr_bfc_paper_scratch_bytes(n, csr.max_degree, E))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            for r in list(range(world)) + [0]:                  # (+ a repeated range: the buffer is simply overwritten)
+                L.check(lib.dcr_bfc_paper_sharded(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), n, csr.max_degree,
+                                                  esrc.data_ptr(), edst.data_ptr(), b[r], b[r + 1] - b[r], comm.handle,
+                                                  scratch.data_ptr(), nbytes, 0, 0, L.current_stream()), "sharded")
+            L.check(lib.dcr_bfc_paper_sharded(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), n, csr.max_degree,
+                                              esrc.data_ptr(), edst.data_ptr(), b[1], 0, comm.handle,
+                                              scratch.data_ptr(), nbytes, 0, 0, L.current_stream()), "sharded (empty)")
+            torch.cuda.synchronize()
+            for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+                assert torch.equal(comm.views[k], full[k]), (name, world, k)
+            assert comm.error() == 0
+            comm.close()
+        sh = ddist.ShardedPaperBFC(csr)
+        assert sh.mode == "peer" and (sh.lo, sh.hi) == (0, E)
+        out = sh.run()
+        for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+            assert torch.equal(out[k], full[k]), (name, k)
+        sh.check()
+        sh.close()
+
+
+def test_host_end_to_end_pass_single_rank():
+    """HostShardedPaperBFC (pinned host CSR in, host result block out) at world size 1."""
+    import torch
+    from dcr import bfc, dist as ddist, graph
+    from dcr.synth import named_graph
+    ei, n = named_graph("cora")
+    rowptr, col = graph.undirected_csr(ei, n)
+    m = ei[0] < ei[1]
+    esrc, edst = ei[0][m].astype(np.int32), ei[1][m].astype(np.int32)
+    csr = bfc.DeviceCSR.from_host(rowptr, col)
+    full = bfc.paper_flavour(csr)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hs = ddist.HostShardedPaperBFC(n, col.size, esrc.size, csr.max_degree)
+    lo, hi = hs.run(pin(rowptr.astype(np.int32)), pin(col), pin(esrc), pin(edst))
+    torch.cuda.synchronize()
+    assert (lo, hi) == (0, esrc.size)
+    hv = hs.host_views()
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        assert np.array_equal(hv[k].numpy(), full[k].cpu().numpy()), k
+    hs.close()
+
+
+def test_two_gpus_peer_memory_exchange():
+    """The real thing when the box has two GPUs: two ranks under torchrun, peer-memory route and NCCL route, device and
+    host forms, every rank's full arrays compared with the single-GPU pass (tests/multi_gpu_worker.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(here, "multi_gpu_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "multi_gpu_worker ok" in r.stdout
 
 
 def test_tensor_core_support_matches_sparse_support():
