@@ -11,7 +11,7 @@
 // "support == 1" counts read at the matched positions.  One warp per directed entry; lanes take elements of the
 // shorter row (coalesced) and binary-search the longer one.  Memory-system bound (gathers served by L2);
 // algorithmic bytes per undirected edge: 16 + 4(d_i+d_j) + 8 tri + 24.
-#include "dcr_common.cuh"
+#include "dcr_directed.cuh"
 
 namespace dcr {
 
@@ -81,6 +81,31 @@ __global__ void __launch_bounds__(256) cuda_flavour_kernel(const int32_t* __rest
     }
 }
 
+// Asymmetric 0/1 adjacency (directed simple graph): the loop of bfc_cuda.py:31-44 evaluated sparsely by the
+// definition (dcr_directed.cuh).  One warp per entry i -> j of the successor CSR.
+__global__ void __launch_bounds__(256) cuda_flavour_directed_kernel(GraphView out, GraphView in, int n,
+                                                                    int32_t* __restrict__ tri_out,
+                                                                    int32_t* __restrict__ sharp_out,
+                                                                    int32_t* __restrict__ lam_out,
+                                                                    double* __restrict__ c64_out,
+                                                                    float* __restrict__ c32_out, int64_t lo, int64_t hi) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < hi; p += warps) {
+        const int i = row_of_entry(out.start, n, p);
+        const int j = out.col[p];
+        int sharp, lam, a2;
+        const Closing c = directed_entry_curvature(out, in, i, j, lane, &sharp, &lam, &a2);
+        if (lane == 0) {
+            if (tri_out) tri_out[p] = a2;
+            if (sharp_out) sharp_out[p] = sharp;
+            if (lam_out) lam_out[p] = lam;
+            if (c64_out) c64_out[p] = c.c64;
+            c32_out[p] = c.c32;
+        }
+    }
+}
+
 }  // namespace dcr
 
 using namespace dcr;
@@ -111,6 +136,19 @@ extern "C" int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx
     if (!c32) { set_error("dcr_bfc_cuda_flavour: c32 must not be NULL"); return 1; }
     cuda_flavour_kernel<<<grid_for_warps(entry_hi - entry_lo), 256, 0, (cudaStream_t)stream>>>(
         rowptr, colidx, n, tri, sharp, lam, c64, c32, entry_lo, entry_hi);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcr_bfc_cuda_flavour_directed(const int32_t* out_rowptr, const int32_t* out_colidx,
+                                             const int32_t* in_rowptr, const int32_t* in_colidx, int n, int32_t* tri,
+                                             int32_t* sharp, int32_t* lam, double* c64, float* c32, int64_t entry_lo,
+                                             int64_t entry_hi, void* stream) {
+    if (entry_hi <= entry_lo) return 0;
+    if (!c32) { set_error("dcr_bfc_cuda_flavour_directed: c32 must not be NULL"); return 1; }
+    GraphView out{out_rowptr, nullptr, out_colidx}, in{in_rowptr, nullptr, in_colidx};
+    cuda_flavour_directed_kernel<<<grid_for_warps(entry_hi - entry_lo), 256, 0, (cudaStream_t)stream>>>(
+        out, in, n, tri, sharp, lam, c64, c32, entry_lo, entry_hi);
     DCR_LAUNCH_CHECK();
     return 0;
 }

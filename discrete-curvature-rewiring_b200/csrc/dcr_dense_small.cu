@@ -6,8 +6,8 @@
 // bit-packed once (n/32 words per row: the graph lives in a few KB of L1/L2), and ONE kernel — a CTA per row —
 // computes, for every entry of the row that sits on an edge, the support |N(i) ∩ N(j)| as popc(row_i & row_j), the two
 // "support == 1" counts over the common neighbours (App. A.2) the same way, and the closing formula of the compiled
-// reference kernel; the other entries of the row are written as +0.0, so C needs no memset.  Two launches, no host
-// synchronisation before the result.
+// reference kernel; the other entries of the row are written as +0.0, so C needs no memset.  Two launches; when the
+// pack kernel finds A outside the covered domain (flags != 0) the second kernel writes nothing.
 #include "dcr_common.cuh"
 
 namespace dcr {
@@ -50,7 +50,9 @@ __device__ __forceinline__ int packed_support(const uint32_t* ru, const uint32_t
 
 // CTA per row i (4 warps): warps take the entries j of the row in turn
 __global__ void __launch_bounds__(128) dense_small_bfc_kernel(int n, int words, const uint32_t* __restrict__ bits,
-                                                              const int32_t* __restrict__ deg, float* __restrict__ C) {
+                                                              const int32_t* __restrict__ deg,
+                                                              const int32_t* __restrict__ flags, float* __restrict__ C) {
+    if (*flags) return;   // outside the covered domain (pack kernel's verdict): leave the caller's C untouched
     __shared__ uint32_t s_row[SMALL_MAX_WORDS];
     __shared__ uint32_t s_common[4][SMALL_MAX_WORDS];
     const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,7 +116,7 @@ extern "C" int dcr_bfc_cuda_dense_small(const float* A, int n, float* C, int32_t
     int32_t* deg = (int32_t*)(bits + (size_t)n * words);
     dense_small_pack_kernel<<<(unsigned)(((size_t)n * 32 + 127) / 128), 128, 0, st>>>(A, n, words, bits, deg, flags);
     DCR_LAUNCH_CHECK();
-    dense_small_bfc_kernel<<<n, 128, 0, st>>>(n, words, bits, deg, C);
+    dense_small_bfc_kernel<<<n, 128, 0, st>>>(n, words, bits, deg, flags, C);
     DCR_LAUNCH_CHECK();
     return 0;
 }

@@ -19,9 +19,18 @@
 #include <cmath>
 #include <vector>
 
-#include "dcr_score.cuh"
+#include "dcr_directed.cuh"
 
 namespace dcr {
+
+// Loop flavours (template parameter of the loop kernel; DCR_SDRF_MODE_* of dcr.h map onto them):
+//   LOOP_BFC       sdrf_cuda_bfc, is_undirected=True   (rewiring/sdrf_cuda_bfc.py:14-93) — symmetric arena, maintained
+//                  supports, closed-form curvature and scoring (dcr_score.cuh)
+//   LOOP_DIRECTED  sdrf_cuda_bfc, is_undirected=False  (:47-49, :72-73, :87-88) — rows [0,n) hold the successors,
+//                  rows [n,2n) the predecessors; curvature and scoring by the definition (dcr_directed.cuh)
+//   LOOP_CLASSICAL sdrf_no_cuda with '1d' / 'augmented' / 'haantjes' (rewiring/sdrf_no_cuda.py:9-68,
+//                  curvature/classical_curvatures.py:6-46) — integer curvatures from the maintained degrees / supports
+enum { LOOP_BFC = 0, LOOP_DIRECTED = 1, LOOP_CLASSICAL = 2 };
 
 #ifndef DCR_SDRF_THREADS
 #define DCR_SDRF_THREADS 1024
@@ -49,6 +58,8 @@ __device__ unsigned long long g_sdrf_phase[16];
 
 struct SdrfDev {
     int n;
+    int rows;             // n, or 2n for the directed loop (row n+v = predecessors of v)
+    int ctype;            // classical loop: 0 = '1d', 1 = 'augmented', 2 = 'haantjes'
     int cap_total;        // arena slots
     int row_cap_max;      // capacity of the per-row scratch arrays
     long long imp_cap;    // cells of the improvement scratch
@@ -333,6 +344,7 @@ __device__ __forceinline__ void push_dirty(const SdrfDev& S, int* counter, int a
 
 // Exact support update + dirty marking for toggling edge (k,l); the edge must currently be PRESENT in the arena.
 // delta = +1 after an insertion, -1 before a deletion.
+template <bool CLOSING_EDGES>
 __device__ void toggle_supports(const SdrfDev& S, const GraphView& g, int k, int l, int delta, int* dirty_count,
                                 LoopShared* sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -360,8 +372,9 @@ __device__ void toggle_supports(const SdrfDev& S, const GraphView& g, int k, int
         S.supp[edge_slot(g, k, l)] = nw;
         S.supp[edge_slot(g, l, k)] = nw;
     }
-    // edges (w,z) closing a triangle with (k,w) or (l,w)
-    for (int t = warp; t < nw; t += SDRF_WARPS) {
+    // edges (w,z) closing a triangle with (k,w) or (l,w): their "support == 1" counts may change (BFC only; the
+    // classical curvatures read nothing but the degrees and the support of the edge itself)
+    for (int t = warp; CLOSING_EDGES && t < nw; t += SDRF_WARPS) {
         const int w = S.wlist[t];
         const int sw = S.rstart[w], dw = S.rlen[w];
         for (int p = lane; p < dw; p += 32) {
@@ -389,6 +402,46 @@ __device__ __forceinline__ float entry_curvature(const SdrfDev& S, int a, int b,
     return closing_value(dmax, dmin, S.supp[slot_ab], 1, di_dj - ta - tb, dmax).c32;
 }
 
+// classical curvature of an entry from the maintained degrees / support (curvature/classical_curvatures.py:15-28);
+// small integers, exact in fp32
+__device__ __forceinline__ float classical_curvature(const SdrfDev& S, int a, int b, int slot_ab) {
+    const int base = 4 - S.rlen[a] - S.rlen[b];
+    if (S.ctype == 0) return (float)base;                         // '1d'
+    if (S.ctype == 1) return (float)(base + 3 * S.supp[slot_ab]);  // 'augmented'
+    return (float)S.supp[slot_ab];                                // 'haantjes'
+}
+
+// Directed loop: entries whose curvature may change when the entry k -> l is toggled (call while it is PRESENT).
+// C[i,j] reads d_in[i], d_out[j], N_out(i), N_in(j), A2[i,*] over N_in(j) and A2[*,j] over N_out(i)
+// (bfc_cuda.py:20-44); A2[a,b] changes iff (a = k and l -> b) or (b = l and a -> k).  Hence: the entries leaving k
+// and l, the entries arriving at k and l, and the entries i -> j with i -> k and l -> j.
+__device__ __forceinline__ void push_dirty_pair(const SdrfDev& S, int* counter, int a, int b) {
+    const int p = atomicAdd(counter, 1);
+    if (p < S.dirty_cap) {
+        S.dirty[2 * p] = a;
+        S.dirty[2 * p + 1] = b;
+    }
+}
+__device__ void directed_mark_dirty(const SdrfDev& S, int k, int l, int* dirty_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = S.n;
+    const int sok = S.rstart[k], nok = S.rlen[k], sol = S.rstart[l], nol = S.rlen[l];
+    const int sik = S.rstart[n + k], nik = S.rlen[n + k], sil = S.rstart[n + l], nil = S.rlen[n + l];
+    for (int t = threadIdx.x; t < nok; t += SDRF_THREADS) push_dirty_pair(S, dirty_count, k, S.col[sok + t]);
+    for (int t = threadIdx.x; t < nol; t += SDRF_THREADS) push_dirty_pair(S, dirty_count, l, S.col[sol + t]);
+    for (int t = threadIdx.x; t < nik; t += SDRF_THREADS) push_dirty_pair(S, dirty_count, S.col[sik + t], k);
+    for (int t = threadIdx.x; t < nil; t += SDRF_THREADS) push_dirty_pair(S, dirty_count, S.col[sil + t], l);
+    for (int t = warp; t < nik; t += SDRF_WARPS) {
+        const int i = S.col[sik + t];
+        const int soi = S.rstart[i], noi = S.rlen[i];
+        for (int p = lane; p < noi; p += 32) {
+            const int j = S.col[soi + p];
+            if (find_sorted(S.col, sol, nol, j) >= 0) push_dirty_pair(S, dirty_count, i, j);
+        }
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // initialisation kernels over arena slots (multi-CTA)
 // ------------------------------------------------------------------------------------------------------------
@@ -403,13 +456,23 @@ __global__ void sdrf_init_support_kernel(SdrfDev S, int top) {
         if (lane == 0) S.supp[s] = c;
     }
 }
+template <int MODE>
 __global__ void sdrf_init_curvature_kernel(SdrfDev S, int top) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < top; s += warps) {
         const int a = S.owner[s];
         if (a < 0) continue;
-        const float c = entry_curvature(S, a, S.col[s], s, lane);
+        float c;
+        if constexpr (MODE == LOOP_DIRECTED) {
+            if (a >= S.n) continue;                 // predecessor rows carry no curvature
+            const GraphView gout{S.rstart, S.rlen, S.col}, gin{S.rstart + S.n, S.rlen + S.n, S.col};
+            c = directed_entry_curvature(gout, gin, a, S.col[s], lane).c32;
+        } else if constexpr (MODE == LOOP_CLASSICAL) {
+            c = classical_curvature(S, a, S.col[s], s);
+        } else {
+            c = entry_curvature(S, a, S.col[s], s, lane);
+        }
         if (lane == 0) S.c32[s] = c;
     }
 }
@@ -417,14 +480,17 @@ __global__ void sdrf_init_curvature_kernel(SdrfDev S, int top) {
 // ------------------------------------------------------------------------------------------------------------
 // the loop
 // ------------------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(SDRF_THREADS, 1)
-sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double tau, int tau_inf,
+sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double bound64, double tau, int tau_inf,
                  const double* __restrict__ uniforms, long long n_uniforms, int forced_choice, double guard,
                  int32_t* __restrict__ log, dcr_sdrf_result* __restrict__ result) {
     __shared__ LoopShared sh;
-    __shared__ int dirty_count, work_count;
+    __shared__ DirScoreShared dsh;
+    __shared__ int dirty_count, work_count, dred[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GraphView g{S.rstart, S.rlen, S.col};
+    GraphView g{S.rstart, S.rlen, S.col};                       // undirected adjacency / successors
+    GraphView gin{S.rstart + S.n, S.rlen + S.n, S.col};         // predecessors (directed loop only)
     ScoreScratch sc{S.base1, S.base2, S.posI, S.posJ};
     int it = 0, draws = 0;
     if (tid == 0) { sh.status = DCR_SDRF_OK; sh.stop = 0; }
@@ -434,10 +500,62 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
     long long tick__ = clock64();
 #endif
     for (; it < loops; ++it) {
+        const int top = S.scalars[0];
+        if constexpr (MODE == LOOP_CLASSICAL) {
+            // ---- 1c. min(G.edges, key=curvature) / max(...) (sdrf_no_cuda.py:27, :59-61) --------------------
+            // G.edges lists every edge once, from its first endpoint in node order, neighbours in insertion order:
+            // the first minimum is at the smallest u that has an entry (u, v > u) with the minimal value, and among
+            // those at the earliest position of u's insertion-order row.  The maximum is taken over the same C_t
+            // (curv_dict predates the addition; the new edge is excluded, :59).
+            float vmin = INFINITY, vmax = -INFINITY;
+            for (int s = tid; s < top; s += SDRF_THREADS) {
+                if (S.owner[s] < 0) continue;
+                const float v = S.c32[s];
+                vmin = fminf(vmin, v);
+                vmax = fmaxf(vmax, v);
+            }
+            vmin = block_best(Best{vmin, 0ull}, &sh.red).v;
+            vmax = -block_best(Best{-vmax, 0ull}, &sh.red).v;
+            if (!(vmin <= vmax)) {                              // no edges: min() of an empty sequence
+                if (tid == 0) sh.status = DCR_SDRF_EMPTY_GRAPH;
+                __syncthreads();
+                break;
+            }
+            unsigned long long umin = ~0ull, umax = ~0ull;
+            for (int s = tid; s < top; s += SDRF_THREADS) {
+                const int o = S.owner[s];
+                if (o < 0 || S.col[s] < o) continue;
+                const float v = S.c32[s];
+                if (v == vmin) umin = min(umin, (unsigned long long)o);
+                if (v == vmax) umax = min(umax, (unsigned long long)o);
+            }
+            const int xu = (int)block_best(Best{0.0f, umin}, &sh.red).key;
+            const int xru = (int)block_best(Best{0.0f, umax}, &sh.red).key;
+            unsigned long long pmin = ~0ull, pmax = ~0ull;
+            {
+                const int st = S.rstart[xu], len = S.rlen[xu];
+                for (int t = tid; t < len; t += SDRF_THREADS) {
+                    const int v = S.ord[st + t];
+                    if (v > xu && S.c32[find_sorted(S.col, st, len, v)] == vmin) pmin = min(pmin, (unsigned long long)t);
+                }
+                const int st2 = S.rstart[xru], len2 = S.rlen[xru];
+                for (int t = tid; t < len2; t += SDRF_THREADS) {
+                    const int v = S.ord[st2 + t];
+                    if (v > xru && S.c32[find_sorted(S.col, st2, len2, v)] == vmax) pmax = min(pmax, (unsigned long long)t);
+                }
+            }
+            pmin = block_best(Best{0.0f, pmin}, &sh.red).key;
+            pmax = block_best(Best{0.0f, pmax}, &sh.red).key;
+            if (tid == 0) {
+                sh.have_min = 1; sh.have_max = 1;
+                sh.x = xu;  sh.y = S.ord[S.rstart[xu] + (int)pmin];   sh.cxy = vmin;
+                sh.xr = xru; sh.yr = S.ord[S.rstart[xru] + (int)pmax]; sh.cmax = vmax;
+            }
+        } else {
         // ---- 1. argmin / argmax of C_t (sdrf_cuda_bfc.py:40-42, :80-82) ---------------------------------
         // Pass 1 reads only the curvatures (free slots hold 0, which is neither < 0 nor > 0) and reduces the two
         // extreme VALUES; pass 2 visits the few slots that attain them and reduces the first row-major key.
-        const int top = S.scalars[0];
+        // (Directed loop: predecessor rows keep c32 = 0, so only successor entries can attain an extreme.)
         float vmin = 0.0f, vmax = 0.0f;
         for (int s = tid; s < top; s += SDRF_THREADS) {
             const float v = S.c32[s];
@@ -473,10 +591,13 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             sh.xr = sh.have_max ? (int)(bmax.key >> 32) : 0;
             sh.yr = sh.have_max ? (int)(bmax.key & 0xffffffffu) : 0;
             sh.cmax = sh.have_max ? -bmax.v : 0.0f;
+        }
+        }
+        if (tid == 0) {
             sh.can_add = 1; sh.do_remove = 0; sh.k = -1; sh.l = -1; sh.choice = -1; sh.chosen_flat = -1;
             sh.found_flat = 0x7fffffffffffffffLL;
-            sh.n_i = S.rlen[sh.x] + 1;
-            sh.n_j = S.rlen[sh.y] + 1;
+            sh.n_i = S.rlen[sh.x] + 1;                                        // successors of x (:45 / :48)
+            sh.n_j = S.rlen[(MODE == LOOP_DIRECTED ? S.n : 0) + sh.y] + 1;    // neighbours / predecessors of y (:46 / :49)
         }
         __syncthreads();
         const int x = sh.x, y = sh.y;
@@ -489,16 +610,33 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
         }
         SDRF_TICK(0);   // argmin/argmax
         // ---- 2. candidate matrix in networkx order (:45-54) and improvements (:57-62) ------------------
-        const int ox = S.rstart[x], oy = S.rstart[y];
+        const int ox = S.rstart[x], oy = S.rstart[(MODE == LOOP_DIRECTED ? S.n : 0) + y];
         auto nbI = [=](int I) { return I < n_i - 1 ? S.ord[ox + I] : x; };
         auto nbJ = [=](int J) { return J < n_j - 1 ? S.ord[oy + J] : y; };
-        score_prepare(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score);
         {
             const float cxy = sh.cxy;
             uint32_t* imp = S.imp;
-            score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, [=](int I, int J, float d) {
+            auto put = [=](int I, int J, float d) {
                 imp[(long long)I * n_j + J] = (d == MASKED_D) ? IMP_MASKED : __float_as_uint(__fsub_rn(d, cxy));
-            }, n_i - 1, n_j - 1);
+            };
+            if constexpr (MODE == LOOP_BFC) {
+                score_prepare(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score);
+                score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, put, n_i - 1, n_j - 1);
+            } else if constexpr (MODE == LOOP_DIRECTED) {
+                directed_score_prepare(g, gin, x, y, nbI, n_i, nbJ, n_j, sc, &dsh, dred);
+                directed_score_cells(g, gin, x, y, nbI, n_i, nbJ, n_j, sc, &dsh, put);
+            } else {
+                // sdrf_no_cuda.py:41-46 in closed form: adding (i,j) changes curvature(x,y) only when it touches x or y.
+                // i == x (then j in N(y)\N(x)): deg x + 1 and one more triangle; j == y mirrored; every other
+                // candidate leaves both degrees and the common neighbours alone.
+                const float special = S.ctype == 0 ? -1.0f : (S.ctype == 1 ? 2.0f : 1.0f);
+                for (long long c = tid; c < cells; c += SDRF_THREADS) {
+                    const int I = (int)(c / n_j), J = (int)(c - (long long)I * n_j);
+                    const int i = nbI(I), j = nbJ(J);
+                    const bool masked = (i == j) || edge_slot(g, i, j) >= 0;       // :34
+                    imp[c] = masked ? IMP_MASKED : __float_as_uint((i == x || j == y) ? special : 0.0f);
+                }
+            }
         }
         __syncthreads();
         SDRF_TICK(1);   // scoring
@@ -621,8 +759,10 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
             ++draws;
             if (tid == 0) {
                 const long long f = sh.chosen_flat;
-                sh.k = nbI((int)(f / n_j));
-                sh.l = nbJ((int)(f % n_j));
+                const int ck = nbI((int)(f / n_j)), cl = nbJ((int)(f % n_j));
+                const bool swap = (MODE == LOOP_CLASSICAL) && ck > cl;           // sorted(...) (sdrf_no_cuda.py:37,50)
+                sh.k = swap ? cl : ck;
+                sh.l = swap ? ck : cl;
             }
         } else {
             if (tid == 0) { sh.can_add = 0; if (!remove_edges) sh.stop = 1; }   // :74-77
@@ -631,7 +771,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
         SDRF_TICK(2);   // selection
         // ---- removal decision on the SAME C_t (:79-91) --------------------------------------------------
         if (tid == 0 && remove_edges && !sh.stop) {
-            if (sh.cmax > bound32) {                   // fp32 compare: torch casts the Python float (:83)
+            // BFC: fp32 compare, torch casts the Python float (:83); classical: Python int > float (sdrf_no_cuda.py:62)
+            const bool above = (MODE == LOOP_CLASSICAL) ? ((double)sh.cmax > bound64) : (sh.cmax > bound32);
+            if (above) {
                 if (!sh.have_max) sh.status = DCR_SDRF_REMOVE_NONEDGE;   // (0,0) fallback beat a negative bound
                 else sh.do_remove = 1;
             } else if (!sh.can_add) {
@@ -644,26 +786,29 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
         if (tid == 0) { dirty_count = 0; work_count = 0; }
         __syncthreads();
         const int k = sh.k, l = sh.l;
+        constexpr int L_ROW = (MODE == LOOP_DIRECTED);  // directed: the mirror entry lives in the predecessor rows
         if (k >= 0) {                                   // :69-73
             bool ok = row_insert(S, k, l, &sh);
-            ok = ok && row_insert(S, l, k, &sh);
+            ok = ok && row_insert(S, L_ROW * S.n + l, k, &sh);
             if (!ok) {
                 if (tid == 0) sh.status = DCR_SDRF_ARENA_FULL;
                 __syncthreads();
                 break;
             }
-            if (tid == 0) S.scalars[1] += 2;
+            if (tid == 0) S.scalars[1] += L_ROW ? 1 : 2;
             __syncthreads();
             SDRF_TICK(3);   // insert rows
-            toggle_supports(S, g, k, l, +1, &dirty_count, &sh);
+            if constexpr (MODE == LOOP_DIRECTED) directed_mark_dirty(S, k, l, &dirty_count);
+            else toggle_supports<MODE == LOOP_BFC>(S, g, k, l, +1, &dirty_count, &sh);
             SDRF_TICK(4);   // supports + dirty (add)
         }
         if (sh.do_remove) {                             // :84-88
             const int xr = sh.xr, yr = sh.yr;
-            toggle_supports(S, g, xr, yr, -1, &dirty_count, &sh);
+            if constexpr (MODE == LOOP_DIRECTED) directed_mark_dirty(S, xr, yr, &dirty_count);
+            else toggle_supports<MODE == LOOP_BFC>(S, g, xr, yr, -1, &dirty_count, &sh);
             row_delete(S, xr, yr, &sh);
-            row_delete(S, yr, xr, &sh);
-            if (tid == 0) S.scalars[1] -= 2;
+            row_delete(S, L_ROW * S.n + yr, xr, &sh);
+            if (tid == 0) S.scalars[1] -= L_ROW ? 1 : 2;
             __syncthreads();
         }
         SDRF_TICK(5);   // removal: supports + delete rows
@@ -684,10 +829,13 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double t
         for (int t = warp; t < nwk; t += SDRF_WARPS) {
             const int s = S.work[t];
             const int a = S.owner[s], b = S.col[s];
-            const float c = entry_curvature(S, a, b, s, lane);
+            float c;
+            if constexpr (MODE == LOOP_DIRECTED) c = directed_entry_curvature(g, gin, a, b, lane).c32;
+            else if constexpr (MODE == LOOP_CLASSICAL) c = classical_curvature(S, a, b, s);
+            else c = entry_curvature(S, a, b, s, lane);
             if (lane == 0) {
                 S.c32[s] = c;
-                S.c32[edge_slot(g, b, a)] = c;          // symmetric A: C[b,a] == C[a,b] bit for bit
+                if (MODE != LOOP_DIRECTED) S.c32[edge_slot(g, b, a)] = c;   // symmetric A: C[b,a] == C[a,b] bit for bit
                 S.flag[s] = 0;
             }
         }
@@ -758,6 +906,7 @@ struct dcr_sdrf {
     SdrfDev dev;
     void* slab;           // one allocation backing every array
     int32_t pending_n;
+    int mode;             // DCR_SDRF_MODE_*
 };
 
 template <class T>
@@ -767,30 +916,41 @@ static T* carve(char*& p, size_t count) {
     return out;
 }
 
-extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host, int64_t max_additions,
-                               dcr_sdrf** out) {
+// rows [0,n): rowptr/order (neighbours, or successors in the directed mode); rows [n,2n): in_rowptr/in_order
+// (predecessors, directed mode only)
+static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const int32_t* order_host,
+                            const int32_t* in_rowptr_host, const int32_t* in_order_host, int64_t max_additions,
+                            dcr_sdrf** out) {
     if (n <= 0 || !rowptr_host || !out) { set_error("dcr_sdrf_create: bad arguments"); return 1; }
+    if (mode < DCR_SDRF_MODE_BFC || mode > DCR_SDRF_MODE_HAANTJES) { set_error("dcr_sdrf_create: unknown mode"); return 1; }
+    const bool directed = mode == DCR_SDRF_MODE_BFC_DIRECTED;
+    if (directed && !in_rowptr_host) { set_error("dcr_sdrf_create: the directed mode needs the predecessor lists"); return 1; }
+    const int rows = directed ? 2 * n : n;
     const int64_t nnz = rowptr_host[n];
-    std::vector<int32_t> rstart(n), rlen(n), rcap(n);
+    if (directed && in_rowptr_host[n] != nnz) { set_error("dcr_sdrf_create: successor / predecessor lists disagree"); return 1; }
+    auto row_len = [&](int r) { return r < n ? rowptr_host[r + 1] - rowptr_host[r] : in_rowptr_host[r - n + 1] - in_rowptr_host[r - n]; };
+    auto row_src = [&](int r) { return r < n ? order_host + rowptr_host[r] : in_order_host + in_rowptr_host[r - n]; };
+    std::vector<int32_t> rstart(rows), rlen(rows), rcap(rows);
     int64_t sum_cap = 0;
-    int max_deg = 0;
-    for (int v = 0; v < n; ++v) {
-        const int len = rowptr_host[v + 1] - rowptr_host[v];
+    int d1 = 0, d2 = 0;   // the two largest row lengths
+    for (int v = 0; v < rows; ++v) {
+        const int len = row_len(v);
         const int cap = len + std::max(2, len / 8);
         rstart[v] = (int32_t)sum_cap;
         rlen[v] = len;
         rcap[v] = cap;
         sum_cap += cap;
-        max_deg = std::max(max_deg, len);
+        if (len > d1) { d2 = d1; d1 = len; } else if (len > d2) d2 = len;
     }
     const int64_t cap_total = 5 * sum_cap + 8 * max_additions + 1024;
     if (cap_total > 0x7ffffff0LL) { set_error("dcr_sdrf_create: graph too large for a 32-bit arena"); return 1; }
     std::vector<int32_t> col(sum_cap, 0), ord(sum_cap, 0), owner(sum_cap, -1);
-    for (int v = 0; v < n; ++v) {
+    for (int v = 0; v < rows; ++v) {
         const int len = rlen[v];
-        const int32_t* src = order_host + rowptr_host[v];
+        const int32_t* src = row_src(v);
+        const int self = v < n ? v : v - n;
         for (int t = 0; t < len; ++t) {
-            if (src[t] < 0 || src[t] >= n || src[t] == v) { set_error("dcr_sdrf_create: bad neighbour id"); return 1; }
+            if (src[t] < 0 || src[t] >= n || src[t] == self) { set_error("dcr_sdrf_create: bad neighbour id"); return 1; }
             ord[rstart[v] + t] = src[t];
             col[rstart[v] + t] = src[t];
             owner[rstart[v] + t] = v;
@@ -799,17 +959,33 @@ extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t*
         for (int t = 1; t < len; ++t)
             if (col[rstart[v] + t] == col[rstart[v] + t - 1]) { set_error("dcr_sdrf_create: duplicate neighbour"); return 1; }
     }
+    if (directed) {   // the predecessor rows must be the transpose of the successor rows
+        for (int v = 0; v < n; ++v)
+            for (int t = 0; t < rlen[v]; ++t) {
+                const int w = col[rstart[v] + t];
+                const int32_t* b = col.data() + rstart[n + w];
+                if (!std::binary_search(b, b + rlen[n + w], v)) {
+                    set_error("dcr_sdrf_create: successor / predecessor lists disagree");
+                    return 1;
+                }
+            }
+    }
     dcr_sdrf* s = new dcr_sdrf();
+    s->mode = mode;
     SdrfDev& D = s->dev;
     D.n = n;
+    D.rows = rows;
+    D.ctype = mode >= DCR_SDRF_MODE_1D ? mode - DCR_SDRF_MODE_1D : 0;
     D.cap_total = (int)cap_total;
-    const int64_t row_cap_max = (int64_t)max_deg + max_additions + 2;
+    const int64_t row_cap_max = (int64_t)d1 + max_additions + 2;
     D.row_cap_max = (int)std::min<int64_t>(row_cap_max, 0x7ffffff0LL);
-    D.imp_cap = std::min<int64_t>(row_cap_max * row_cap_max, (int64_t)1 << 28);   // <= 1 GiB of fp32 cells
-    D.dirty_cap = (int)std::min<int64_t>(4 * cap_total + 64, 0x3ffffff0LL);
+    // candidate matrix: (deg x + 1)(deg y + 1) <= the product of the two longest rows after all additions
+    D.imp_cap = std::min<int64_t>(((int64_t)d1 + max_additions + 2) * ((int64_t)d2 + max_additions + 2), (int64_t)1 << 28);
+    // dirty pairs of one iteration: two toggles, each at most the entries at four rows + the closing edges
+    D.dirty_cap = (int)std::min<int64_t>(4 * (nnz + 2 * max_additions) + 4096, 0x3ffffff0LL);
     size_t bytes = 0;
     auto add = [&](size_t count, size_t elem) { bytes += (count * elem + 255) / 256 * 256; };
-    add(n, 4); add(n, 4); add(n, 4);                         // rstart rlen rcap
+    add(rows, 4); add(rows, 4); add(rows, 4);                // rstart rlen rcap
     for (int i = 0; i < 6; ++i) add(cap_total, 4);           // col ord supp c32 owner flag
     add(8, 4);                                               // scalars
     for (int i = 0; i < 4; ++i) add(D.row_cap_max, 4);       // base1 base2 posI posJ
@@ -819,7 +995,7 @@ extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t*
     cudaError_t e = cudaMalloc(&s->slab, bytes);
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(sdrf slab)", __FILE__, __LINE__); }
     char* p = (char*)s->slab;
-    D.rstart = carve<int32_t>(p, n); D.rlen = carve<int32_t>(p, n); D.rcap = carve<int32_t>(p, n);
+    D.rstart = carve<int32_t>(p, rows); D.rlen = carve<int32_t>(p, rows); D.rcap = carve<int32_t>(p, rows);
     D.col = carve<int32_t>(p, cap_total); D.ord = carve<int32_t>(p, cap_total);
     D.supp = carve<int32_t>(p, cap_total); D.c32 = carve<float>(p, cap_total);
     D.owner = carve<int32_t>(p, cap_total); D.flag = carve<int32_t>(p, cap_total);
@@ -837,9 +1013,9 @@ extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t*
         return cuda_fail(err, what, __FILE__, __LINE__);
     };
 #define SDRF_TRY(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return fail(e2, #call); } while (0)
-    SDRF_TRY(cudaMemcpy(D.rstart, rstart.data(), n * 4, cudaMemcpyHostToDevice));
-    SDRF_TRY(cudaMemcpy(D.rlen, rlen.data(), n * 4, cudaMemcpyHostToDevice));
-    SDRF_TRY(cudaMemcpy(D.rcap, rcap.data(), n * 4, cudaMemcpyHostToDevice));
+    SDRF_TRY(cudaMemcpy(D.rstart, rstart.data(), rows * 4, cudaMemcpyHostToDevice));
+    SDRF_TRY(cudaMemcpy(D.rlen, rlen.data(), rows * 4, cudaMemcpyHostToDevice));
+    SDRF_TRY(cudaMemcpy(D.rcap, rcap.data(), rows * 4, cudaMemcpyHostToDevice));
     SDRF_TRY(cudaMemset(D.owner, 0xff, cap_total * 4));
     SDRF_TRY(cudaMemset(D.flag, 0, cap_total * 4));
     SDRF_TRY(cudaMemset(D.supp, 0, cap_total * 4));
@@ -853,14 +1029,30 @@ extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t*
     SDRF_TRY(cudaMemcpy(D.scalars, scal, sizeof(scal), cudaMemcpyHostToDevice));
     if (sum_cap > 0) {
         const int ctas = (int)std::min<int64_t>((sum_cap + 7) / 8, (int64_t)sm_count() * 8);
-        sdrf_init_support_kernel<<<ctas, 256>>>(D, (int)sum_cap);
-        sdrf_init_curvature_kernel<<<ctas, 256>>>(D, (int)sum_cap);
+        if (directed) {
+            sdrf_init_curvature_kernel<LOOP_DIRECTED><<<ctas, 256>>>(D, (int)sum_cap);
+        } else {
+            sdrf_init_support_kernel<<<ctas, 256>>>(D, (int)sum_cap);
+            if (mode == DCR_SDRF_MODE_BFC) sdrf_init_curvature_kernel<LOOP_BFC><<<ctas, 256>>>(D, (int)sum_cap);
+            else sdrf_init_curvature_kernel<LOOP_CLASSICAL><<<ctas, 256>>>(D, (int)sum_cap);
+        }
         SDRF_TRY(cudaGetLastError());
     }
     SDRF_TRY(cudaDeviceSynchronize());
 #undef SDRF_TRY
     *out = s;
     return 0;
+}
+
+extern "C" int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host, int64_t max_additions,
+                               dcr_sdrf** out) {
+    return sdrf_create_impl(n, DCR_SDRF_MODE_BFC, rowptr_host, order_host, nullptr, nullptr, max_additions, out);
+}
+
+extern "C" int dcr_sdrf_create_mode(int n, int mode, const int32_t* rowptr_host, const int32_t* order_host,
+                                    const int32_t* in_rowptr_host, const int32_t* in_order_host,
+                                    int64_t max_additions, dcr_sdrf** out) {
+    return sdrf_create_impl(n, mode, rowptr_host, order_host, in_rowptr_host, in_order_host, max_additions, out);
 }
 
 extern "C" void dcr_sdrf_destroy(dcr_sdrf* s) {
@@ -874,9 +1066,15 @@ extern "C" int dcr_sdrf_run(dcr_sdrf* s, int loops, int remove_edges, double rem
                             dcr_sdrf_result* result, void* stream) {
     if (!s || !result || (loops > 0 && !log)) { set_error("dcr_sdrf_run: bad arguments"); return 1; }
     const int tau_inf = std::isinf(tau) && tau > 0;
-    sdrf_loop_kernel<<<1, SDRF_THREADS, 0, (cudaStream_t)stream>>>(s->dev, loops, remove_edges, (float)removal_bound,
-                                                                  tau, tau_inf, uniforms, (long long)n_uniforms,
-                                                                  forced_choice, guard, log, result);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SDRF_LAUNCH(MODE)                                                                                              \
+    sdrf_loop_kernel<MODE><<<1, SDRF_THREADS, 0, st>>>(s->dev, loops, remove_edges, (float)removal_bound, removal_bound, \
+                                                       tau, tau_inf, uniforms, (long long)n_uniforms, forced_choice,    \
+                                                       guard, log, result)
+    if (s->mode == DCR_SDRF_MODE_BFC) SDRF_LAUNCH(LOOP_BFC);
+    else if (s->mode == DCR_SDRF_MODE_BFC_DIRECTED) SDRF_LAUNCH(LOOP_DIRECTED);
+    else SDRF_LAUNCH(LOOP_CLASSICAL);
+#undef SDRF_LAUNCH
     DCR_LAUNCH_CHECK();
     return 0;
 }

@@ -8,8 +8,10 @@ converted on the device to a sorted CSR (one streaming pass), the hand-written s
 compute the same numbers from sorted-list intersections (or, in the dense regime, two tcgen05 int8 products), and the
 dense ``C`` / ``D`` the callers expect is written back; graphs of up to 1024 nodes skip the CSR altogether
 (bit-packed rows, one kernel).  Values are the fp32 numbers the compiled reference kernel stores (fp64 arithmetic, two fp32 roundings).
-Covered: symmetric 0/1 ``A`` without self-loops (what ``is_undirected=True`` produces, sdrf_cuda_bfc.py:26-29);
-anything else raises ``NotImplementedError`` — there is no CPU or dense fallback.
+Covered: 0/1 ``A`` without self-loops — symmetric (what ``is_undirected=True`` produces, sdrf_cuda_bfc.py:26-29) through
+the closed-form kernels, asymmetric (``is_undirected=False``) through the definitional directed kernels
+(csrc/dcr_directed.cuh); weighted ``A`` or a non-zero diagonal raise ``NotImplementedError`` — there is no CPU or dense
+fallback.
 """
 import torch
 
@@ -32,8 +34,12 @@ def balanced_forman_curvature(A, C=None):
             A = A.to(torch.float32).contiguous()
         if C is None:
             C = torch.empty(N, N, dtype=torch.float32, device=A.device)
-        return _bfc.cuda_flavour_dense_small(A, C)
-    csr = _bfc.DeviceCSR.from_dense(A)
+        if _bfc.cuda_flavour_dense_small(A, C) is not None:
+            return C
+        return _directed_curvature(A, C)             # asymmetric A
+    csr = _bfc.DeviceCSR.from_dense(A, validate="directed")
+    if csr.asymmetric:
+        return _directed_curvature(A, C)
     if _dense_regime(csr):
         out = _bfc.cuda_flavour_tc(csr, want_fields=False)     # A·A on the tensor cores (tcgen05 int8)
     else:
@@ -44,14 +50,25 @@ def balanced_forman_curvature(A, C=None):
     return C
 
 
+def _directed_curvature(A, C):
+    d = _bfc.DirectedCSR.from_dense(A)
+    out = _bfc.cuda_flavour_directed(d, want_fields=False)
+    if C is None:
+        C = torch.empty(A.shape[0], A.shape[0], dtype=torch.float32, device=A.device)
+    _bfc.scatter_dense(d.out, out["c32"], C)
+    return C
+
+
 def balanced_forman_post_delta(A, x, y, i_neighbors, j_neighbors, D=None):
-    csr = _bfc.DeviceCSR.from_dense(A)
-    tri = _bfc.support(csr)
+    csr = _bfc.DeviceCSR.from_dense(A, validate="directed")
     i_nb = torch.as_tensor(list(i_neighbors), dtype=torch.int32).to(A.device)
     j_nb = torch.as_tensor(list(j_neighbors), dtype=torch.int32).to(A.device)
     if D is None:
         D = torch.zeros(len(i_neighbors), len(j_neighbors), dtype=torch.float32, device=A.device)
     elif D.dtype != torch.float32 or not D.is_contiguous() or D.shape != (len(i_neighbors), len(j_neighbors)):
         raise ValueError("D must be a contiguous float32 [len(i_neighbors), len(j_neighbors)] tensor")
-    _bfc.post_delta(csr, tri, int(x), int(y), i_nb, j_nb, D)
+    if csr.asymmetric:
+        _bfc.post_delta_directed(_bfc.DirectedCSR.from_dense(A), int(x), int(y), i_nb, j_nb, D)
+    else:
+        _bfc.post_delta(csr, _bfc.support(csr), int(x), int(y), i_nb, j_nb, D)
     return D

@@ -22,6 +22,7 @@ class DeviceCSR:
             max_degree = int((rowptr[1:] - rowptr[:-1]).max().item()) if n > 0 else 0
         self.max_degree = int(max_degree)
         self._edges = None
+        self.asymmetric = False
 
     @classmethod
     def from_host(cls, rowptr: np.ndarray, colidx: np.ndarray, device="cuda") -> "DeviceCSR":
@@ -49,15 +50,19 @@ class DeviceCSR:
         rowptr[1:] = torch.cumsum(counts[:n], 0, dtype=torch.int32)
         host = torch.stack([rowptr[n], flags[0], counts[:n].max() if n else rowptr[n]]).cpu()
         nnz, fl, maxdeg = int(host[0]), int(host[1]), int(host[2])
+        if validate == "directed":
+            fl &= ~4                 # asymmetry is what the directed route is for
         if validate and fl:
             what = [s for b, s in ((1, "entries other than 0/1"), (2, "a non-zero diagonal (self-loops)"),
-                                   (4, "asymmetry (directed graph)")) if fl & b]
+                                   (4, "asymmetry (directed graph: use DirectedCSR)")) if fl & b]
             raise NotImplementedError(
-                "the B200 BFC kernels cover symmetric 0/1 adjacency without self-loops (is_undirected=True, the only "
-                "mode the reference's callers use); A has " + ", ".join(what))
+                "the B200 BFC kernels cover 0/1 adjacency without self-loops; A has " + ", ".join(what))
+        self_asym = bool(int(host[1]) & 4)
         colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=A.device)[:nnz]
         L.check(lib.dcr_dense_fill(A.data_ptr(), n, rowptr.data_ptr(), colidx.data_ptr(), st), "dcr_dense_fill")
-        return cls(rowptr, colidx, n, maxdeg)
+        out = cls(rowptr, colidx, n, maxdeg)
+        out.asymmetric = self_asym
+        return out
 
     def undirected_edges(self):
         """``(esrc, edst, entry)`` int32/int32/int64 device tensors: entries with row < col, in CSR order."""
@@ -148,12 +153,67 @@ def cuda_flavour_dense_small(A: torch.Tensor, C: torch.Tensor) -> torch.Tensor:
     flags.zero_()
     L.check(lib.dcr_bfc_cuda_dense_small(A.data_ptr(), n, C.data_ptr(), flags.data_ptr(), ws.data_ptr(), nbytes,
                                          L.current_stream()), "dcr_bfc_cuda_dense_small")
-    fl = int(flags.item())
+    fl = int(flags.item())       # the one host round trip of this path: the domain verdict of the pack kernel
+    if fl == 4:
+        return None              # asymmetric 0/1 A without self-loops: the caller takes the directed route; C is untouched
     if fl:
         raise NotImplementedError(
-            "the B200 BFC kernels cover symmetric 0/1 adjacency without self-loops (is_undirected=True, the only "
-            "mode the reference's callers use); A has " + ", ".join(s for b, s in _UNSUPPORTED if fl & b))
+            "the B200 BFC kernels cover 0/1 adjacency without self-loops; A has "
+            + ", ".join(s for b, s in _UNSUPPORTED if fl & b and b != 4))
     return C
+
+
+class DirectedCSR:
+    """Successor and predecessor CSRs (both sorted) of an asymmetric 0/1 adjacency without self-loops."""
+
+    def __init__(self, out: DeviceCSR, inn: DeviceCSR):
+        self.out, self.inn, self.n, self.nnz = out, inn, out.n, out.nnz
+
+    @classmethod
+    def from_dense(cls, A: torch.Tensor) -> "DirectedCSR":
+        if A.dtype != torch.float32 or not A.is_contiguous():
+            A = A.to(torch.float32).contiguous()
+        return cls(DeviceCSR.from_dense(A, validate="directed"), DeviceCSR.from_dense(A.t().contiguous(), validate=False))
+
+    @classmethod
+    def from_edge_index(cls, edge_index, n: int, device="cuda") -> "DirectedCSR":
+        """From a host ``[2, E]`` list of distinct directed edges without self-loops."""
+        ei = np.asarray(edge_index, dtype=np.int64)
+
+        def csr(src, dst):
+            key = np.unique(src * n + dst)
+            rowptr = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.bincount(key // n, minlength=n), out=rowptr[1:])
+            return DeviceCSR.from_host(rowptr.astype(np.int32), (key % n).astype(np.int32), device)
+        return cls(csr(ei[0], ei[1]), csr(ei[1], ei[0]))
+
+
+def cuda_flavour_directed(d: DirectedCSR, want_fields: bool = True) -> dict:
+    """cuda-flavour BFC of a directed simple graph per successor entry (curvature/bfc_cuda.py:11-48 by the definition)."""
+    lib = L.load()
+    dev = d.out.colidx.device
+    nnz = d.nnz
+    alloc = lambda dt: torch.zeros(max(nnz, 1), dtype=dt, device=dev)[:nnz]
+    c32 = alloc(torch.float32)
+    tri = alloc(torch.int32) if want_fields else None
+    sharp = alloc(torch.int32) if want_fields else None
+    lam = alloc(torch.int32) if want_fields else None
+    c64 = alloc(torch.float64) if want_fields else None
+    L.check(lib.dcr_bfc_cuda_flavour_directed(d.out.rowptr.data_ptr(), d.out.colidx.data_ptr(), d.inn.rowptr.data_ptr(),
+                                              d.inn.colidx.data_ptr(), d.n, L.ptr(tri), L.ptr(sharp), L.ptr(lam),
+                                              L.ptr(c64), c32.data_ptr(), 0, nnz, L.current_stream()),
+            "dcr_bfc_cuda_flavour_directed")
+    return {"tri": tri, "sharp": sharp, "lam": lam, "c64": c64, "c32": c32}
+
+
+def post_delta_directed(d: DirectedCSR, x: int, y: int, i_nb: torch.Tensor, j_nb: torch.Tensor,
+                        D: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    L.check(lib.dcr_post_delta_directed(d.out.rowptr.data_ptr(), d.out.colidx.data_ptr(), d.inn.rowptr.data_ptr(),
+                                        d.inn.colidx.data_ptr(), d.n, int(x), int(y), i_nb.data_ptr(),
+                                        int(i_nb.numel()), j_nb.data_ptr(), int(j_nb.numel()), D.data_ptr(),
+                                        L.current_stream()), "dcr_post_delta_directed")
+    return D
 
 
 class PaperWorkspace:

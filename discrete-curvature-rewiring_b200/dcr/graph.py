@@ -4,6 +4,9 @@ Restates, vectorised, the third-party canonicalisation the reference relies on (
   * ``to_undirected`` + ``remove_self_loops``           (rewiring/sdrf_cuda_bfc.py:26-29)  -> :func:`undirected_csr`
   * ``to_networkx(data).to_undirected()`` insertion order (:31-33)                          -> :func:`networkx_order`
   * ``from_networkx(G).edge_index`` column order          (:93)                             -> :func:`from_networkx_order`
+  * ``to_networkx(data)`` kept as a ``DiGraph`` (is_undirected=False, :31, :48-49)          -> :func:`digraph_order`,
+    :func:`from_digraph_order`
+  * ``to_networkx(data, node_attrs=['x'], to_undirected=True)`` (rewiring/sdrf_no_cuda.py:19) -> :func:`classical_order`
 """
 from __future__ import annotations
 
@@ -114,3 +117,77 @@ def from_networkx_order(rowptr: np.ndarray, order: np.ndarray) -> np.ndarray:
     key = np.where(earlier, order, n + pos)
     o = np.lexsort((key, rows))
     return np.stack([rows[o], order[o]])
+
+
+def _first_occurrences(u: np.ndarray, v: np.ndarray, n: int):
+    """Columns of ``(u, v)`` without repeats of a directed pair, in order of first appearance."""
+    _, first = np.unique(u * n + v, return_index=True)
+    first.sort()
+    return u[first], v[first]
+
+
+def _rows_in_time_order(rows: np.ndarray, cols: np.ndarray, n: int):
+    """CSR ``(rowptr, cols)`` with each row's entries in the order they appear in the input."""
+    o = np.argsort(rows, kind="stable")
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=rowptr[1:])
+    return rowptr.astype(np.int32), cols[o].astype(np.int32)
+
+
+def digraph_order(edge_index, num_nodes: int):
+    """Successor and predecessor lists of ``to_networkx(data)`` — a ``DiGraph`` filled by ``add_edge(u, v)`` in column
+    order (rewiring/sdrf_cuda_bfc.py:31; is_undirected=False keeps it directed) — in networkx insertion order:
+    ``(succ_rowptr, succ_order, pred_rowptr, pred_order)``.  ``G.successors(x)`` / ``G.predecessors(y)`` (:48-49) yield
+    exactly these orders.  Self-loops are dropped with a warning (the reference keeps them in ``G`` but not in ``A``);
+    a repeated directed pair raises: ``to_dense_adj`` would sum it into a weight 2 (:29), which the 0/1 kernels do not
+    model."""
+    ei = _as_numpy_edge_index(edge_index)
+    n = int(num_nodes)
+    if ei.size and int(ei.max()) >= n:
+        n = int(ei.max()) + 1
+    u, v = ei[0], ei[1]
+    loops = u == v
+    if loops.any():
+        warnings.warn("self-loops dropped from the rewiring graph (the reference keeps them in G but not in A)")
+        u, v = u[~loops], v[~loops]
+    if u.size and np.unique(u * n + v).size != u.size:
+        raise NotImplementedError("directed SDRF: repeated directed edges would make A weighted (to_dense_adj sums "
+                                  "them); only 0/1 adjacency is supported")
+    s_rp, s_ord = _rows_in_time_order(u, v, n)
+    p_rp, p_ord = _rows_in_time_order(v, u, n)
+    return s_rp, s_ord, p_rp, p_ord
+
+
+def from_digraph_order(rowptr: np.ndarray, order: np.ndarray) -> np.ndarray:
+    """``from_networkx(G).edge_index`` for a ``DiGraph``: ``convert_node_labels_to_integers`` re-adds the edges in
+    ``G.edges`` order — sources in node order, successors in insertion order — which is the order of the result."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    rows = np.repeat(np.arange(rowptr.size - 1, dtype=np.int64), np.diff(rowptr))
+    return np.stack([rows, np.asarray(order, dtype=np.int64)])
+
+
+def classical_order(edge_index, num_nodes: int):
+    """Adjacency of ``to_networkx(data, node_attrs=['x'], to_undirected=True)`` (rewiring/sdrf_no_cuda.py:19) in networkx
+    insertion order: PyG 2.0.3 skips every column with ``v > u`` and calls ``add_edge(u, v)`` for the others, in column
+    order — an edge listed only as ``(u, v)`` with ``u < v`` is therefore lost, like in the reference.  Self-loops are
+    dropped with a warning (the reference would keep them).  Returns ``(rowptr int32[n+1], order int32[nnz])``."""
+    ei = _as_numpy_edge_index(edge_index)
+    n = int(num_nodes)
+    if ei.size and int(ei.max()) >= n:
+        n = int(ei.max()) + 1
+    u, v = ei[0], ei[1]
+    if (u == v).any():
+        warnings.warn("self-loops dropped from the rewiring graph (the reference's sdrf_no_cuda would keep them)")
+    keep = v < u
+    u, v = u[keep], v[keep]
+    if u.size == 0:
+        return np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32)
+    u, v = _first_occurrences(u, v, n)
+    t = np.arange(u.size, dtype=np.int64)
+    rows = np.concatenate([u, v])
+    cols = np.concatenate([v, u])
+    tm = np.concatenate([t, t])
+    o = np.lexsort((tm, rows))
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=n), out=rowptr[1:])
+    return rowptr.astype(np.int32), cols[o].astype(np.int32)

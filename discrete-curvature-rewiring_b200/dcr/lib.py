@@ -20,7 +20,8 @@ class SdrfResult(C.Structure):
 
 # status codes of include/dcr.h
 SDRF_OK, SDRF_NEED_HOST, SDRF_PROB_NAN, SDRF_PROB_SUM, SDRF_REMOVE_NONEDGE, SDRF_NO_UNIFORM, SDRF_ARENA_FULL, \
-    SDRF_TOO_MANY_CANDIDATES = range(8)
+    SDRF_TOO_MANY_CANDIDATES, SDRF_EMPTY_GRAPH = range(9)
+SDRF_MODE_BFC, SDRF_MODE_BFC_DIRECTED, SDRF_MODE_1D, SDRF_MODE_AUGMENTED, SDRF_MODE_HAANTJES = range(5)
 SDRF_LOG_INTS = 8
 
 _P = C.c_void_p
@@ -38,6 +39,7 @@ SIGNATURES = {
     "dcr_scatter_dense": (_I, [_P, _P, _I, _P, _P, _P]),
     "dcr_bfc_support": (_I, [_P, _P, _I, _P, _L, _L, _P]),
     "dcr_bfc_cuda_flavour": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),
+    "dcr_bfc_cuda_flavour_directed": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),
     "dcr_bfc_support_tc_workspace_bytes": (_L, [_I]),
     "dcr_bfc_support_tc": (_I, [_P, _P, _I, _P, _P, _L, _P]),
     "dcr_bfc_cuda_flavour_tc_workspace_bytes": (_L, [_I, _L]),
@@ -58,7 +60,9 @@ SIGNATURES = {
     "dcr_comm_destroy": (_I, [_P]),
     "dcr_bfc_paper_sharded": (_I, [_P, _P, _I, _I, _P, _P, _L, _L, _P, _P, _L, _P, _P, _P]),
     "dcr_post_delta": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P]),
+    "dcr_post_delta_directed": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "dcr_sdrf_create": (_I, [_I, _P, _P, _L, C.POINTER(_P)]),
+    "dcr_sdrf_create_mode": (_I, [_I, _I, _P, _P, _P, _P, _L, C.POINTER(_P)]),
     "dcr_sdrf_destroy": (None, [_P]),
     "dcr_sdrf_run": (_I, [_P, _I, _I, _D, _D, _P, _L, _I, _D, _P, _P, _P]),
     "dcr_sdrf_pending_improvements": (_I, [_P, _P, _L, _P]),

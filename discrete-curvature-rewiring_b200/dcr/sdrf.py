@@ -42,15 +42,27 @@ def host_choice(improvements: np.ndarray, tau, u: float) -> int:
 class SdrfState:
     """Owns one ``dcr_sdrf`` handle (device-resident dynamic adjacency + incremental curvature)."""
 
-    def __init__(self, rowptr_order: np.ndarray, order: np.ndarray, max_additions: int):
+    def __init__(self, rowptr_order: np.ndarray, order: np.ndarray, max_additions: int, mode: int = L.SDRF_MODE_BFC,
+                 in_rowptr: np.ndarray | None = None, in_order: np.ndarray | None = None):
+        """``mode``: one of ``L.SDRF_MODE_*``.  The directed mode takes the successor lists as ``rowptr_order/order`` and
+        the predecessor lists as ``in_rowptr/in_order`` (all in networkx insertion order)."""
         L.require_cuda()
         self.lib = L.load()
+        self.mode = int(mode)
         self.n = int(len(rowptr_order) - 1)
         rp = np.ascontiguousarray(rowptr_order, dtype=np.int32)
         od = np.ascontiguousarray(order, dtype=np.int32)
         handle = C.c_void_p()
-        L.check(self.lib.dcr_sdrf_create(self.n, rp.ctypes.data, od.ctypes.data if od.size else 0,
-                                         int(max_additions), C.byref(handle)), "dcr_sdrf_create")
+        if self.mode == L.SDRF_MODE_BFC_DIRECTED:
+            irp = np.ascontiguousarray(in_rowptr, dtype=np.int32)
+            iod = np.ascontiguousarray(in_order, dtype=np.int32)
+        else:
+            irp = iod = None
+        self._keep = (rp, od, irp, iod)
+        L.check(self.lib.dcr_sdrf_create_mode(self.n, self.mode, rp.ctypes.data, od.ctypes.data if od.size else 0,
+                                              irp.ctypes.data if irp is not None else 0,
+                                              iod.ctypes.data if iod is not None and iod.size else 0,
+                                              int(max_additions), C.byref(handle)), "dcr_sdrf_create_mode")
         self.handle = handle
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._result = torch.zeros(8, dtype=torch.int32, device=self.device)
@@ -124,24 +136,46 @@ def _raise_for_status(status: int):
         raise L.DcrError("ran out of uniforms (one is consumed per iteration that has candidates)")
     if status == L.SDRF_ARENA_FULL:
         raise L.DcrError("SDRF adjacency arena exhausted")
+    if status == L.SDRF_EMPTY_GRAPH:
+        raise ValueError("min() arg is an empty sequence")      # sdrf_no_cuda.py:26 on a graph without edges
     if status == L.SDRF_TOO_MANY_CANDIDATES:
         raise L.DcrError("candidate matrix (deg x + 1)(deg y + 1) exceeds the scratch of the SDRF state")
     raise L.DcrError(f"unexpected SDRF status {status}")
 
 
+CLASSICAL_MODES = {"1d": L.SDRF_MODE_1D, "augmented": L.SDRF_MODE_AUGMENTED, "haantjes": L.SDRF_MODE_HAANTJES}
+
+
 def sdrf(edge_index, num_nodes: int, loops: int, remove_edges: bool, removal_bound: float, tau,
          uniforms: np.ndarray | None = None, guard: float = 1e-9, return_log: bool = False,
-         state_out: list | None = None):
-    """BFC-SDRF on the GPU (is_undirected=True).  Returns ``edge_index`` (int64 numpy ``[2, 2E']``) in the column
-    order ``from_networkx`` produces, and with ``return_log`` the int32 ``[iters, 8]`` per-iteration log.
+         state_out: list | None = None, is_undirected: bool = True, curv_type: str = "bfc"):
+    """SDRF on the GPU.  Returns ``edge_index`` (int64 numpy) in the column order ``from_networkx`` produces, and with
+    ``return_log`` the int32 ``[iters, 8]`` per-iteration log.
+
+    ``curv_type='bfc'``: ``sdrf_cuda_bfc`` (rewiring/sdrf_cuda_bfc.py:14-93), undirected or — ``is_undirected=False`` —
+    on the ``DiGraph`` of the input with single directed entries added / removed (:47-49, :72-73, :87-88).
+    ``curv_type`` in ``'1d' | 'augmented' | 'haantjes'``: ``sdrf_no_cuda`` (rewiring/sdrf_no_cuda.py:9-68).
 
     ``uniforms``: the doubles ``np.random`` would produce (one per iteration that has candidates).  When omitted
     they are taken from numpy's global legacy generator exactly as the reference consumes it: the global state
     ends up advanced by the number of draws actually used.
     """
     L.require_cuda()
-    rowptr, order = G.networkx_order(edge_index, num_nodes)
-    state = SdrfState(rowptr, order, max_additions=max(int(loops), 0))
+    directed = False
+    if curv_type == "bfc":
+        if is_undirected:
+            rowptr, order = G.networkx_order(edge_index, num_nodes)
+            state = SdrfState(rowptr, order, max_additions=max(int(loops), 0))
+        else:
+            directed = True
+            s_rp, s_ord, p_rp, p_ord = G.digraph_order(edge_index, num_nodes)
+            state = SdrfState(s_rp, s_ord, max_additions=max(int(loops), 0), mode=L.SDRF_MODE_BFC_DIRECTED,
+                              in_rowptr=p_rp, in_order=p_ord)
+    elif curv_type in CLASSICAL_MODES:
+        rowptr, order = G.classical_order(edge_index, num_nodes)
+        state = SdrfState(rowptr, order, max_additions=max(int(loops), 0), mode=CLASSICAL_MODES[curv_type])
+    else:
+        raise Exception(f"Method {curv_type} not available.")    # classical_curvatures.py:27-28
     own_stream = uniforms is None
     if own_stream:
         rng_state = np.random.get_state()
@@ -180,7 +214,7 @@ def sdrf(edge_index, num_nodes: int, loops: int, remove_edges: bool, removal_bou
             state_out.append(state)
         else:
             state.close()
-    edge_index_out = G.from_networkx_order(out_rowptr, out_order)
+    edge_index_out = (G.from_digraph_order if directed else G.from_networkx_order)(out_rowptr, out_order)
     if return_log:
         return edge_index_out, (np.concatenate(logs) if logs else np.zeros((0, L.SDRF_LOG_INTS), dtype=np.int32))
     return edge_index_out

@@ -5,8 +5,9 @@ insertion/removal, incremental curvature refresh — runs inside one persistent 
 device-resident adjacency; the host only sets the graph up (networkx insertion order, PyG canonicalisation) and
 rebuilds the ``Data`` object.  Random numbers: one double from ``np.random``'s global generator per iteration that
 has candidates, exactly as the reference consumes them (pass ``uniforms=`` to supply them explicitly).
-Only ``is_undirected=True`` is implemented — the only mode any caller of the reference uses (rewire.py:10,
-ph/eval_rewiring_ph.py:34).
+``is_undirected=False`` runs the same loop on the ``DiGraph`` of the input (successors of ``x`` x predecessors of ``y``,
+single directed entries added / removed, :47-49, :72-73, :87-88) with the definitional curvature of an asymmetric
+adjacency (csrc/dcr_directed.cuh).
 """
 import torch
 
@@ -28,16 +29,13 @@ def sdrf_cuda_bfc(data: "torch_geometric.data.Data", loops: int, remove_edges: b
     :param remove_edges: whether to delete highly curved edges each iteration to compensate for the addition.
     :param removal_bound: curvature lower bound of deleting edges (delete edges only with higher curvature).
     :param tau: softmax temperature for choosing the edge to add; ``float('inf')`` picks the maximum.
-    :param is_undirected: must be True.
+    :param is_undirected: flag specifying whether the data is undirected.
     :return: rewired data (``edge_index`` in the order ``from_networkx`` yields, ``num_nodes``).
     """
-    if not is_undirected:
-        raise NotImplementedError("directed SDRF (is_undirected=False) is not implemented on the B200 path; "
-                                  "no caller of the reference uses it (rewire.py:10)")
     edge_index = data.edge_index
     num_nodes = int(data.num_nodes)
     res = _sdrf.sdrf(edge_index, num_nodes, int(loops), bool(remove_edges), float(removal_bound), tau,
-                     uniforms=uniforms, return_log=return_log)
+                     uniforms=uniforms, return_log=return_log, is_undirected=bool(is_undirected))
     ei, log = res if return_log else (res, None)
     out = Data(edge_index=torch.from_numpy(ei).to(torch.long))
     out.num_nodes = max(num_nodes, int(ei.max()) + 1 if ei.size else 0)

@@ -36,6 +36,14 @@ extern "C" {
 #define DCR_SDRF_NO_UNIFORM 5     /* ran out of host-supplied uniforms                                            */
 #define DCR_SDRF_ARENA_FULL 6     /* adjacency arena exhausted (create with a larger max_additions)               */
 #define DCR_SDRF_TOO_MANY_CANDIDATES 7 /* (deg x+1)(deg y+1) exceeds the candidate scratch of the state          */
+#define DCR_SDRF_EMPTY_GRAPH 8    /* classical loop on a graph without edges (python: min() of an empty sequence)  */
+
+/* loop flavours of dcr_sdrf_create_mode */
+#define DCR_SDRF_MODE_BFC 0          /* sdrf_cuda_bfc(..., is_undirected=True)   rewiring/sdrf_cuda_bfc.py:14-93        */
+#define DCR_SDRF_MODE_BFC_DIRECTED 1 /* sdrf_cuda_bfc(..., is_undirected=False)  :47-49, :72-73, :87-88                 */
+#define DCR_SDRF_MODE_1D 2           /* sdrf_no_cuda(curv_type='1d')             rewiring/sdrf_no_cuda.py:9-68          */
+#define DCR_SDRF_MODE_AUGMENTED 3    /* sdrf_no_cuda(curv_type='augmented')      curvature/classical_curvatures.py:17-21 */
+#define DCR_SDRF_MODE_HAANTJES 4     /* sdrf_no_cuda(curv_type='haantjes')       curvature/classical_curvatures.py:22-26 */
 
 const char* dcr_last_error(void);
 int dcr_version(void);
@@ -76,6 +84,15 @@ int dcr_bfc_cuda_flavour(const int32_t* rowptr, const int32_t* colidx, int n, co
                          int32_t* sharp, int32_t* lam, double* c64, float* c32, int64_t entry_lo,
                          int64_t entry_hi, void* stream);
 
+/* The same kernel for an ASYMMETRIC 0/1 adjacency without self-loops (a directed simple graph; is_undirected=False
+ * callers, curvature/bfc_cuda.py:20-25 take d_in[i] and d_out[j]): out_* = CSR of the successors (rows of A), in_* =
+ * CSR of the predecessors (rows of A^T), both sorted.  Per entry p of the successor CSR: tri[p] = A2[i,j] =
+ * #{m : i -> m -> j}, sharp / lam by the loop of :31-44 (lam is no longer d_max), c64 / c32 as above.  tri, sharp, lam,
+ * c64 may be NULL; no support pass is needed before. */
+int dcr_bfc_cuda_flavour_directed(const int32_t* out_rowptr, const int32_t* out_colidx, const int32_t* in_rowptr,
+                                  const int32_t* in_colidx, int n, int32_t* tri, int32_t* sharp, int32_t* lam,
+                                  double* c64, float* c32, int64_t entry_lo, int64_t entry_hi, void* stream);
+
 /* Dense-regime alternative to dcr_bfc_support (n <= 32768): A2 = A·A on the tensor cores (tcgen05 kind::i8, TMA,
  * TMEM), replacing `torch.matmul(A, A)` of curvature/bfc_cuda.py:53,146; the fused epilogue writes only the entries
  * that sit on an edge, in CSR order — tri[0..nnz) is identical to dcr_bfc_support's.
@@ -94,7 +111,7 @@ int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n,
  * curvature/bfc_cuda.py:51-65 straight from the dense fp32 A — rows bit-packed once, then one kernel computes supports,
  * the "support == 1" counts and the closing formula per entry and writes ALL n*n entries of C (+0.0 off-edge).  Two
  * launches and no host round trip, where the CSR route is launch-bound.  *flags receives the validation bits of
- * dcr_dense_count (the caller zeroes it and decides what to do with a non-zero value; C is then unspecified).
+ * dcr_dense_count (the caller zeroes it and decides what to do with a non-zero value; C is then left untouched).
  * workspace: dcr_bfc_cuda_dense_small_workspace_bytes(n) bytes of device memory. */
 int64_t dcr_bfc_cuda_dense_small_workspace_bytes(int n);
 int dcr_bfc_cuda_dense_small(const float* A, int n, float* C, int32_t* flags, void* workspace,
@@ -175,6 +192,12 @@ int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t chunk, int64_
 int dcr_post_delta(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* tri, int x, int y,
                    const int32_t* i_nb, int n_i, const int32_t* j_nb, int n_j, float* D, void* stream);
 
+/* Asymmetric A (see dcr_bfc_cuda_flavour_directed): i_nb are usually the successors of x plus x, j_nb the predecessors
+ * of y plus y (rewiring/sdrf_cuda_bfc.py:48-49). */
+int dcr_post_delta_directed(const int32_t* out_rowptr, const int32_t* out_colidx, const int32_t* in_rowptr,
+                            const int32_t* in_colidx, int n, int x, int y, const int32_t* i_nb, int n_i,
+                            const int32_t* j_nb, int n_j, float* D, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * SDRF loop.  Replaces the loop body of sdrf_cuda_bfc (rewiring/sdrf_cuda_bfc.py:37-91) including
  * utils/softmax.py:4-10 and the np.random.choice draw (:64-68), for is_undirected=True.
@@ -200,6 +223,15 @@ typedef struct dcr_sdrf_result {
  * number of edge insertions over the lifetime of the state (arena sizing). */
 int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host, int64_t max_additions,
                     dcr_sdrf** out);
+/* The other loop flavours (DCR_SDRF_MODE_*).  BFC_DIRECTED: rowptr/order list the SUCCESSORS of every node in
+ * networkx insertion order (G.successors, sdrf_cuda_bfc.py:48) and in_rowptr/in_order the PREDECESSORS (G.predecessors,
+ * :49); the graph must be simple (no self-loops, no repeated entries: to_dense_adj would sum them into a weight).
+ * 1D / AUGMENTED / HAANTJES: the loop of sdrf_no_cuda over the undirected graph rowptr/order (adjacency order of
+ * to_networkx(data, to_undirected=True)); in_* are ignored.  dcr_sdrf_run's log record then holds the (x, y) of
+ * min(G.edges) (x < y), the sorted (k, l) that was added and the removed edge; removal_bound is compared in fp64. */
+int dcr_sdrf_create_mode(int n, int mode, const int32_t* rowptr_host, const int32_t* order_host,
+                         const int32_t* in_rowptr_host, const int32_t* in_order_host, int64_t max_additions,
+                         dcr_sdrf** out);
 void dcr_sdrf_destroy(dcr_sdrf* s);
 /* Run up to `loops` iterations.  uniforms[draw_offset + t] is the t-th uniform of this call (device, fp64).
  * forced_choice >= 0 forces the candidate index of the FIRST iteration of this call (host re-decision after

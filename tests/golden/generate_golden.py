@@ -359,8 +359,70 @@ def gen_sdrf_directed(out):
     print("sdrf_directed_seq:", len(cases), "cases")
 
 
+def run_reference_classical(ei, n, curv_type, loops, bound, tau, seed):
+    """Unmodified ``rewire(data, curv_type, ...)`` -> ``sdrf_no_cuda`` (rewiring/sdrf_no_cuda.py:9-68).  The scoring loop
+    probes every candidate with ``add_edge`` / ``remove_edge`` (:42-45); a probe is an addition IMMEDIATELY followed by
+    the removal of the same pair and is dropped from the log, what remains are the loop's own mutations (:51, :63)."""
+    log = []
+    orig_add, orig_rm = nx.Graph.add_edge, nx.Graph.remove_edge
+
+    def add_edge(self, u, v, **kw):
+        log.append((1, int(u), int(v)))
+        return orig_add(self, u, v, **kw)
+
+    def remove_edge(self, u, v):
+        if log and log[-1] == (1, int(u), int(v)):
+            log.pop()
+        else:
+            log.append((-1, int(u), int(v)))
+        return orig_rm(self, u, v)
+
+    data = Data(edge_index=torch.from_numpy(ei).long())
+    data.num_nodes = n
+    data.x = torch.arange(n, dtype=torch.float32).view(n, 1).repeat(1, 2)     # to_networkx(..., node_attrs=['x']) (:19)
+    np.random.seed(seed)
+    uniforms = np.random.RandomState(seed).random_sample(loops)
+    nx.Graph.add_edge, nx.Graph.remove_edge = add_edge, remove_edge
+    try:
+        out = ref_rewire(data, curv_type, loops, bound, tau)
+    finally:
+        nx.Graph.add_edge, nx.Graph.remove_edge = orig_add, orig_rm
+    setup = int((ei[1] <= ei[0]).sum())            # to_networkx's own add_edge calls (columns with v <= u)
+    return out.numpy().copy(), np.array(log[setup:], dtype=np.int64).reshape(-1, 3), uniforms
+
+
+def gen_sdrf_classical(out):
+    cases = []
+    # (name, graph, curv_type, loops, removal_bound, tau, seed)
+    for ct, bound in (("1d", -3.0), ("augmented", 0.5), ("haantjes", 0.5)):
+        cases.append((f"gnp14_{ct}_greedy", nx.gnp_random_graph(14, 0.25, seed=3), ct, 8, bound, float("inf"), 41))
+        cases.append((f"gnp16_{ct}_tau2", nx.gnp_random_graph(16, 0.22, seed=5), ct, 8, bound, 2, 42))
+        cases.append((f"barbell_{ct}_tau1", nx.barbell_graph(5, 2), ct, 8, bound, 1, 43))
+        cases.append((f"tree_{ct}_nobound", nx.balanced_tree(2, 3), ct, 6, 100.0, 3, 44))
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, g, ct, loops, bound, tau, seed in cases:
+        t0 = time.time()
+        ei = sorted_symmetric_edge_index(g)
+        n = g.number_of_nodes()
+        eo, log, uni = run_reference_classical(ei, n, ct, loops, bound, tau, seed)
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/curv_type"] = np.array(ct)
+        pack[f"{name}/loops"] = np.int64(loops)
+        pack[f"{name}/bound"] = np.float64(bound)
+        pack[f"{name}/tau"] = np.float64(tau)
+        pack[f"{name}/uniforms"] = uni
+        pack[f"{name}/out"] = eo
+        pack[f"{name}/log"] = log
+        print(f"  sdrf-classical {name}: n={n} loops={loops} log={len(log)} {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(out, **pack)
+    print("sdrf_classical_seq:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed"]
+    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical"]
+    if "sdrf_classical" in which:
+        gen_sdrf_classical(os.path.join(HERE, "sdrf_classical_seq.npz"))
     if "paper_ints" in which:
         gen_paper_ints(os.path.join(HERE, "paper_ints_kat.npz"))
     if "sdrf_directed" in which:

@@ -42,12 +42,18 @@ def test_small_dense_path_bitwise_and_validation():
         assert out is C
         ref = bfc_cuda_dense(An)["C"]
         assert np.array_equal(C.cpu().numpy().view(np.uint32), ref.view(np.uint32)), name
-    bad = torch.zeros(8, 8, device="cuda")
-    bad[0, 1] = 1                                        # asymmetric
-    with pytest.raises(NotImplementedError):
-        balanced_forman_curvature(bad)
+    asym = torch.zeros(8, 8, device="cuda")
+    asym[0, 1] = asym[1, 2] = asym[2, 0] = asym[0, 2] = 1   # asymmetric: the directed route (tests/test_gpu_directed.py)
+    got = balanced_forman_curvature(asym).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), bfc_cuda_dense(asym.cpu().numpy())["C"].view(np.uint32))
     bad = torch.zeros(8, 8, device="cuda")
     bad[2, 2] = 1                                        # self-loop
+    keep = torch.full((8, 8), 5.0, device="cuda")
+    with pytest.raises(NotImplementedError):
+        balanced_forman_curvature(bad, C=keep)
+    assert bool((keep == 5.0).all())                     # a rejected input leaves the caller's C untouched
+    bad = torch.zeros(8, 8, device="cuda")
+    bad[0, 1] = bad[1, 0] = 2                            # weighted
     with pytest.raises(NotImplementedError):
         balanced_forman_curvature(bad)
 

@@ -56,8 +56,7 @@ def test_sdrf_oracle_sim32_reproduces_reference_sequences():
 
 def test_sdrf_oracle_directed_mode_reproduces_reference_sequences():
     """is_undirected=False (rewiring/sdrf_cuda_bfc.py:47-49,72-73,87-88): add/remove sequence and the
-    output edge_index of the UNMODIFIED reference on random directed graphs with unsorted insertion order.  The CUDA
-    path does not cover this mode yet (it raises NotImplementedError); the oracle and the goldens are in place for it."""
+    output edge_index of the UNMODIFIED reference on random directed graphs with unsorted insertion order."""
     z = golden("sdrf_directed_seq.npz")
     for name in _names(z):
         ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
@@ -72,6 +71,33 @@ def test_sdrf_oracle_directed_mode_reproduces_reference_sequences():
                 mine.append((-1,) + tuple(r["removed"]))
         assert np.array_equal(np.array(mine).reshape(-1, 3), z[f"{name}/log"]), name
         assert np.array_equal(out, z[f"{name}/out"]), name
+
+
+def _mutations(log):
+    mine = []
+    for r in log:
+        if r["k"] >= 0:
+            mine.append((1, r["k"], r["l"]))
+        if r["removed"] is not None:
+            mine.append((-1,) + tuple(r["removed"]))
+    return np.array(mine, dtype=np.int64).reshape(-1, 3)
+
+
+def test_sdrf_classical_oracle_reproduces_reference_sequences():
+    """rewiring/sdrf_no_cuda.py:9-68 with '1d' / 'augmented' / 'haantjes' (SURVEY.md §8f-4): add/remove sequence and
+    output edge_index of the UNMODIFIED reference, greedy and stochastic."""
+    from oracle.sdrf_classical import sdrf_classical_oracle
+    z = golden("sdrf_classical_seq.npz")
+    seen = set()
+    for name in _names(z):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        ct = str(z[f"{name}/curv_type"])
+        seen.add(ct)
+        out, log = sdrf_classical_oracle(ei, n, ct, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]),
+                                         float(z[f"{name}/tau"]), z[f"{name}/uniforms"])
+        assert np.array_equal(_mutations(log), z[f"{name}/log"]), name
+        assert np.array_equal(out, z[f"{name}/out"]), name
+    assert seen == {"1d", "augmented", "haantjes"}
 
 
 # SURVEY.md Appendix G: (graph, edge) -> cuda (d_i, d_j, A2ij, sharp, lam, C) ; paper (tri, sq1, sq2, gamma, bfc)
