@@ -33,7 +33,7 @@
 #include <mutex>
 #include <stdlib.h>
 
-#include "dcr_common.cuh"
+#include "dcr_comm.cuh"
 
 namespace dcr {
 
@@ -1970,54 +1970,7 @@ extern "C" int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t ch
 // arrays per buffer carry the hand-shake: ready[p] = "rank p has passed the start of pass k" (its consumers of the
 // previous pass are done: its buffer may be overwritten), done[p] = "all of rank p's results of pass k have landed".
 // ------------------------------------------------------------------------------------------------------------
-constexpr int COMM_MAX_WORLD = 32;
-struct CommFlags {
-    unsigned int ready[COMM_MAX_WORLD];
-    unsigned int done[COMM_MAX_WORLD];
-    unsigned int blocks_done;        // last-block detection of the closing kernel
-    unsigned int error;              // a wait timed out (the peers never arrived)
-};
-struct dcr_comm {
-    int rank, world, device;
-    int64_t n_edges, chunk;          // arrays are `chunk` entries long (n_edges rounded up to 4)
-    size_t bytes, flag_off;
-    unsigned char* local;
-    unsigned char* peer[COMM_MAX_WORLD];
-    unsigned char** d_peers;         // the same pointers on the device
-    unsigned int epoch;
-    bool connected;
-};
-
 namespace dcr {
-
-struct CommView {
-    unsigned char* const* peers;     // [world] buffers
-    int rank, world;
-    int64_t chunk;
-    size_t flag_off;
-    unsigned int epoch;
-};
-__device__ __forceinline__ CommFlags* comm_flags(unsigned char* buf, size_t flag_off) { return (CommFlags*)(buf + flag_off); }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long comm_now() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr unsigned long long COMM_TIMEOUT_NS = 4000000000ull;     // a peer that has not arrived after 4 s never will
-
-// start of a pass: tell every peer that this rank's buffer may be overwritten
-__global__ void comm_ready_kernel(CommView c) {
-    const int p = threadIdx.x;
-    if (p < c.world && p != c.rank) st_release_sys(&comm_flags(c.peers[p], c.flag_off)->ready[c.rank], c.epoch);
-}
 
 // bfc_naive.py:31-32 / :39-40 for the edges [e_lo, e_lo + count) + the fused all-gather (see above)
 __global__ void __launch_bounds__(256) paper_value_exchange_kernel(PaperArgs a, CommView c) {
@@ -2064,90 +2017,7 @@ __global__ void __launch_bounds__(256) paper_value_exchange_kernel(PaperArgs a, 
     }
 }
 
-// end of a pass: the peers' results have landed in this rank's buffer
-__global__ void comm_wait_kernel(CommView c) {
-    CommFlags* fl = comm_flags(c.peers[c.rank], c.flag_off);
-    const int p = threadIdx.x;
-    if (p < c.world && p != c.rank) {
-        const unsigned long long t0 = comm_now();
-        while ((int)(ld_acquire_sys(&fl->done[p]) - c.epoch) < 0) {
-            if (comm_now() - t0 > COMM_TIMEOUT_NS) { fl->error = 1u; break; }
-            __nanosleep(200);
-        }
-    }
-    __threadfence_system();
-}
-
 }  // namespace dcr
-
-extern "C" int dcr_comm_create(int rank, int world, int64_t n_edges, dcr_comm** out) {
-    if (!out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || n_edges < 0) {
-        set_error("dcr_comm_create: bad arguments (world <= %d)", COMM_MAX_WORLD);
-        return 1;
-    }
-    dcr_comm* c = new dcr_comm();
-    c->rank = rank; c->world = world; c->device = current_device();
-    c->n_edges = n_edges;
-    c->chunk = std::max<int64_t>(4, (n_edges + 3) / 4 * 4);
-    c->flag_off = align_up((size_t)c->chunk * 24, 256);
-    c->bytes = c->flag_off + align_up(sizeof(CommFlags), 256);
-    c->epoch = 0;
-    c->connected = (world == 1);
-    c->local = nullptr; c->d_peers = nullptr;
-    for (int p = 0; p < COMM_MAX_WORLD; ++p) c->peer[p] = nullptr;
-    cudaError_t e = cudaMalloc((void**)&c->local, c->bytes);            // plain cudaMalloc: exportable through CUDA IPC
-    if (e == cudaSuccess) e = cudaMemset(c->local, 0, c->bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_peers, sizeof(unsigned char*) * COMM_MAX_WORLD);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "dcr_comm_create", __FILE__, __LINE__); }
-    c->peer[rank] = c->local;
-    e = cudaMemcpy(c->d_peers, c->peer, sizeof(unsigned char*) * COMM_MAX_WORLD, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "dcr_comm_create", __FILE__, __LINE__); }
-    *out = c;
-    return 0;
-}
-
-extern "C" int dcr_comm_handle(dcr_comm* c, void* handle64_host) {
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    if (!c || !handle64_host) { set_error("dcr_comm_handle: NULL argument"); return 1; }
-    DCR_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_host, c->local));
-    return 0;
-}
-
-extern "C" int dcr_comm_connect(dcr_comm* c, const void* handles_host) {
-    if (!c || !handles_host) { set_error("dcr_comm_connect: NULL argument"); return 1; }
-    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles_host;
-    for (int p = 0; p < c->world; ++p) {
-        if (p == c->rank) continue;
-        void* ptr = nullptr;
-        DCR_CUDA(cudaIpcOpenMemHandle(&ptr, h[p], cudaIpcMemLazyEnablePeerAccess));
-        c->peer[p] = (unsigned char*)ptr;
-    }
-    DCR_CUDA(cudaMemcpy(c->d_peers, c->peer, sizeof(unsigned char*) * COMM_MAX_WORLD, cudaMemcpyHostToDevice));
-    c->connected = true;
-    return 0;
-}
-
-extern "C" void* dcr_comm_buffer(dcr_comm* c) { return c ? c->local : nullptr; }
-extern "C" int64_t dcr_comm_chunk(dcr_comm* c) { return c ? c->chunk : 0; }
-
-extern "C" int dcr_comm_error(dcr_comm* c) {                               // synchronises
-    if (!c) return 1;
-    unsigned int err = 0;
-    if (cudaMemcpy(&err, c->local + c->flag_off + offsetof(CommFlags, error), sizeof(err), cudaMemcpyDeviceToHost) != cudaSuccess)
-        return 1;
-    return (int)err;
-}
-
-extern "C" int dcr_comm_destroy(dcr_comm* c) {
-    if (!c) return 0;
-    cudaDeviceSynchronize();
-    for (int p = 0; p < c->world; ++p)
-        if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
-    if (c->d_peers) cudaFree(c->d_peers);
-    if (c->local) cudaFree(c->local);
-    delete c;
-    return 0;
-}
 
 extern "C" int dcr_bfc_paper_sharded(const int32_t* rowptr, const int32_t* colidx, int n, int max_degree,
                                      const int32_t* esrc, const int32_t* edst, int64_t e_lo, int64_t count,

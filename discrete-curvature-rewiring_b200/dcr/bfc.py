@@ -22,6 +22,7 @@ class DeviceCSR:
             max_degree = int((rowptr[1:] - rowptr[:-1]).max().item()) if n > 0 else 0
         self.max_degree = int(max_degree)
         self._edges = None
+        self._edges_aux = None
         self.asymmetric = False
 
     @classmethod
@@ -74,6 +75,43 @@ class DeviceCSR:
         return self._edges
 
 
+def edges_aux(csr: DeviceCSR) -> torch.Tensor:
+    """Per-graph set-up of the edge-centric cuda-flavour kernels (cached on the CSR): entry -> edge id + hub-hub list."""
+    if getattr(csr, "_edges_aux", None) is None:
+        lib = L.load()
+        esrc, edst, _ = csr.undirected_edges()
+        e = int(esrc.numel())
+        aux = torch.zeros(int(lib.dcr_bfc_cuda_edges_aux_ints(csr.nnz, e)), dtype=torch.int32, device=csr.colidx.device)
+        L.check(lib.dcr_bfc_cuda_edges_prepare(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, esrc.data_ptr(),
+                                               edst.data_ptr(), e, csr.nnz, aux.data_ptr(), L.current_stream()),
+                "dcr_bfc_cuda_edges_prepare")
+        csr._edges_aux = aux
+    return csr._edges_aux
+
+
+def cuda_flavour_edges(csr: DeviceCSR, e_lo: int = 0, count: int | None = None, phases: int = 3, out: dict | None = None,
+                       want_fields: bool = True) -> dict:
+    """cuda-flavour BFC per UNDIRECTED edge (``esrc < edst``, CSR order): ``tri, sharp, lam`` int32, ``c64``, ``c32``,
+    arrays indexed by edge id.  One intersection per edge instead of one per direction; hub-hub edges get a CTA."""
+    lib = L.load()
+    dev = csr.colidx.device
+    esrc, edst, _ = csr.undirected_edges()
+    e = int(esrc.numel())
+    aux = edges_aux(csr)
+    if count is None:
+        count = e - e_lo
+    if out is None:
+        alloc = lambda dt: torch.zeros(max(e, 1), dtype=dt, device=dev)[:e]
+        out = {"tri": alloc(torch.int32), "c32": alloc(torch.float32),
+               "sharp": alloc(torch.int32) if want_fields else None, "lam": alloc(torch.int32) if want_fields else None,
+               "c64": alloc(torch.float64) if want_fields else None}
+    L.check(lib.dcr_bfc_cuda_edges(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, esrc.data_ptr(), edst.data_ptr(),
+                                   csr.nnz, aux.data_ptr(), int(e_lo), int(count), out["tri"].data_ptr(),
+                                   L.ptr(out.get("sharp")), L.ptr(out.get("lam")), L.ptr(out.get("c64")),
+                                   out["c32"].data_ptr(), int(phases), L.current_stream()), "dcr_bfc_cuda_edges")
+    return out
+
+
 def support(csr: DeviceCSR, out: torch.Tensor | None = None) -> torch.Tensor:
     """``A2[i,j]`` (#common neighbours) of every directed entry, int32 ``[nnz]``."""
     lib = L.load()
@@ -119,11 +157,18 @@ def cuda_flavour_tc(csr: DeviceCSR, want_fields: bool = True, workspace: torch.T
 
 def cuda_flavour(csr: DeviceCSR, entry_lo: int = 0, entry_hi: int | None = None, want_fields: bool = True,
                  tri: torch.Tensor | None = None) -> dict:
-    """cuda-flavour BFC per directed entry: ``tri, sharp, lam`` (int32), ``c64`` (fp64), ``c32`` (fp32)."""
+    """cuda-flavour BFC per directed entry: ``tri, sharp, lam`` (int32), ``c64`` (fp64), ``c32`` (fp32).
+
+    The whole graph goes through the edge-centric kernels (every undirected edge once, :func:`cuda_flavour_edges`) and
+    is expanded to both entries; an entry sub-range uses the per-entry kernels."""
     lib = L.load()
     dev = csr.colidx.device
     nnz = csr.nnz
     hi = nnz if entry_hi is None else entry_hi
+    if entry_lo == 0 and hi == nnz and tri is None and nnz > 0:
+        per_edge = cuda_flavour_edges(csr, want_fields=want_fields)
+        eid = edges_aux(csr)[:nnz].long()
+        return {k: (v[eid] if v is not None else None) for k, v in per_edge.items()}
     if tri is None:
         tri = support(csr)
     alloc = lambda dt: torch.zeros(max(nnz, 1), dtype=dt, device=dev)[:nnz]

@@ -224,6 +224,54 @@ class ShardedPaperBFC:
             self.comm = None
 
 
+CUDA_FIELDS = ("c64", "tri", "sharp", "lam", "c32")
+
+
+class ShardedCudaBFC:
+    """Multi-GPU full-graph CUDA-flavour BFC (``balanced_forman_curvature`` of
+    curvature/bfc_cuda.py:51-65 at full-graph scale): graph replicated, contiguous edge ranges balanced by the
+    intersection work ``min(d_i, d_j) * log2(max(d_i, d_j))``, two passes with the all-gather of the supports between
+    them fused into the kernels over CUDA-IPC peer memory (``dcr_bfc_cuda_sharded``).  ``run()`` returns the full-graph
+    per-edge arrays ``c64, tri, sharp, lam, c32`` (views of the rank's ``dcr_comm`` buffer)."""
+
+    def __init__(self, csr: "bfc.DeviceCSR", group=None):
+        self.csr = csr
+        self.group = group
+        self.rank, self.world = _world(group)
+        esrc, edst, _ = csr.undirected_edges()
+        self.esrc, self.edst = esrc, edst
+        self.n_edges = int(esrc.numel())
+        self.aux = bfc.edges_aux(csr)
+        self.comm = PeerComm(self.n_edges, self.rank, self.world, group, device=csr.colidx.device)
+        deg = (csr.rowptr[1:] - csr.rowptr[:-1]).to(torch.int64)
+        di, dj = deg[esrc.long()], deg[edst.long()]
+        cost = torch.minimum(di, dj) * (torch.log2(torch.maximum(di, dj).double() + 1).ceil().to(torch.int64) + 1) + 16
+        self.bounds = balanced_bounds(torch.cumsum(cost, 0), self.world)
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        v = self.comm.views
+        self.views = {"c64": v["bfc"], "tri": v["tri"], "sharp": v["sq_i"], "lam": v["sq_j"],
+                      "c32": v["gamma"].view(torch.float32)}
+
+    def run(self) -> dict:
+        """One pass over this rank's range; only enqueues work on the current stream."""
+        lib = L.load()
+        csr = self.csr
+        L.check(lib.dcr_bfc_cuda_sharded(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, self.esrc.data_ptr(),
+                                         self.edst.data_ptr(), csr.nnz, self.aux.data_ptr(), self.lo, self.hi - self.lo,
+                                         self.comm.handle, L.current_stream()), "dcr_bfc_cuda_sharded")
+        return self.views
+
+    def check(self):
+        if self.comm is not None and self.comm.error():
+            raise L.DcrError("dcr.dist: a peer rank never arrived at a pass (hand-shake timed out)")
+
+    def close(self):
+        if self.comm is not None:
+            self.views = None
+            self.comm.close()
+            self.comm = None
+
+
 class HostShardedPaperBFC:
     """End to end on host buffers: pinned host CSR + edge list in, one host result block (shared by the ranks) out.
 

@@ -59,6 +59,10 @@ SIGNATURES = {
     "dcr_comm_error": (_I, [_P]),
     "dcr_comm_destroy": (_I, [_P]),
     "dcr_bfc_paper_sharded": (_I, [_P, _P, _I, _I, _P, _P, _L, _L, _P, _P, _L, _P, _P, _P]),
+    "dcr_bfc_cuda_edges_aux_ints": (_L, [_L, _L]),
+    "dcr_bfc_cuda_edges_prepare": (_I, [_P, _P, _I, _P, _P, _L, _L, _P, _P]),
+    "dcr_bfc_cuda_edges": (_I, [_P, _P, _I, _P, _P, _L, _P, _L, _L, _P, _P, _P, _P, _P, _I, _P]),
+    "dcr_bfc_cuda_sharded": (_I, [_P, _P, _I, _P, _P, _L, _P, _L, _L, _P, _P]),
     "dcr_post_delta": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P]),
     "dcr_post_delta_directed": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "dcr_sdrf_create": (_I, [_I, _P, _P, _L, C.POINTER(_P)]),

@@ -178,6 +178,29 @@ int dcr_bfc_paper_sharded(const int32_t* rowptr, const int32_t* colidx, int n, i
                           const int32_t* edst, int64_t e_lo, int64_t count, dcr_comm* comm, void* scratch,
                           int64_t scratch_bytes, void* ev_edge_begin, void* ev_edge_end, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * cuda-flavour BFC, one work item per UNDIRECTED edge (the fast path at full-graph scale) and its multi-GPU form
+ * (SURVEY.md §8e row 2).  Replaces balanced_forman_curvature (curvature/bfc_cuda.py:51-65) for a symmetric 0/1 adjacency
+ * given as a sorted CSR plus its undirected edge list (esrc[e] < edst[e], CSR order).  C[i,j] = C[j,i] is computed once.
+ *   aux: dcr_bfc_cuda_edges_aux_ints(nnz, n_edges) int32 of device memory filled ONCE per graph by
+ *        dcr_bfc_cuda_edges_prepare (directed entry -> edge id, and the list of hub-hub edges that get a whole CTA).
+ *   dcr_bfc_cuda_edges: edges [e_lo, e_lo + count); outputs are indexed by EDGE ID (full-length arrays).  phases bit 0 =
+ *        supports tri[e] = A2[i,j], bit 1 = sharp / lam / c64 / c32 (needs tri of ALL edges: run bit 0 over the whole
+ *        graph first, or all-gather it).  sharp, lam, c64 may be NULL.
+ *   dcr_bfc_cuda_sharded: both phases for this rank's range with the exchange fused into the kernels: supports are
+ *        stored into every rank's dcr_comm buffer (the all-gather of `tri` between the two passes of §8e), the ranks meet
+ *        on device-side flags, the results follow the same way.  Afterwards the local buffer holds, for ALL edges,
+ *        c64 f64[chunk] | tri | sharp | lam int32[chunk] | c32 float[chunk].  Every rank makes the same sequence of calls.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t dcr_bfc_cuda_edges_aux_ints(int64_t nnz, int64_t n_edges);
+int dcr_bfc_cuda_edges_prepare(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc,
+                               const int32_t* edst, int64_t n_edges, int64_t nnz, int32_t* aux, void* stream);
+int dcr_bfc_cuda_edges(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc, const int32_t* edst,
+                       int64_t nnz, const int32_t* aux, int64_t e_lo, int64_t count, int32_t* tri, int32_t* sharp,
+                       int32_t* lam, double* c64, float* c32, int phases, void* stream);
+int dcr_bfc_cuda_sharded(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* esrc, const int32_t* edst,
+                         int64_t nnz, const int32_t* aux, int64_t e_lo, int64_t count, dcr_comm* comm, void* stream);
+
 /* Multi-GPU epilogue of the NCCL route (strided shards): `gathered` = the all-gathered per-rank result blocks, rank r's block at byte offset
  * r*chunk*24 laid out as bfc[chunk] f64 | tri[chunk] | sq_i[chunk] | sq_j[chunk] | gamma[chunk] int32, where
  * local index t of rank r is edge e = r + t*world.  Writes the full-graph arrays indexed by edge id. */

@@ -46,6 +46,23 @@ def main():
                 dist.barrier()
             sh.check()
             sh.close()
+        # cuda flavour: two passes with the all-gather of the supports fused between them
+        want = {k: v.clone() for k, v in bfc.cuda_flavour_edges(csr).items()}
+        sc = ddist.ShardedCudaBFC(csr)
+        for it in range(4):
+            out = sc.run()
+            torch.cuda.synchronize()
+            for k in ddist.CUDA_FIELDS:
+                a, b = out[k], want[k]
+                if a.dtype.is_floating_point:
+                    a, b = a.view(torch.int64 if a.dtype == torch.float64 else torch.int32), \
+                        b.view(torch.int64 if b.dtype == torch.float64 else torch.int32)
+                assert torch.equal(a, b), (name, "cuda-sharded", it, k, rank)
+            for k in ddist.CUDA_FIELDS:
+                out[k].zero_()
+            dist.barrier()
+        sc.check()
+        sc.close()
         m = ei[0] < ei[1]
         esrc, edst = ei[0][m].astype(np.int32), ei[1][m].astype(np.int32)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

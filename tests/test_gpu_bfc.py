@@ -541,3 +541,44 @@ def test_full_size_arxiv_shape_exact_against_c_oracle(paper_mode):
     supp = bfc.support(csr).cpu().numpy().astype(np.int64)
     assert tri.sum() % 3 == 0 and supp.sum() == 2 * tri.sum()
     assert np.array_equal(out["sq_i"].cpu().numpy() > 0, out["sq_j"].cpu().numpy() > 0)
+
+
+def test_edge_centric_cuda_flavour_matches_per_entry_kernels_and_oracle():
+    """dcr_bfc_cuda_edges (one work item per undirected edge, hub-hub edges by a CTA) against the per-entry kernels at
+    every size incl. the arxiv shape, and against the dense oracle on small graphs; a single-GPU dcr_comm run of the
+    sharded entry point gives the same arrays."""
+    import torch
+    from dcr import bfc
+    from dcr import dist as ddist
+    from dcr.synth import named_graph
+    from oracle.cuda_flavour import bfc_cuda_dense
+    cases = [(gnp(60, 0.2, 3), 60), toy_graphs()["k5"], toy_graphs()["star5"]]
+    cases += [named_graph(nm) for nm in ("cornell", "cora", "squirrel", "arxiv")]
+    hub = sym_edge_index([(0, i) for i in range(1, 1500)] + [(1, i) for i in range(2, 1400)] +
+                         [(i, i + 1) for i in range(2, 1300)], 1500)          # one edge with a 1398-long shorter row
+    cases.append((hub, 1500))
+    for ei, n in cases:
+        csr = _csr(ei, n)
+        per_entry = bfc.cuda_flavour(csr, tri=bfc.support(csr))      # tri given: the per-entry kernels
+        esrc, edst, entry = csr.undirected_edges()
+        got = bfc.cuda_flavour_edges(csr)
+        for k in ("tri", "sharp", "lam"):
+            assert torch.equal(got[k], per_entry[k][entry]), (n, k)
+        assert torch.equal(got["c64"].view(torch.int64), per_entry["c64"][entry].view(torch.int64)), n
+        assert torch.equal(got["c32"].view(torch.int32), per_entry["c32"][entry].view(torch.int32)), n
+        if n <= 200:
+            C = bfc_cuda_dense(dense_of(ei, n))["C"]
+            want = C[esrc.cpu().numpy(), edst.cpu().numpy()]
+            assert np.array_equal(got["c32"].cpu().numpy().view(np.uint32), want.view(np.uint32)), n
+        # ranges: supports of everything first, then the closing pass in two halves
+        e = int(esrc.numel())
+        out = bfc.cuda_flavour_edges(csr, phases=1)
+        bfc.cuda_flavour_edges(csr, 0, e // 2, phases=2, out=out)
+        bfc.cuda_flavour_edges(csr, e // 2, e - e // 2, phases=2, out=out)
+        assert torch.equal(out["c32"].view(torch.int32), got["c32"].view(torch.int32)), n
+        sc = ddist.ShardedCudaBFC(csr)
+        v = sc.run()
+        torch.cuda.synchronize()
+        assert torch.equal(v["c32"].view(torch.int32), got["c32"].view(torch.int32)) and torch.equal(v["tri"], got["tri"])
+        assert torch.equal(v["sharp"], got["sharp"]) and torch.equal(v["lam"], got["lam"])
+        sc.close()
