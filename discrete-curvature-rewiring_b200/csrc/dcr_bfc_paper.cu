@@ -165,7 +165,11 @@ struct PaperPlan {           // lives at the head of the scratch buffer
     unsigned int group_cursor[N_CLASSES];        // range reservation inside the classes
     unsigned int class_begin[N_CLASSES + 1];
     unsigned int next[N_CLASSES + 1];            // work-stealing counters
-    unsigned int n_runs[2];                      // run tables of the group classes (G1, G2)
+    unsigned int n_runs[2];                      // run tables of the group classes (G1, G2): the LIGHT runs, filled from the back
+    unsigned int n_runs_heavy[2];                // ... and the HEAVY runs, filled from the front and drained first
+    unsigned int coop_tier[2][4], coop_cur[2][4];   // cooperative edges of C1 / C2 by size tier (largest first): counts, cursors
+    unsigned long long light_stream[2];          // streamed entries / 64 of the light edges of G1 / G2
+    unsigned int l0_heavy, l0_heavy_cursor, l0_heavy_next;   // L0 edges with a stream > SIZE_B1: first in the class range, drained first
     unsigned int n_split[2], split_items[2], split_next[2];   // split edges of the kernels of G1 / G2
     unsigned long long shash_used[2];            // words of the hash pools handed out
     SplitEdge split[2][MAX_SPLIT];
@@ -192,6 +196,7 @@ struct PaperArgs {
     uint32_t* grp;         // [5][n] (start, count) of the vertex's light group and of its cooperative group in `order`, #runs
     uint2* runs;           // [2][max_runs] (first position, length) of the runs of the group classes
     uint32_t max_runs;
+    int group_ctas;        // CTAs of a group kernel (run sizing)
     int n;
     int dense;             // 1: n is small enough for an exact bitmap of N(va) in shared memory (classes L0 + G1 only)
     uint32_t* gtables;     // class-X tables in global memory, gslots per CTA
@@ -258,20 +263,62 @@ __device__ __forceinline__ double paper_value(int d1, int d2, int tri, int sq1, 
 // planning kernels: S_v, per-edge class/bucket, bucket offsets, order
 // ------------------------------------------------------------------------------------------------------------
 // S_v = sum of the degrees of v's neighbours (the two row offsets of a neighbour share a sector).
-__global__ void node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
-                              int64_t* __restrict__ node_s) {
-    const int lane = threadIdx.x & 31;
-    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (v >= n) return;
-    const int b = rowptr[v], e = rowptr[v + 1];
-    int64_t s = 0;
-    for (int p = b + lane; p < e; p += 32) {
-        const int k = colidx[p];
-        s += rowptr[k + 1] - rowptr[k];
-    }
+// 32 vertices per 256-thread CTA.  Rows of up to 64 entries: eight lanes per vertex (the average degree of the benchmark
+// graphs is 14-76: a warp per vertex leaves most lanes idle); rows of up to 2048 entries: one warp; longer rows (hubs: a
+// single warp would walk 6893 entries for 100 us after the rest of the kernel is done): the whole CTA.
+__global__ void __launch_bounds__(256) node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                     int n, int64_t* __restrict__ node_s) {
+    __shared__ long long s_part[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid & 7;
+    const int v0 = blockIdx.x * 32;
+    auto row_sum = [&](int b, int e, int first, int step) {
+        long long s = 0;
+        for (int p = b + first; p < e; p += step) {
+            const int k = colidx[p];
+            s += rowptr[k + 1] - rowptr[k];
+        }
+        return s;
+    };
+    {
+        const int v = v0 + (tid >> 3);
+        long long s = 0;
+        bool mine = false;
+        if (v < n) {
+            const int b = rowptr[v], e = rowptr[v + 1];
+            mine = e - b <= 64;
+            if (mine) s = row_sum(b, e, sub, 8);
+        }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (lane == 0) node_s[v] = s;
+        for (int o = 4; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (mine && sub == 0) node_s[v] = s;
+    }
+    for (int q = warp; q < 32; q += 8) {
+        const int v = v0 + q;
+        if (v >= n) break;
+        const int b = rowptr[v], e = rowptr[v + 1];
+        if (e - b <= 64 || e - b > 2048) continue;
+        long long s = row_sum(b, e, lane, 32);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) node_s[v] = s;
+    }
+    for (int q = 0; q < 32; ++q) {
+        const int v = v0 + q;
+        if (v >= n) break;
+        const int b = rowptr[v], e = rowptr[v + 1];
+        if (e - b <= 2048) continue;                      // (block-uniform)
+        long long s = row_sum(b, e, tid, 256);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        __syncthreads();
+        if (lane == 0) s_part[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            long long t = 0;
+            for (int w = 0; w < 8; ++w) t += s_part[w];
+            node_s[v] = t;
+        }
+    }
 }
 
 constexpr int BUCKET_TRIVIAL = 255, BUCKET_SPLIT = 254;
@@ -300,9 +347,23 @@ __device__ __forceinline__ EdgeRole edge_role(const PaperArgs& a, int i, int j, 
     return r;
 }
 
+// Cooperative edges (one CTA per edge) are drained largest first: the CTA that would otherwise pull a 98304-entry
+// stream last holds the kernel's tail.  Four size tiers inside the class range instead of a sort.
+__device__ __forceinline__ int coop_tier_of(long long stream) {
+    return stream >= 65536 ? 0 : (stream >= 40960 ? 1 : (stream >= 24576 ? 2 : 3));
+}
+// Light-group streams are accumulated per tested endpoint in units of RUN_UNIT entries (32-bit counters)
+constexpr int RUN_UNIT_SHIFT = 6;
+
 __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
     __shared__ unsigned int s_grp[N_CLASSES + 1];
+    __shared__ unsigned int s_tier[2][4];
+    __shared__ unsigned long long s_stream[2];
+    __shared__ unsigned int s_l0h;
+    if (threadIdx.x == 0) s_l0h = 0;
     if (threadIdx.x <= N_CLASSES) s_grp[threadIdx.x] = 0;
+    if (threadIdx.x < 8) s_tier[threadIdx.x >> 2][threadIdx.x & 3] = 0;
+    if (threadIdx.x < 2) s_stream[threadIdx.x] = 0;
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.count) {
@@ -338,12 +399,26 @@ __global__ void __launch_bounds__(256) classify_kernel(PaperArgs a) {
             } else {
                 a.bucket[t] = (uint8_t)r.cls;
                 atomicAdd(&s_grp[r.cls], 1u);
-                atomicAdd(&a.va_cnt[(size_t)r.slot * a.n + r.va], 1u);
+                if (r.slot == 0) {
+                    atomicAdd(&s_tier[r.cls == CL_C2 ? 1 : 0][coop_tier_of(r.stream)], 1u);
+                } else {
+                    atomicAdd(&a.va_cnt[(size_t)r.slot * a.n + r.va], 1u);
+                    if (r.cls == CL_L0 && r.slot == 1) atomicAdd(&s_l0h, 1u);
+                    if (r.cls == CL_G1 || r.cls == CL_G2) {
+                        const unsigned int units = (unsigned int)(r.stream >> RUN_UNIT_SHIFT) + 1u;
+                        atomicAdd(&a.va_cnt[(size_t)N_SLOTS * a.n + r.va], units);
+                        atomicAdd(&s_stream[run_table_of(r.cls)], (unsigned long long)units);
+                    }
+                }
             }
         }
     }
     __syncthreads();
     if (threadIdx.x <= N_CLASSES && s_grp[threadIdx.x]) atomicAdd(&a.plan->grouped[threadIdx.x], s_grp[threadIdx.x]);
+    if (threadIdx.x < 8 && s_tier[threadIdx.x >> 2][threadIdx.x & 3])
+        atomicAdd(&a.plan->coop_tier[threadIdx.x >> 2][threadIdx.x & 3], s_tier[threadIdx.x >> 2][threadIdx.x & 3]);
+    if (threadIdx.x < 2 && s_stream[threadIdx.x]) atomicAdd(&a.plan->light_stream[threadIdx.x], s_stream[threadIdx.x]);
+    if (threadIdx.x == 0 && s_l0h) atomicAdd(&a.plan->l0_heavy, s_l0h);
 }
 
 // position of rank s inside a group of `cnt` edges that starts at `gstart` (see RUN_EDGES)
@@ -352,12 +427,23 @@ __device__ __forceinline__ unsigned int run_layout_pos(unsigned int gstart, unsi
     const unsigned int r = s % R;
     return gstart + r * q + min(r, rem) + s / R;
 }
-__device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned int gstart, unsigned int cnt, unsigned int R) {
+// heavy runs are appended at the front of the class's run table, light runs at its back (sum of R <= #edges < max_runs)
+__device__ __forceinline__ void emit_runs(const PaperArgs& a, int cls, unsigned int gstart, unsigned int cnt, unsigned int R,
+                                          bool heavy) {
     const unsigned int q = cnt / R, rem = cnt % R;
     const int tbl = run_table_of(cls);
-    const unsigned int base = atomicAdd(&a.plan->n_runs[tbl], R);
-    for (unsigned int r = 0; r < R; ++r)
-        a.runs[(size_t)tbl * a.max_runs + base + r] = make_uint2(gstart + r * q + min(r, rem), q + (r < rem ? 1u : 0u));
+    uint2* table = a.runs + (size_t)tbl * a.max_runs;
+    const unsigned int base = atomicAdd(heavy ? &a.plan->n_runs_heavy[tbl] : &a.plan->n_runs[tbl], R);
+    for (unsigned int r = 0; r < R; ++r) {
+        const unsigned int at = heavy ? base + r : a.max_runs - 1u - (base + r);
+        table[at] = make_uint2(gstart + r * q + min(r, rem), q + (r < rem ? 1u : 0u));
+    }
+}
+// largest stream (in run units) one run should hold: every CTA of the group kernel gets about 8 runs' worth of the
+// pass, within [64 Ki, 512 Ki] entries — a run is the unit of work stealing, and the last one pulled is the tail
+__device__ __forceinline__ unsigned int run_cap_units(const PaperArgs& a, int tbl) {
+    const unsigned long long per = a.plan->light_stream[tbl] / (unsigned long long)(8 * max(a.group_ctas, 1));
+    return (unsigned int)min(max(per, (unsigned long long)(65536 >> RUN_UNIT_SHIFT)), (unsigned long long)(524288 >> RUN_UNIT_SHIFT));
 }
 
 // Every vertex that is the tested endpoint of edges reserves a contiguous range of `order` inside the class of its
@@ -369,7 +455,9 @@ __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
     // ranges are reserved per block (shared-memory counters, then ONE global atomic per class and block): one global
     // atomic per vertex would serialise ~n operations on a handful of addresses
     __shared__ unsigned int s_cnt[N_CLASSES], s_base[N_CLASSES], s_begin[N_CLASSES + 1];
+    __shared__ unsigned int s_l0h_cnt, s_l0h_base;
     if (threadIdx.x < N_CLASSES) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_l0h_cnt = 0;
     if (threadIdx.x == 0) {                       // class ranges: every block derives them; block 0 publishes them
         unsigned int acc = 0;
         for (int c = 0; c < N_CLASSES; ++c) { s_begin[c] = acc; acc += a.plan->grouped[c]; }
@@ -386,41 +474,52 @@ __global__ void __launch_bounds__(256) plan_groups_kernel(PaperArgs a) {
     }
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int c[N_SLOTS] = {0, 0, 0, 0}, own = 0, own_off = 0, coop_off = 0;
-    int cls = 0, cc = 0;
+    unsigned int c[N_SLOTS] = {0, 0, 0, 0}, own = 0, own_off = 0, heavy = 0, heavy_off = 0;
+    int cls = 0;
     if (v < a.n) {
+        cls = degree_class(a.rowptr[v + 1] - a.rowptr[v], a.dense);
 #pragma unroll
         for (int q = 0; q < N_SLOTS; ++q) {
             c[q] = a.va_cnt[(size_t)q * a.n + v];
             if (q > 0) {
-                a.va_cnt[(size_t)q * a.n + v] = own;        // rank offset of the bucket inside the light group
-                own += c[q];
+                if (cls == CL_L0 && q == 1) {               // L0: the heaviest bucket forms a group of its own (see below)
+                    a.va_cnt[(size_t)q * a.n + v] = 0;
+                    heavy = c[q];
+                } else {
+                    a.va_cnt[(size_t)q * a.n + v] = own;    // rank offset of the bucket inside the light group
+                    own += c[q];
+                }
             }
         }
         a.va_cnt[v] = 0;
-        cls = degree_class(a.rowptr[v + 1] - a.rowptr[v], a.dense);
-        cc = coop_class_of(cls);
         if (own) own_off = atomicAdd(&s_cnt[cls], own);
-        if (c[0]) coop_off = atomicAdd(&s_cnt[cc], c[0]);
+        if (heavy) heavy_off = atomicAdd(&s_l0h_cnt, heavy);
     }
     __syncthreads();
+    // The class range of L0 starts with ALL its heavy edges (stream > SIZE_B1, grouped by tested endpoint), then the rest:
+    // the warps of the L0 kernel pull the long streams first, one at a time, so that no warp is left with a 16384-entry
+    // stream (150 us) when the others run out of work.
     if (threadIdx.x < N_CLASSES && s_cnt[threadIdx.x])
-        s_base[threadIdx.x] = s_begin[threadIdx.x] + atomicAdd(&a.plan->group_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+        s_base[threadIdx.x] = s_begin[threadIdx.x] + (threadIdx.x == CL_L0 ? a.plan->l0_heavy : 0u) +
+                              atomicAdd(&a.plan->group_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_l0h_cnt) s_l0h_base = s_begin[CL_L0] + atomicAdd(&a.plan->l0_heavy_cursor, s_l0h_cnt);
     __syncthreads();
+    if (heavy) {
+        a.grp[(size_t)2 * a.n + v] = s_l0h_base + heavy_off;
+        a.grp[(size_t)3 * a.n + v] = heavy;
+    }
     if (own) {
         const unsigned int gstart = s_base[cls] + own_off;
         a.grp[v] = gstart;
         a.grp[(size_t)a.n + v] = own;
         if (cls == CL_G1 || cls == CL_G2) {
-            unsigned int R = (own + RUN_EDGES - 1) / RUN_EDGES;
+            // runs by edge count AND by stream: 64 edges of 16384 entries each would hold one CTA for a millisecond
+            const unsigned int units = a.va_cnt[(size_t)N_SLOTS * a.n + v], cap = run_cap_units(a, run_table_of(cls));
+            unsigned int R = max((own + RUN_EDGES - 1) / RUN_EDGES, (units + cap - 1) / cap);
             R = max(1u, min(R, own));
             a.grp[(size_t)4 * a.n + v] = R;
-            emit_runs(a, cls, gstart, own, R);
+            emit_runs(a, cls, gstart, own, R, /*heavy=*/(unsigned long long)units * 4ull >= (unsigned long long)cap * R);
         }
-    }
-    if (c[0]) {
-        a.grp[(size_t)2 * a.n + v] = s_base[cc] + coop_off;
-        a.grp[(size_t)3 * a.n + v] = c[0];
     }
 }
 
@@ -433,11 +532,19 @@ __global__ void __launch_bounds__(256) order_kernel(PaperArgs a) {
     const int i = a.esrc[e], j = a.edst[e];
     const int di = a.rowptr[i + 1] - a.rowptr[i], dj = a.rowptr[j + 1] - a.rowptr[j];
     const EdgeRole r = edge_role(a, i, j, di, dj);
-    const size_t slot = (size_t)r.slot * a.n + r.va;
-    const unsigned int s = a.va_cnt[slot] + atomicAdd(&a.va_cur[slot], 1u);
-    const size_t g = (r.slot == 0 ? (size_t)2 * a.n : 0) + r.va;
-    const unsigned int gstart = a.grp[g], cnt = a.grp[g + a.n];
-    const unsigned int pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, a.grp[(size_t)4 * a.n + r.va], s) : gstart + s;
+    unsigned int pos;
+    if (r.slot == 0) {            // cooperative edge: by size tier inside the class range, largest first
+        const int k = r.cls == CL_C2 ? 1 : 0, tier = coop_tier_of(r.stream);
+        unsigned int base = a.plan->class_begin[r.cls];
+        for (int q = 0; q < tier; ++q) base += a.plan->coop_tier[k][q];
+        pos = base + atomicAdd(&a.plan->coop_cur[k][tier], 1u);
+    } else {
+        const size_t slot = (size_t)r.slot * a.n + r.va;
+        const unsigned int s = a.va_cnt[slot] + atomicAdd(&a.va_cur[slot], 1u);
+        const bool l0_heavy = r.cls == CL_L0 && r.slot == 1;
+        const unsigned int gstart = a.grp[(l0_heavy ? (size_t)2 * a.n : 0) + r.va], cnt = a.grp[(size_t)a.n + r.va];
+        pos = (r.cls == CL_G1 || r.cls == CL_G2) ? run_layout_pos(gstart, cnt, a.grp[(size_t)4 * a.n + r.va], s) : gstart + s;
+    }
     a.order[pos] = (uint32_t)t;
     a.ova[pos] = (uint32_t)r.va;
 }
@@ -1295,12 +1402,21 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
     cx.colidx = a.colidx; cx.tab = tab; cx.bm = bm; cx.cnt = cnt; cx.mask = 0; cx.shift = 0;
     cx.q = base + WSTATE_INTS; cx.qn = 0; cx.lcnt = st + WS_LCNT;
     cx.bm_off = (uint32_t)warp * (L0_BITS / 8);
+    const unsigned int n_heavy = a.plan->l0_heavy;       // the class range starts with the long streams: one per grab
+    bool heavy_phase = n_heavy > 0;
     while (true) {
-        unsigned int idx0 = 0;
-        if (lane == 0) idx0 = atomicAdd(ws.next, (unsigned)DCR_L0_GRAB);
-        idx0 = __shfl_sync(FULL, idx0, 0);
-        if (idx0 >= ws.count) break;
-        const unsigned int idx1 = min(ws.count, idx0 + (unsigned)DCR_L0_GRAB);
+        unsigned int idx0 = 0, idx1;
+        if (heavy_phase) {
+            if (lane == 0) idx0 = atomicAdd(&a.plan->l0_heavy_next, 1u);
+            idx0 = __shfl_sync(FULL, idx0, 0);
+            if (idx0 >= n_heavy) { heavy_phase = false; continue; }
+            idx1 = idx0 + 1u;
+        } else {
+            if (lane == 0) idx0 = atomicAdd(ws.next, (unsigned)DCR_L0_GRAB);
+            idx0 = __shfl_sync(FULL, idx0, 0) + n_heavy;
+            if (idx0 >= ws.count) break;
+            idx1 = min(ws.count, idx0 + (unsigned)DCR_L0_GRAB);
+        }
         for (unsigned int q = idx0; q < idx1; ++q) {
             const int va = (int)ova[q];
             if (va != cur_va) {
@@ -1490,6 +1606,20 @@ __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& m
 }
 
 
+#ifdef DCR_PAPER_TRACE
+// debug: per CTA of the group kernel [t_begin, t_phase1_end, t_end, longest item ns, its (phase<<30 | index), #items]
+__device__ unsigned long long g_trace[4096 * 6];
+__device__ unsigned long long g_trace_cnt[8];   // [0] deferred edges [1] their stream [2] CTA-path edges that needed the big hash
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(...) __VA_ARGS__
+#else
+#define TRACE(...)
+#endif
+
 // cooperative edge with the CTA-wide shared hash; on overflow once more with this CTA's hash in global memory
 // (2*ghash_cap words, ghash_cap >= 2 * max degree: it cannot fill up).  Ends with the CTA synchronised.
 template <int NWARPS, int CAP, bool DENSE>
@@ -1498,6 +1628,7 @@ __device__ __forceinline__ void cta_edge_retry(const PaperArgs& a, const Member<
                                                int* s_big) {
     cta_edge<NWARPS, DENSE>(a, mem, t, va, st_all, tset_sh, mh_all, NWARPS * CAP, q_all, s_acc, s_big, 0, 1, nullptr);
     __syncthreads();
+    TRACE(if (threadIdx.x == 0) { atomicAdd(&g_trace_cnt[3], 1ull); if (s_acc[5]) atomicAdd(&g_trace_cnt[2], 1ull); })
     if (s_acc[5]) {
         uint32_t* gh = a.ghash + (size_t)blockIdx.x * 2 * a.ghash_cap;
         for (uint32_t p = threadIdx.x; p < 2 * a.ghash_cap; p += NWARPS * 32) gh[p] = 0u;
@@ -1508,18 +1639,6 @@ __device__ __forceinline__ void cta_edge_retry(const PaperArgs& a, const Member<
     }
 }
 
-#ifdef DCR_PAPER_TRACE
-// debug: per CTA of the group kernel [t_begin, t_phase1_end, t_end, longest item ns, its (phase<<30 | index), #items]
-__device__ unsigned long long g_trace[4096 * 6];
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define TRACE(...) __VA_ARGS__
-#else
-#define TRACE(...)
-#endif
 
 // (Re)build the membership structures of N(va) for the CTA; all threads; ends synchronised.  One out-of-line copy (three
 // call sites in the group kernel).
@@ -1599,7 +1718,8 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
         for (int s = tid; s < bm_words; s += THREADS) bm[s] = 0u;
     }
     const uint2* runs = a.runs + (size_t)run_table_of(cls) * a.max_runs;
-    const unsigned int n_runs = a.plan->n_runs[run_table_of(cls)];
+    const unsigned int n_heavy = a.plan->n_runs_heavy[run_table_of(cls)];
+    const unsigned int n_runs = n_heavy + a.plan->n_runs[run_table_of(cls)];   // heavy runs first, then the light ones
     const int ccls = coop_class_of(cls);
     const WorkSource cws = work_source(a, ccls);
     const uint32_t* cova = a.ova + a.plan->class_begin[ccls];
@@ -1662,7 +1782,7 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
         __syncthreads();
         if (s_idx >= n_runs) break;
         TRACE(const unsigned long long tr_a = gtimer();)
-        const uint2 run = runs[s_idx];                    // (first position in `order`, length)
+        const uint2 run = runs[s_idx < n_heavy ? s_idx : a.max_runs - 1u - (s_idx - n_heavy)];   // (first position in `order`, length)
         const uint32_t* ord = a.order + run.x;
         const int q_end = (int)run.y;
         const int va = (int)a.ova[run.x];
@@ -1678,6 +1798,7 @@ __global__ void __launch_bounds__(NWARPS * 32, CTAS_PER_SM) paper_group_kernel(P
         }
         __syncthreads();                                  // every warp is done with the run
         const int nd = s_ndefer;
+        TRACE(if (tid == 0 && nd) atomicAdd(&g_trace_cnt[0], (unsigned long long)nd);)
         for (int d = 0; d < nd; ++d)
             cta_edge_retry<NWARPS, CAP, DENSE>(a, mem, s_defer[d], va, st_all, tb_coop, mh_all, q_all, s_acc, s_big);
         if (nd > 0 && lane == 0) st[WS_NDIST] = 0;
@@ -1737,7 +1858,7 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     size_t off = 0;
     // plan | va_cnt | va_cur are adjacent: one memset clears the three of them
     L.plan = off; off = align_up(off + sizeof(PaperPlan), 256);
-    L.va_cnt = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
+    L.va_cnt = off; off = align_up(off + (size_t)(N_SLOTS + 1) * n * sizeof(uint32_t), 256);   // + the light-group streams
     L.va_cur = off; off = align_up(off + (size_t)N_SLOTS * n * sizeof(uint32_t), 256);
     L.zero_bytes = off;
     L.node_s = off; off = align_up(off + (size_t)n * sizeof(int64_t), 256);
@@ -1745,8 +1866,8 @@ static ScratchLayout scratch_layout(int n, int max_degree, int64_t count) {
     L.order = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.ova = off; off = align_up(off + (size_t)count * sizeof(uint32_t), 256);
     L.grp = off; off = align_up(off + (size_t)5 * n * sizeof(uint32_t), 256);
-    // a light group of c edges has ceil(c / RUN_EDGES) runs; there are at most min(n, count) light groups
-    L.max_runs = (uint32_t)(count / RUN_EDGES + std::min<int64_t>((int64_t)n, count) + 1);
+    // a light group of c edges is cut into at most c runs (by edge count and by stream)
+    L.max_runs = (uint32_t)(count + 1);
     L.runs = off; off = align_up(off + (size_t)2 * L.max_runs * sizeof(uint2), 256);
     // tables of the CTA-team kernel (class X: tested endpoints beyond the shared-memory tables, hashed mode only)
     L.gslots = 0;
@@ -1817,6 +1938,7 @@ static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int m
     a.grp = (uint32_t*)(base + L.grp);
     a.runs = (uint2*)(base + L.runs);
     a.max_runs = L.max_runs;
+    a.group_ctas = L.group_ctas;
     a.n = n;
     a.dense = use_dense_mode(n) ? 1 : 0;
     a.gtables = (uint32_t*)(base + L.gtables);
@@ -1828,7 +1950,7 @@ static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int m
     a.split_item = (uint32_t*)(base + L.split_item);
 
     DCR_CUDA(cudaMemsetAsync(base + L.plan, 0, L.zero_bytes - L.plan, st));      // plan, va_cnt, va_cur
-    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s);
+    node_s_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(rowptr, colidx, n, node_s);
     DCR_LAUNCH_CHECK();
     const unsigned tb = (unsigned)((count + 255) / 256);
     classify_kernel<<<tb, 256, 0, st>>>(a);
@@ -1886,8 +2008,10 @@ static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int m
     const int n_aux = a.dense ? 1 : N_AUX;
     for (int q = 0; q < n_aux; ++q) DCR_CUDA(cudaStreamWaitEvent(aux[q], ev_fork, 0));
     if (a.dense) {
+#ifndef DCR_ONLY_LIGHT     // (tuning builds: time one of the two edge kernels alone)
         k_gd<<<sms * GD_CTAS_PER_SM, GD_WARPS * 32, smem_gd, st>>>(a, CL_G1, dense_words);
         DCR_LAUNCH_CHECK();
+#endif
     } else {
         if (L.gslots) {
             paper_edge_kernel<BIG_THREADS, BIG_SLOTS, true><<<L.g_ctas, BIG_THREADS, smem_x, aux[2]>>>(a, CL_X);
@@ -1898,8 +2022,10 @@ static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int m
         k_g1<<<sms * G1_CTAS_PER_SM, G1_WARPS * 32, smem_g1, aux[1]>>>(a, CL_G1, 0);
         DCR_LAUNCH_CHECK();
     }
+#ifndef DCR_ONLY_GROUP
     paper_light_warp_kernel<<<sms * L0_CTAS_PER_SM, L0_WARPS * 32, smem_l0, aux[0]>>>(a);
     DCR_LAUNCH_CHECK();
+#endif
     for (int q = 0; q < n_aux; ++q) {
         DCR_CUDA(cudaEventRecord(ev_join[q], aux[q]));
         DCR_CUDA(cudaStreamWaitEvent(st, ev_join[q], 0));
@@ -1924,6 +2050,14 @@ extern "C" int dcr_bfc_paper(const int32_t* rowptr, const int32_t* colidx, int n
 #ifdef DCR_PAPER_TRACE
 extern "C" int dcr_paper_trace_read(unsigned long long* host_out, int n_ctas) {
     return cudaMemcpyFromSymbol(host_out, dcr::g_trace, sizeof(unsigned long long) * 6 * n_ctas) == cudaSuccess ? 0 : 1;
+}
+extern "C" int dcr_paper_trace_counters(unsigned long long* host_out, int reset) {
+    if (cudaMemcpyFromSymbol(host_out, dcr::g_trace_cnt, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        if (cudaMemcpyToSymbol(dcr::g_trace_cnt, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
 }
 #endif
 
@@ -2073,8 +2207,12 @@ __global__ void edge_cost_kernel(const int32_t* __restrict__ rowptr, const int64
     if (min(di, dj) <= 1) { cost[e] = 2; return; }
     const int64_t ca = node_s[j] - di, cb = node_s[i] - dj;
     const bool swapped = cb < ca;                    // stream i's side
-    const int64_t stream = swapped ? cb : ca, heads = swapped ? di : dj;
-    cost[e] = stream + 24 * heads + 160;
+    const int64_t stream = swapped ? cb : ca, heads = swapped ? di : dj, da = swapped ? dj : di;
+    // Relative cost per streamed entry of the three paths, fitted to the measured edge-kernel times of 44 contiguous
+    // ranges of the arxiv-shaped edge list (profiles/cost_model_fit.py): warp path with the warp-private table (d_a <=
+    // 128) 1, warp path of the group kernel 2, one CTA per edge (stream > COOP) 4.5.
+    const int64_t w2 = stream > COOP_G ? 9 : (da > CLASS_DA0 ? 4 : 2);      // weights x 2
+    cost[e] = (w2 * stream) / 2 + 24 * heads + 160;
 }
 }  // namespace dcr
 
@@ -2083,7 +2221,7 @@ extern "C" int dcr_bfc_paper_edge_cost(const int32_t* rowptr, const int32_t* col
                                        void* stream) {
     if (n <= 0 || n_edges <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    node_s_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, node_s_scratch);
+    node_s_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(rowptr, colidx, n, node_s_scratch);
     DCR_LAUNCH_CHECK();
     edge_cost_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(rowptr, node_s_scratch, esrc, edst, n_edges, out_cost);
     DCR_LAUNCH_CHECK();

@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+DCR_LIB_PATH=$PWD/build/libdcr_trace.so PROBE_WORLD=1 timeout 300 python profiles/range_tail_probe.py 2>&1 | tail -4
