@@ -369,6 +369,73 @@ def sdrf_bench(args, torch):
                            "iterations": sres["iterations_done"], "ms_total": e0.elapsed_time(e1), "status": sres["status"]}
     except Exception as exc:
         out["squirrel"] = {"unavailable": repr(exc)[:300]}
+    # the other loop flavours, same cora-shaped graph
+    def loop_rate(state, lp, bnd, tu, un):
+        u_dev = torch.from_numpy(un).cuda()
+        lg = torch.empty((lp, 8), dtype=torch.int32, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        r_, _ = state.run(lp, True, bnd, tu, u_dev, log=lg)
+        e1.record()
+        torch.cuda.synchronize()
+        state.close()
+        return r_["iterations_done"] / (e0.elapsed_time(e1) * 1e-3), r_["iterations_done"], r_["status"], lg.cpu().numpy()
+
+    def tuples(wlog_):
+        return [(r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
+                 -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
+                for r in wlog_]
+    try:
+        from dcr import lib as L_
+        from oracle.sdrf_classical import sdrf_classical_oracle
+        cl = {}
+        for ct, mode, bnd, tu in (("augmented", L_.SDRF_MODE_AUGMENTED, 0.5, 2), ("1d", L_.SDRF_MODE_1D, -6.0, 2),
+                                  ("haantjes", L_.SDRF_MODE_HAANTJES, 0.5, 2)):
+            crow, cord = graph.classical_order(ei, n)
+            rate, done, status, lg = loop_rate(sdrf.SdrfState(crow, cord, max_additions=loops, mode=mode), loops, bnd, tu, uni)
+            cpu_it = min(loops, 60)
+            t0 = time.perf_counter()
+            _, wl = sdrf_classical_oracle(ei, n, ct, cpu_it, True, bnd, tu, uni)
+            dtc = time.perf_counter() - t0
+            cl[ct] = {"iters_per_s": rate, "iterations": done, "status": status, "tau": tu, "removal_bound": bnd,
+                      "cpu_baseline": {"value": len(wl) / dtc, "unit": "iterations/s", "cores": 1, "kind": "port",
+                                       "sample": f"first {cpu_it} iterations, oracle/sdrf_classical.py — the statements of the "
+                                                 "reference's own CPU loop rewiring/sdrf_no_cuda.py at Python speed"},
+                      "prefix_matches_cpu": [tuple(int(v) for v in r) for r in lg[:len(wl)]] == tuples(wl),
+                      "speedup_vs_cpu": rate / (len(wl) / dtc)}
+        out["classical"] = cl
+    except Exception as exc:
+        out["classical"] = {"unavailable": repr(exc)[:300]}
+    try:
+        from dcr import lib as L_
+        rng = np.random.default_rng(7)
+        und = ei[:, ei[0] < ei[1]]
+        both = rng.random(und.shape[1]) < 0.5                       # half of the edges keep both directions
+        flip = rng.random(und.shape[1]) < 0.5
+        one = np.where(flip, und[::-1], und)
+        dei = np.concatenate([one, one[::-1][:, both]], axis=1)
+        dei = dei[:, rng.permutation(dei.shape[1])]
+        dl, dtau, dbound = min(loops, 300), 20, 0.5
+        duni = np.random.RandomState(9).random_sample(dl)
+        s_rp, s_ord, p_rp, p_ord = graph.digraph_order(dei, n)
+        rate, done, status, lg = loop_rate(sdrf.SdrfState(s_rp, s_ord, max_additions=dl, mode=L_.SDRF_MODE_BFC_DIRECTED,
+                                                          in_rowptr=p_rp, in_order=p_ord), dl, dbound, dtau, duni)
+        cpu_it = 4
+        t0 = time.perf_counter()
+        _, wl = sdrf_oracle(dei, n, cpu_it, True, dbound, dtau, duni, rounding="compiled", incremental_a2=False,
+                            is_undirected=False)
+        dtc = time.perf_counter() - t0
+        out["directed"] = {"workload": f"cora-shaped graph with one direction dropped on half of the edges ({dei.shape[1]} "
+                                       f"directed entries), is_undirected=False, {dl} iterations, tau={dtau}, bound={dbound}",
+                           "iters_per_s": rate, "iterations": done, "status": status,
+                           "cpu_baseline": {"value": len(wl) / dtc, "unit": "iterations/s", "cores": host_threads(),
+                                            "kind": "port", "sample": f"first {cpu_it} iterations, dense numpy restatement "
+                                                                      "(oracle/sdrf.py, is_undirected=False)"},
+                           "prefix_matches_cpu": [tuple(int(v) for v in r) for r in lg[:len(wl)]] == tuples(wl),
+                           "speedup_vs_cpu": rate / (len(wl) / dtc)}
+    except Exception as exc:
+        out["directed"] = {"unavailable": repr(exc)[:300]}
     # The reference's OWN numba kernels on this GPU (oracle/_ref PTX, built from /root/reference by oracle/build_ref.py,
     # loaded with the driver API) driven the reference's way: two A@A + an N^2 x N kernel per iteration, one .item()
     # per candidate.  A reported baseline ("the repo's numba bfc_cuda on the same B200"), present when oracle/_ref is.
@@ -685,6 +752,15 @@ def run_ours(args):
             line["dense"] = dense_bench(args, torch)
         except Exception as exc:
             line["dense"] = {"unavailable": repr(exc)[:300]}
+    if args.workload == "arxiv" and not args.no_cuda_flavour:
+        try:
+            cf = cuda_flavour_bench(args, torch, dist, csr, esrc, edst, rowptr, world, rank, dev, flush)
+        except Exception as exc:
+            if world > 1:
+                raise
+            cf = {"unavailable": repr(exc)[:300]}
+        if rank == 0:
+            line["cuda_flavour"] = cf
     if rank == 0 and not args.no_sdrf:
         line["sdrf"] = sdrf_bench(args, torch)
     if rank == 0:
@@ -692,6 +768,64 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cuda_flavour_bench(args, torch, dist, csr, esrc_np, edst_np, rowptr, world, rank, dev, flush):
+    """Full-graph CUDA-flavour BFC (balanced_forman_curvature of curvature/bfc_cuda.py:51-65 at the arxiv shape): one work
+    item per undirected edge, at N > 1 edge-range sharded with the all-gather of the supports fused between the two passes
+    (SURVEY.md §8e row 2).  Every rank takes part; returns the object on rank 0."""
+    from dcr import bfc
+    from dcr.dist import ShardedCudaBFC
+    E = int(esrc_np.size)
+    steps, warmup = max(5, min(args.steps, 20)), 3
+    sc = ShardedCudaBFC(csr)
+    for _ in range(warmup + (3 if world > 1 else 0)):
+        flush.zero_()
+        sc.run()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        out = sc.run()
+        ev[k][1].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sc.check()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t = torch.tensor(ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total = float(t.sum().item())
+    # parity: the per-entry kernels (the round-1 route) on a sample of entries of this rank's full arrays
+    ref = bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr))
+    entry = csr.undirected_edges()[2]
+    if entry is None:
+        deg = np.diff(rowptr.astype(np.int64))
+        rows = np.repeat(np.arange(deg.size), deg)
+        entry = torch.from_numpy(np.flatnonzero(rows < csr.colidx.cpu().numpy())).to(dev)
+    same = bool(torch.equal(out["c32"].view(torch.int32), ref["c32"][entry].view(torch.int32))) and \
+        bool(torch.equal(out["tri"], ref["tri"][entry]))
+    flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    deg = np.diff(rowptr.astype(np.int64))
+    b_alg = int((16 + 4 * (deg[esrc_np] + deg[edst_np]) + 24).sum()) + 8 * int(out["tri"].sum().item())
+    peak, peak_src = load_peaks()
+    res = {"workload": "arxiv-shaped synthetic graph: full-graph CUDA-flavour BFC (curvature/bfc_cuda.py) per undirected edge "
+                       "(tri, sharp, lambda, fp64 + fp32 value), supports all-gathered between the two passes at N > 1",
+           "value": E / (total / steps * 1e-3), "unit": "edges/s", "ms_per_step": total / steps, "steps": steps, "n_gpus": world,
+           "ranges": [int(b) for b in sc.bounds],
+           "all_ranks_bit_identical_to_per_entry_kernels": bool(flag.item()),
+           "roofline": {"bound": "hbm", "kernel": "edges_support_kernel + edges_closing_kernel (light + hub launches)",
+                        "algorithmic_bytes": b_alg, "achieved": b_alg / world / (total / steps * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": b_alg / world / (total / steps * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                        "model": "SURVEY.md §8d: 16 + 4(d_i+d_j) + 8 tri + 24 bytes per edge, per rank = total / N"}}
+    sc.close()
+    return res if rank == 0 else None
 
 
 _REAL_STDOUT = None
@@ -826,6 +960,7 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: fused peer-memory closing kernel (default) or NCCL all-gather")
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-cuda-flavour", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sdrf", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks")

@@ -263,6 +263,25 @@ __device__ __forceinline__ double paper_value(int d1, int d2, int tri, int sq1, 
 // planning kernels: S_v, per-edge class/bucket, bucket offsets, order
 // ------------------------------------------------------------------------------------------------------------
 // S_v = sum of the degrees of v's neighbours (the two row offsets of a neighbour share a sector).
+#ifdef DCR_NODE_S_WARP      // (tuning build: the round-1 kernel, one warp per vertex)
+__global__ void __launch_bounds__(256) node_s_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                     int n, int64_t* __restrict__ node_s) {
+    const int lane = threadIdx.x & 31;
+    for (int q = threadIdx.x >> 5; q < 32; q += 8) {
+        const int v = blockIdx.x * 32 + q;
+        if (v >= n) return;
+        const int b = rowptr[v], e = rowptr[v + 1];
+        int64_t s = 0;
+        for (int p = b + lane; p < e; p += 32) {
+            const int k = colidx[p];
+            s += rowptr[k + 1] - rowptr[k];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) node_s[v] = s;
+    }
+}
+#else
 // 32 vertices per 256-thread CTA.  Rows of up to 64 entries: eight lanes per vertex (the average degree of the benchmark
 // graphs is 14-76: a warp per vertex leaves most lanes idle); rows of up to 2048 entries: one warp; longer rows (hubs: a
 // single warp would walk 6893 entries for 100 us after the rest of the kernel is done): the whole CTA.
@@ -320,6 +339,8 @@ __global__ void __launch_bounds__(256) node_s_kernel(const int32_t* __restrict__
         }
     }
 }
+
+#endif
 
 constexpr int BUCKET_TRIVIAL = 255, BUCKET_SPLIT = 254;
 
