@@ -129,6 +129,27 @@ __device__ Best block_best(Best a, Reduce* r) {
     return out;
 }
 
+// two independent "smaller (v, key) wins" reductions in one go: three barriers instead of six
+__device__ void block_best2(Best& a, Best& b, Reduce* r, Reduce* r2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_best(a);
+    b = warp_best(b);
+    if (lane == 0) { r->v[warp] = a.v; r->k[warp] = a.key; r2->v[warp] = b.v; r2->k[warp] = b.key; }
+    __syncthreads();
+    if (warp < 2) {
+        Reduce* q = warp == 0 ? r : r2;
+        Best t;
+        t.v = lane < SDRF_WARPS ? q->v[lane] : INFINITY;
+        t.key = lane < SDRF_WARPS ? q->k[lane] : ~0ull;
+        t = warp_best(t);
+        if (lane == 0) q->best = t;
+    }
+    __syncthreads();
+    a = r->best;
+    b = r2->best;
+    __syncthreads();
+}
+
 __device__ long long block_sum_ll(long long v, Reduce* r) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -223,7 +244,7 @@ __device__ void block_exscan_pair(long long c, double d, long long* c_off, doubl
 // arena row edits (block-cooperative; arguments are block-uniform)
 // ------------------------------------------------------------------------------------------------------------
 struct LoopShared {
-    Reduce red;
+    Reduce red, red2;
     ScoreShared score;
     int x, y, xr, yr, have_min, have_max;
     float cxy, cmax;
@@ -264,6 +285,33 @@ __device__ void shift_left(T* a, int lo, int hi) {    // a[lo-1 .. hi-2] = a[lo 
     }
 }
 
+// the three arrays that follow the SORTED order of a row move together: one pass, two barriers per chunk
+__device__ void shift_right3(const SdrfDev& S, int lo, int hi) {
+    for (int top = hi; top > lo; top -= SDRF_THREADS) {
+        const int base = max(lo, top - SDRF_THREADS);
+        const int idx = base + threadIdx.x;
+        const bool on = idx < top;
+        int32_t c = 0, u = 0;
+        float f = 0.0f;
+        if (on) { c = S.col[idx]; u = S.supp[idx]; f = S.c32[idx]; }
+        __syncthreads();
+        if (on) { S.col[idx + 1] = c; S.supp[idx + 1] = u; S.c32[idx + 1] = f; }
+        __syncthreads();
+    }
+}
+__device__ void shift_left3(const SdrfDev& S, int lo, int hi) {
+    for (int base = lo; base < hi; base += SDRF_THREADS) {
+        const int idx = base + threadIdx.x;
+        const bool on = idx < hi;
+        int32_t c = 0, u = 0;
+        float f = 0.0f;
+        if (on) { c = S.col[idx]; u = S.supp[idx]; f = S.c32[idx]; }
+        __syncthreads();
+        if (on) { S.col[idx - 1] = c; S.supp[idx - 1] = u; S.c32[idx - 1] = f; }
+        __syncthreads();
+    }
+}
+
 // make room for one more entry in row v (relocate to the arena top with doubled capacity when full)
 __device__ bool row_reserve(const SdrfDev& S, int v, LoopShared* sh) {
     const int len = S.rlen[v], cap = S.rcap[v], start = S.rstart[v];
@@ -297,9 +345,7 @@ __device__ bool row_insert(const SdrfDev& S, int v, int key, LoopShared* sh) {
     const int start = S.rstart[v], len = S.rlen[v];
     const int pos = start + lower_bound(S.col, start, len, key);
     __syncthreads();
-    shift_right(S.col, pos, start + len);
-    shift_right(S.supp, pos, start + len);
-    shift_right(S.c32, pos, start + len);
+    shift_right3(S, pos, start + len);
     if (threadIdx.x == 0) {
         S.col[pos] = key;
         S.supp[pos] = 0;
@@ -322,9 +368,7 @@ __device__ void row_delete(const SdrfDev& S, int v, int key, LoopShared* sh) {
         if (S.ord[start + t] == key) sh->edit_pos = start + t;
     __syncthreads();
     const int opos = sh->edit_pos;
-    shift_left(S.col, pos + 1, start + len);
-    shift_left(S.supp, pos + 1, start + len);
-    shift_left(S.c32, pos + 1, start + len);
+    shift_left3(S, pos + 1, start + len);
     shift_left(S.ord, opos + 1, start + len);
     if (threadIdx.x == 0) {
         S.owner[start + len - 1] = -1;
@@ -556,32 +600,21 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
         // Pass 1 reads only the curvatures (free slots hold 0, which is neither < 0 nor > 0) and reduces the two
         // extreme VALUES; pass 2 visits the few slots that attain them and reduces the first row-major key.
         // (Directed loop: predecessor rows keep c32 = 0, so only successor entries can attain an extreme.)
-        float vmin = 0.0f, vmax = 0.0f;
+        // One pass: every thread keeps its best (value, first row-major key) for the minimum and for the maximum (the
+        // key is only fetched when a slot improves or ties the thread's current best), then ONE fused block reduction.
+        Best bmin{0.0f, ~0ull}, bmax{0.0f, ~0ull};   // bmax holds the NEGATED value
         for (int s = tid; s < top; s += SDRF_THREADS) {
             const float v = S.c32[s];
-            vmin = fminf(vmin, v);
-            vmax = fmaxf(vmax, v);
-        }
-        {
-            Best a = block_best(Best{vmin, 0ull}, &sh.red);
-            Best b = block_best(Best{-vmax, 0ull}, &sh.red);
-            vmin = a.v;
-            vmax = -b.v;
-        }
-        Best bmin{0.0f, ~0ull}, bmax{0.0f, ~0ull};   // bmax holds the NEGATED value
-        if (vmin < 0.0f || vmax > 0.0f) {
-            unsigned long long kmin = ~0ull, kmax = ~0ull;
-            for (int s = tid; s < top; s += SDRF_THREADS) {
-                const float v = S.c32[s];
-                if ((v == vmin && vmin < 0.0f) || (v == vmax && vmax > 0.0f)) {
-                    const unsigned long long key = ((unsigned long long)(unsigned)S.owner[s] << 32) | (unsigned)S.col[s];
-                    if (v == vmin && vmin < 0.0f) kmin = min(kmin, key);
-                    if (v == vmax && vmax > 0.0f) kmax = min(kmax, key);
-                }
+            if (v < 0.0f && v <= bmin.v) {
+                const unsigned long long key = ((unsigned long long)(unsigned)S.owner[s] << 32) | (unsigned)S.col[s];
+                if (v < bmin.v || key < bmin.key) { bmin.v = v; bmin.key = key; }
             }
-            bmin = block_best(Best{vmin < 0.0f ? vmin : 0.0f, kmin}, &sh.red);
-            bmax = block_best(Best{vmax > 0.0f ? -vmax : 0.0f, kmax}, &sh.red);
+            if (v > 0.0f && -v <= bmax.v) {
+                const unsigned long long key = ((unsigned long long)(unsigned)S.owner[s] << 32) | (unsigned)S.col[s];
+                if (-v < bmax.v || key < bmax.key) { bmax.v = -v; bmax.key = key; }
+            }
         }
+        block_best2(bmin, bmax, &sh.red, &sh.red2);
         if (tid == 0) {
             sh.have_min = bmin.v < 0.0f;
             sh.x = sh.have_min ? (int)(bmin.key >> 32) : 0;
