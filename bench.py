@@ -855,7 +855,7 @@ def dense_bench(args, torch) -> dict:
     E = int(esrc.size)
     csr = bfc.DeviceCSR.from_host(rowptr, col)
     n_pad = (n + 127) // 128 * 128
-    ws = torch.empty(int(bfc.L.load().dcr_bfc_support_tc_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(int(bfc.L.load().dcr_bfc_support_tc_workspace_bytes(n, csr.nnz)), dtype=torch.uint8, device="cuda")
     tri = torch.empty(csr.nnz, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     steps, warmup = max(5, min(args.steps, 20)), 3
@@ -891,7 +891,8 @@ def dense_bench(args, torch) -> dict:
         "value": E / (ms_full * 1e-3), "unit": "edges/s", "ms_per_step": ms_full, "steps": steps,
         "dtype": "int8 x int8 -> int32 (tcgen05 kind::i8), f64 closing formula",
         "outputs_bit_identical_to_sparse_path": same,
-        "roofline": {"bound": "tensor", "kernel": "tc_support_kernel (+ the operand fill of the same call)",
+        "roofline": {"bound": "tensor", "kernel": "tc_support_kernel (+ the operand fill and the mirror pass of the same call); achieved = the FULL product's "
+                               "2*N_pad^3 ops / time — A*A is symmetric, the kernel issues the upper-triangular half of the MMAs",
                      "achieved": ops / (ms_tc * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s (int8)",
                      "frac": ops / (ms_tc * 1e-3) / 1e12 / peak_i8, "peak_source": peak_src,
                      "traffic": None, "support_tc_ms": ms_tc, "ops": ops},

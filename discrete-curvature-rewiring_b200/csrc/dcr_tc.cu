@@ -15,6 +15,8 @@
 //                           accumulators in TMEM (128 lanes x 128 columns of int32); tcgen05.commit frees the stage
 //   warps 2-5 epilogue      tcgen05.ld 32x32b.x32 (each warp its 32-lane quarter), then per row: walk the 128-byte
 //                           row segment of A and store acc[c] for every non-zero A[i, j] at its CSR position
+// A·A is symmetric: only the upper-triangular tiles are computed (half the MMAs); a coalesced pass over the CSR then
+// copies every value to the reverse entry below the block diagonal.
 // Roofline: tensor-bound, 2·N_pad³ int8 ops.  Evidence: UTCIMMA / UTMALDG / LDTM in the SASS (cuobjdump), and
 // sm__pipe_tensor_cycles_active under ncu.
 #include <cuda.h>
@@ -94,9 +96,30 @@ __global__ void tc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= n) return;
     const int b = rowptr[row], e = rowptr[row + 1];
-    for (int p = b + lane; p < e; p += 32) A8[(size_t)row * n_pad + colidx[p]] = 1;
+    for (int p = b + lane; p < e; p += 32) {
+        const int c = colidx[p];
+        A8[(size_t)row * n_pad + c] = 1;
+    }
     const int nblk = n_pad / TC_BN;
     for (int t = lane; t < nblk; t += 32) blkpre[(size_t)row * nblk + t] = lower_bound(colidx, b, e - b, t * TC_BN);
+}
+
+// entries below the block diagonal of a symmetric product: A2[i,j] = A2[j,i].  One thread per directed entry (a warp
+// per row would leave a hub row's 3420 binary searches to 32 lanes).
+__global__ void __launch_bounds__(256) tc_mirror_kernel(const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ colidx, int n, int64_t nnz,
+                                                        int32_t* __restrict__ tri) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int a = 0, b = n;                       // row of entry p: rowptr[a] <= p < rowptr[b]
+    while (b - a > 1) {
+        const int m = (a + b) >> 1;
+        if ((int64_t)rowptr[m] <= p) a = m; else b = m;
+    }
+    const int c = colidx[p];
+    if (c / TC_BN >= a / TC_BM) return;     // on or above the block diagonal: written by the product kernel
+    const int cb = rowptr[c];
+    tri[p] = tri[find_sorted(colidx, cb, rowptr[c + 1] - cb, a)];
 }
 
 // ---- the GEMM + fused edge-extraction kernel ---------------------------------------------------------------
@@ -104,7 +127,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_support_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const int8_t* __restrict__ A8,
                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ blkpre, int n, int n_pad,
-                  int32_t* __restrict__ tri) {
+                  int32_t* __restrict__ tri, int symmetric) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -114,7 +137,16 @@ tc_support_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint8_t* smem_b = smem + TC_STAGES * TC_STAGE_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.y, nt = blockIdx.x;
+    // symmetric != 0: the product is SYMMETRIC (A·A) — only the tiles with nt >= mt are computed (1-D grid over the
+    // upper triangle, row by row); tc_mirror_kernel copies the values to the entries below the block diagonal
+    int mt = blockIdx.y, nt = blockIdx.x;
+    if (symmetric) {
+        const int T = n_pad / TC_BM;
+        int t = blockIdx.x;
+        mt = 0;
+        while (t >= T - mt) { t -= T - mt; ++mt; }
+        nt = mt + t;
+    }
     const int num_kb = n_pad / TC_BK;
 
     if (warp == 0 && lane == 0) {
@@ -208,9 +240,78 @@ tc_support_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 }
 
+// Measurement aid: the int8 tensor rate this GPU sustains with the SAME instruction the product kernel issues
+// (tcgen05.mma.cta_group::1.kind::i8, M128 N128 K32, operands resident in shared memory, accumulator in TMEM), no loads
+// and no epilogue — the denominator bench.py holds the product kernel against (MEASURED_PEAKS.json has no int8 figure).
+__global__ void __launch_bounds__(64, 2) tc_int8_peak_kernel(int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_base_slot;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = threadIdx.x; p < 2 * TC_STAGE_BYTES / 4; p += blockDim.x) ((uint32_t*)smem)[p] = 0x01010101u;
+    if (warp == 0 && lane == 0) {
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the MMA's async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    if (warp == 0 && lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_i8(TC_BM, TC_BN);
+        const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + TC_STAGE_BYTES);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+                umma_i8(tmem_base, umma_desc_k_sw128(a_addr + k * TC_UMMA_K), umma_desc_k_sw128(b_addr + k * TC_UMMA_K), idesc,
+                        (it | k) != 0);
+        }
+        umma_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
 }  // namespace dcr
 
 using namespace dcr;
+
+// TOP/s (int8, dense) of the resident-tile loop; synchronises.  *out_tops is DEVICE memory (fp64).
+extern "C" int dcr_tc_int8_peak(double* out_tops, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = 2 * TC_STAGE_BYTES + 1024, iters = 2048, ctas = sm_count() * 2;
+    DCR_CUDA(cudaFuncSetAttribute(tc_int8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1;
+    DCR_CUDA(cudaEventCreate(&e0));
+    DCR_CUDA(cudaEventCreate(&e1));
+    tc_int8_peak_kernel<<<ctas, 64, smem, st>>>(64);                    // warm-up
+    DCR_CUDA(cudaEventRecord(e0, st));
+    tc_int8_peak_kernel<<<ctas, 64, smem, st>>>(iters);
+    DCR_CUDA(cudaEventRecord(e1, st));
+    DCR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    DCR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double ops = 2.0 * TC_BM * TC_BN * TC_BK * (double)iters * ctas;
+    const double tops = ops / (ms * 1e-3) / 1e12;
+    DCR_CUDA(cudaMemcpyAsync(out_tops, &tops, sizeof(double), cudaMemcpyHostToDevice, st));
+    DCR_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -245,15 +346,22 @@ static int make_tmap(CUtensorMap* tmap, const int8_t* base, int np) {
 }
 
 static int launch_edge_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const int8_t* A8, const int32_t* rowptr,
-                            const int32_t* blkpre, int n, int np, int32_t* out, cudaStream_t st) {
+                            const int32_t* blkpre, int n, int np, int32_t* out, bool symmetric, cudaStream_t st) {
     static bool attr_done_dev[MAX_DEVICES] = {false};
     bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         DCR_CUDA(cudaFuncSetAttribute(tc_support_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_done = true;
     }
-    const dim3 grid((unsigned)(np / TC_BN), (unsigned)(np / TC_BM));
-    tc_support_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, A8, rowptr, blkpre, n, np, out);
+    const unsigned T = (unsigned)(np / TC_BM);
+    const dim3 grid = symmetric ? dim3(T * (T + 1) / 2, 1) : dim3(T, T);
+    tc_support_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, A8, rowptr, blkpre, n, np, out, symmetric ? 1 : 0);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_mirror(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri, cudaStream_t st) {
+    tc_mirror_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, nnz, tri);
     DCR_LAUNCH_CHECK();
     return 0;
 }
@@ -278,22 +386,25 @@ static TcWorkspace tc_layout(void* workspace, int n, int64_t nnz, bool with_q) {
     return w;
 }
 
-extern "C" int64_t dcr_bfc_support_tc_workspace_bytes(int n) { return (int64_t)tc_layout(nullptr, n, 0, false).total; }
+extern "C" int64_t dcr_bfc_support_tc_workspace_bytes(int n, int64_t nnz) {
+    return (int64_t)tc_layout(nullptr, n, nnz, false).total;
+}
 
-extern "C" int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
-    if (n <= 0) return 0;
+extern "C" int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n <= 0 || nnz <= 0) return 0;
     if (n > 32768) { set_error("dcr_bfc_support_tc: dense tensor-core path is for n <= 32768 (got %d)", n); return 1; }
-    if (workspace_bytes < dcr_bfc_support_tc_workspace_bytes(n)) { set_error("dcr_bfc_support_tc: workspace too small"); return 1; }
+    if (workspace_bytes < dcr_bfc_support_tc_workspace_bytes(n, nnz)) { set_error("dcr_bfc_support_tc: workspace too small"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
     const int np = tc_pad(n);
-    const TcWorkspace w = tc_layout(workspace, n, 0, false);
+    const TcWorkspace w = tc_layout(workspace, n, nnz, false);
     DCR_CUDA(cudaMemsetAsync(w.A8, 0, (size_t)np * np, st));
     tc_fill_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, np, w.A8, w.blkpre);
     DCR_LAUNCH_CHECK();
     CUtensorMap tmap;
     if (make_tmap(&tmap, w.A8, np)) return 1;
-    return launch_edge_gemm(tmap, tmap, w.A8, rowptr, w.blkpre, n, np, tri, st);
+    if (launch_edge_gemm(tmap, tmap, w.A8, rowptr, w.blkpre, n, np, tri, true, st)) return 1;   // symmetric: upper triangle
+    return launch_mirror(rowptr, colidx, n, nnz, tri, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -363,10 +474,13 @@ extern "C" int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* col
     DCR_LAUNCH_CHECK();
     CUtensorMap map_a, map_q;
     if (make_tmap(&map_a, w.A8, np) || make_tmap(&map_q, w.Q8, np)) return 1;
-    if (launch_edge_gemm(map_a, map_a, w.A8, rowptr, w.blkpre, n, np, tri, st)) return 1;
+    // A·A is symmetric: upper-triangular tiles (half the MMAs), then the mirror pass
+    if (launch_edge_gemm(map_a, map_a, w.A8, rowptr, w.blkpre, n, np, tri, true, st)) return 1;
+    if (launch_mirror(rowptr, colidx, n, nnz, tri, st)) return 1;
     tc_fill_q_kernel<<<row_grid, 256, 0, st>>>(rowptr, colidx, tri, n, np, w.Q8);
     DCR_LAUNCH_CHECK();
-    if (launch_edge_gemm(map_q, map_a, w.A8, rowptr, w.blkpre, n, np, w.t1, st)) return 1;
+    // Q·A is not ((Q·A)^T = A·Q): every tile
+    if (launch_edge_gemm(map_q, map_a, w.A8, rowptr, w.blkpre, n, np, w.t1, false, st)) return 1;
     tc_closing_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(rowptr, colidx, n, nnz, tri, w.t1, sharp, lam, c64, c32);
     DCR_LAUNCH_CHECK();
     return 0;

@@ -127,10 +127,10 @@ def support_tc(csr: DeviceCSR, out: torch.Tensor | None = None, workspace: torch
     lib = L.load()
     dev = csr.colidx.device
     tri = out if out is not None else torch.empty(max(csr.nnz, 1), dtype=torch.int32, device=dev)[:csr.nnz]
-    nbytes = int(lib.dcr_bfc_support_tc_workspace_bytes(csr.n))
+    nbytes = int(lib.dcr_bfc_support_tc_workspace_bytes(csr.n, csr.nnz))
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    L.check(lib.dcr_bfc_support_tc(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(),
+    L.check(lib.dcr_bfc_support_tc(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, csr.nnz, tri.data_ptr(),
                                    workspace.data_ptr(), nbytes, L.current_stream()), "dcr_bfc_support_tc")
     return tri
 

@@ -40,8 +40,9 @@ SIGNATURES = {
     "dcr_bfc_support": (_I, [_P, _P, _I, _P, _L, _L, _P]),
     "dcr_bfc_cuda_flavour": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),
     "dcr_bfc_cuda_flavour_directed": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),
-    "dcr_bfc_support_tc_workspace_bytes": (_L, [_I]),
-    "dcr_bfc_support_tc": (_I, [_P, _P, _I, _P, _P, _L, _P]),
+    "dcr_bfc_support_tc_workspace_bytes": (_L, [_I, _L]),
+    "dcr_bfc_support_tc": (_I, [_P, _P, _I, _L, _P, _P, _L, _P]),
+    "dcr_tc_int8_peak": (_I, [_P, _P]),
     "dcr_bfc_cuda_flavour_tc_workspace_bytes": (_L, [_I, _L]),
     "dcr_bfc_cuda_flavour_tc": (_I, [_P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _L, _P]),
     "dcr_bfc_cuda_dense_small_workspace_bytes": (_L, [_I]),

@@ -96,9 +96,10 @@ int dcr_bfc_cuda_flavour_directed(const int32_t* out_rowptr, const int32_t* out_
 /* Dense-regime alternative to dcr_bfc_support (n <= 32768): A2 = A·A on the tensor cores (tcgen05 kind::i8, TMA,
  * TMEM), replacing `torch.matmul(A, A)` of curvature/bfc_cuda.py:53,146; the fused epilogue writes only the entries
  * that sit on an edge, in CSR order — tri[0..nnz) is identical to dcr_bfc_support's.
- * workspace: dcr_bfc_support_tc_workspace_bytes(n) bytes of device memory (int8 image of A + per-block offsets). */
-int64_t dcr_bfc_support_tc_workspace_bytes(int n);
-int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int32_t* tri, void* workspace,
+ * The product is symmetric: only the upper-triangular tiles are computed and mirrored.
+ * workspace: dcr_bfc_support_tc_workspace_bytes(n, nnz) bytes of device memory (int8 image of A + per-block offsets). */
+int64_t dcr_bfc_support_tc_workspace_bytes(int n, int64_t nnz);
+int dcr_bfc_support_tc(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri, void* workspace,
                        int64_t workspace_bytes, void* stream);
 /* The whole cuda flavour in the dense regime (same outputs as dcr_bfc_support + dcr_bfc_cuda_flavour over all
  * entries): A2 = A·A and T1 = (A ∧ [A2 == 1])·A on the tensor cores, then an elementwise closing pass. */
@@ -106,6 +107,11 @@ int64_t dcr_bfc_cuda_flavour_tc_workspace_bytes(int n, int64_t nnz);
 int dcr_bfc_cuda_flavour_tc(const int32_t* rowptr, const int32_t* colidx, int n, int64_t nnz, int32_t* tri,
                             int32_t* sharp, int32_t* lam, double* c64, float* c32, void* workspace,
                             int64_t workspace_bytes, void* stream);
+
+/* Measurement aid (no reference counterpart): dense int8 tensor rate of this GPU, TOP/s, measured with the product
+ * kernel's own instruction (tcgen05.mma kind::i8, M128 N128 K32) on tiles resident in shared memory — the denominator of
+ * the tensor roofline in bench.py.  *out_tops is device memory (fp64); synchronises. */
+int dcr_tc_int8_peak(double* out_tops, void* stream);
 
 /* Small dense graphs (n <= 1024: the WebKB shapes of configs 1-2): balanced_forman_curvature(A, C) of
  * curvature/bfc_cuda.py:51-65 straight from the dense fp32 A — rows bit-packed once, then one kernel computes supports,
