@@ -102,3 +102,44 @@ def test_dense_bfc_cora_shape_product_matches_reference_kernel():
     ref = ref_gpu.balanced_forman_curvature(A)
     got = balanced_forman_curvature(A)
     assert torch.equal(ref.view(torch.int32), got.view(torch.int32))
+
+
+def _tuples(wlog):
+    return [(r["x"], r["y"], r["n_candidates"], r["k"], r["l"], r["choice"],
+             -1 if r["removed"] is None else r["removed"][0], -1 if r["removed"] is None else r["removed"][1])
+            for r in wlog]
+
+
+def test_full_length_cora_sequence_matches_reference_kernels():
+    """Config 3 at FULL length: all 1000 iterations of the cora-shaped run (tau = 163, bound 0.95, stochastic) against
+    the reference's loop driven with its own compiled kernels on this GPU — every log record and the output."""
+    ref_gpu = _need_ref()
+    from dcr import sdrf
+    from dcr.synth import named_graph
+    ei, n = named_graph("cora")
+    loops = 1000
+    uni = np.random.RandomState(3).random_sample(loops)
+    got, log = sdrf.sdrf(ei, n, loops, True, 0.95, 163, uniforms=uni, return_log=True)
+    want, wlog = ref_gpu.sdrf_reference_gpu(ei, n, loops, True, 0.95, 163, uni, batched_items=True)
+    assert len(wlog) == loops == len(log)
+    assert [tuple(int(v) for v in r) for r in log] == _tuples(wlog)
+    assert np.array_equal(got, want)
+
+
+def test_squirrel_shape_sequence_matches_reference_kernels():
+    """Config-4 shape with the reference's hyper-parameters for Squirrel (tau 436 overflows the softmax -> greedy here and
+    tau = 20): the first iterations (hub candidate matrices of up to millions of cells) against the reference's loop
+    with its own kernels."""
+    ref_gpu = _need_ref()
+    from dcr import sdrf
+    from dcr.synth import named_graph
+    ei, n = named_graph("squirrel")
+    for tau, loops in ((float("inf"), 24), (20, 12)):
+        uni = np.random.RandomState(5).random_sample(loops)
+        want, wlog = ref_gpu.sdrf_reference_gpu(ei, n, loops, True, 5.88, tau, uni, time_budget_s=90.0, batched_items=True)
+        k = len(wlog)
+        assert k >= min(loops, 8)
+        got, log = sdrf.sdrf(ei, n, k, True, 5.88, tau, uniforms=uni, return_log=True)
+        assert [tuple(int(v) for v in r) for r in log] == _tuples(wlog)
+        if k == loops:
+            assert np.array_equal(got, want)
