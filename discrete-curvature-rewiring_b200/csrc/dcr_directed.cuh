@@ -210,11 +210,12 @@ __device__ __forceinline__ float directed_cell_warp(const GraphView& out, const 
 
 template <class NbI, class NbJ, class Out>
 __device__ void directed_score_cells(const GraphView& out, const GraphView& in, int x, int y, NbI nbI, int n_i, NbJ nbJ,
-                                     int n_j, const ScoreScratch& sc, const DirScoreShared* sh, Out put) {
+                                     int n_j, const ScoreScratch& sc, const DirScoreShared* sh, Out put, int part = 0,
+                                     int parts = 1) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int lane = tid & 31, nwarps = (nthreads >> 5) * parts, warp = part * (nthreads >> 5) + (tid >> 5);
     const long long cells = (long long)n_i * n_j;
-    for (long long c = tid; c < cells; c += nthreads) {
+    for (long long c = (long long)part * nthreads + tid; c < cells; c += (long long)parts * nthreads) {
         const int I = (int)(c / n_j), J = (int)(c - (long long)I * n_j);
         const int i = nbI(I), j = nbJ(J);
         if (i == x || j == y) continue;

@@ -232,11 +232,12 @@ __device__ __forceinline__ float score_cell_warp(const GraphView& g, const int32
 template <class NbI, class NbJ, class Out>
 __device__ void score_cells(const GraphView& g, const int32_t* supp, int x, int y, NbI nbI, int n_i, NbJ nbJ,
                             int n_j, const ScoreScratch& sc, const ScoreShared* sh, Out out, int only_I = -1,
-                            int only_J = -1) {
+                            int only_J = -1, int part = 0, int parts = 1) {
+    // (part, parts): this CTA's share when several CTAs score one matrix (dcr_post_delta on large candidate sets)
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int lane = tid & 31, nwarps = (nthreads >> 5) * parts, warp = part * (nthreads >> 5) + (tid >> 5);
     const long long cells = (long long)n_i * n_j;
-    for (long long c = tid; c < cells; c += nthreads) {
+    for (long long c = (long long)part * nthreads + tid; c < cells; c += (long long)parts * nthreads) {
         const int I = (int)(c / n_j), J = (int)(c - (long long)I * n_j);
         const int i = nbI(I), j = nbJ(J);
         if (i == x || j == y) continue;

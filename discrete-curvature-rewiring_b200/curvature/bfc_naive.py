@@ -33,11 +33,28 @@ def _run(csr, src, dst):
     return out
 
 
-def bfc_edge(G: nx.Graph, v1: int, v2: int) -> float:
-    """Balanced Forman curvature of the edge ``(v1, v2)`` of the undirected graph ``G``."""
-    if min(G.degree[v1], G.degree[v2]) == 1:      # bfc_naive.py:18-19 returns the int 0
+class PreparedGraph:
+    """``prepare(G)``: the device-resident CSR of ``G``, for callers that query many edges of an UNCHANGED graph with
+    ``bfc_edge``.  A networkx graph carries no modification counter, so ``bfc_edge(G, …)`` on a plain graph has to rebuild
+    the CSR on every call (O(E), like the reference's per-call ``nx.adj_matrix(G)``, bfc_naive.py:34); passing the
+    prepared object instead makes a call O(its own kernel)."""
+
+    def __init__(self, G: nx.Graph):
+        self.csr = _csr_of(G)
+        self.degree = dict(G.degree)
+
+
+def prepare(G: nx.Graph) -> PreparedGraph:
+    return PreparedGraph(G)
+
+
+def bfc_edge(G, v1: int, v2: int) -> float:
+    """Balanced Forman curvature of the edge ``(v1, v2)`` of the undirected graph ``G`` (an ``nx.Graph``, or the result of
+    :func:`prepare` for repeated queries on an unchanged graph)."""
+    deg = G.degree
+    if min(deg[v1], deg[v2]) == 1:                # bfc_naive.py:18-19 returns the int 0
         return 0
-    out = _run(_csr_of(G), [v1], [v2])
+    out = _run(G.csr if isinstance(G, PreparedGraph) else _csr_of(G), [v1], [v2])
     return float(out["bfc"].cpu()[0])
 
 

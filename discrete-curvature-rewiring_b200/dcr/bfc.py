@@ -254,10 +254,12 @@ def cuda_flavour_directed(d: DirectedCSR, want_fields: bool = True) -> dict:
 def post_delta_directed(d: DirectedCSR, x: int, y: int, i_nb: torch.Tensor, j_nb: torch.Tensor,
                         D: torch.Tensor) -> torch.Tensor:
     lib = L.load()
+    nb = int(lib.dcr_post_delta_workspace_bytes(d.n, int(i_nb.numel()), int(j_nb.numel())))
+    ws = torch.empty(nb, dtype=torch.uint8, device=D.device)
     L.check(lib.dcr_post_delta_directed(d.out.rowptr.data_ptr(), d.out.colidx.data_ptr(), d.inn.rowptr.data_ptr(),
                                         d.inn.colidx.data_ptr(), d.n, int(x), int(y), i_nb.data_ptr(),
                                         int(i_nb.numel()), j_nb.data_ptr(), int(j_nb.numel()), D.data_ptr(),
-                                        L.current_stream()), "dcr_post_delta_directed")
+                                        ws.data_ptr(), nb, L.current_stream()), "dcr_post_delta_directed")
     return D
 
 
@@ -353,7 +355,9 @@ def scatter_dense(csr: DeviceCSR, vals: torch.Tensor, C: torch.Tensor) -> torch.
 def post_delta(csr: DeviceCSR, tri: torch.Tensor, x: int, y: int, i_nb: torch.Tensor, j_nb: torch.Tensor,
                D: torch.Tensor) -> torch.Tensor:
     lib = L.load()
+    nb = int(lib.dcr_post_delta_workspace_bytes(csr.n, int(i_nb.numel()), int(j_nb.numel())))
+    ws = torch.empty(nb, dtype=torch.uint8, device=D.device)
     L.check(lib.dcr_post_delta(csr.rowptr.data_ptr(), csr.colidx.data_ptr(), csr.n, tri.data_ptr(), int(x), int(y),
                                i_nb.data_ptr(), int(i_nb.numel()), j_nb.data_ptr(), int(j_nb.numel()), D.data_ptr(),
-                               L.current_stream()), "dcr_post_delta")
+                               ws.data_ptr(), nb, L.current_stream()), "dcr_post_delta")
     return D

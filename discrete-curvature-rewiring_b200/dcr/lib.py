@@ -64,8 +64,9 @@ SIGNATURES = {
     "dcr_bfc_cuda_edges_prepare": (_I, [_P, _P, _I, _P, _P, _L, _L, _P, _P]),
     "dcr_bfc_cuda_edges": (_I, [_P, _P, _I, _P, _P, _L, _P, _L, _L, _P, _P, _P, _P, _P, _I, _P]),
     "dcr_bfc_cuda_sharded": (_I, [_P, _P, _I, _P, _P, _L, _P, _L, _L, _P, _P]),
-    "dcr_post_delta": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P]),
-    "dcr_post_delta_directed": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
+    "dcr_post_delta_workspace_bytes": (_L, [_I, _I, _I]),
+    "dcr_post_delta": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _L, _P]),
+    "dcr_post_delta_directed": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _L, _P]),
     "dcr_sdrf_create": (_I, [_I, _P, _P, _L, C.POINTER(_P)]),
     "dcr_sdrf_create_mode": (_I, [_I, _I, _P, _P, _P, _P, _L, C.POINTER(_P)]),
     "dcr_sdrf_destroy": (None, [_P]),

@@ -218,14 +218,18 @@ int dcr_bfc_paper_unshard(const void* gathered, int world, int64_t chunk, int64_
  * (curvature/bfc_cuda.py:68-141, :144-159): D[I,J] for i = i_nb[I], j = j_nb[J]; masked cells = -1000.
  * `tri` = supports of all directed entries (dcr_bfc_support).  D is row-major [n_i, n_j] fp32.
  * ---------------------------------------------------------------------------------------------------------- */
+int64_t dcr_post_delta_workspace_bytes(int n, int n_i, int n_j);
 int dcr_post_delta(const int32_t* rowptr, const int32_t* colidx, int n, const int32_t* tri, int x, int y,
-                   const int32_t* i_nb, int n_i, const int32_t* j_nb, int n_j, float* D, void* stream);
+                   const int32_t* i_nb, int n_i, const int32_t* j_nb, int n_j, float* D, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* workspace: dcr_post_delta_workspace_bytes(n, n_i, n_j) bytes of device memory (what all cells share: base terms over
+ * N(x) / N(y), positions of the list entries).  One CTA fills it, then up to two CTAs per SM score the cells. */
 
 /* Asymmetric A (see dcr_bfc_cuda_flavour_directed): i_nb are usually the successors of x plus x, j_nb the predecessors
  * of y plus y (rewiring/sdrf_cuda_bfc.py:48-49). */
 int dcr_post_delta_directed(const int32_t* out_rowptr, const int32_t* out_colidx, const int32_t* in_rowptr,
                             const int32_t* in_colidx, int n, int x, int y, const int32_t* i_nb, int n_i,
-                            const int32_t* j_nb, int n_j, float* D, void* stream);
+                            const int32_t* j_nb, int n_j, float* D, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * SDRF loop.  Replaces the loop body of sdrf_cuda_bfc (rewiring/sdrf_cuda_bfc.py:37-91) including

@@ -89,6 +89,10 @@ def test_bfc_naive_dropin_on_networkx_graph():
         assert type(G[u][v]["bfc"]) is type(want)     # int 0 when deg_min == 1, else float
     u, v = next(iter(G.edges))
     assert bfc_edge(G, u, v) == bfc_edge_fields(adj, u, v)[6]
+    from curvature.bfc_naive import prepare
+    P = prepare(G)                                       # repeated queries on an unchanged graph: CSR uploaded once
+    for a, b in list(G.edges)[:10]:
+        assert bfc_edge(P, a, b) == bfc_edge_fields(adj, a, b)[6]
 
 
 def test_rewire_dropin_returns_edge_index_and_consumes_numpy_stream():
@@ -163,3 +167,28 @@ def test_config2_rewire_then_gcn_on_gpu():
             opt.step()
             first = loss.item() if first is None else first
         assert loss.item() < 0.5 * first
+
+
+def test_post_delta_large_candidate_matrix_uses_several_ctas():
+    """(deg x + 1)(deg y + 1) > 4096 cells: the cells kernel runs on several CTAs (one CTA prepares the shared terms);
+    symmetric and asymmetric A against the dense oracle, bit for bit."""
+    import torch
+    from curvature.bfc_cuda import balanced_forman_post_delta
+    from oracle.cuda_flavour import post_delta_dense
+    n = 420
+    ei = gnp(n, 0.3, 77)
+    An = dense_of(ei, n)
+    rng = np.random.default_rng(1)
+    for directed in (False, True):
+        if directed:
+            An = An * (rng.random((n, n)) < 0.7)          # drop 30 % of the entries: asymmetric
+            np.fill_diagonal(An, 0)
+        A = torch.from_numpy(An.astype(np.float32)).cuda()
+        nz = np.argwhere(An > 0)
+        for x, y in [tuple(nz[len(nz) // 3]), tuple(nz[-1]), (0, 0)]:
+            xn = np.flatnonzero(An[x]).tolist() + [int(x)]
+            yn = (np.flatnonzero(An[:, y]) if directed else np.flatnonzero(An[y])).tolist() + [int(y)]
+            assert len(xn) * len(yn) > 4096
+            want = post_delta_dense(An.astype(np.float32), int(x), int(y), xn, yn, "compiled")
+            got = balanced_forman_post_delta(A, int(x), int(y), xn, yn).cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (directed, x, y)
