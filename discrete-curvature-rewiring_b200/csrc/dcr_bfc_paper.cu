@@ -61,6 +61,13 @@ constexpr int CLASS_DA0 = 128, CLASS_DA1 = 1024, CLASS_DA2 = 16384;
 // the arxiv shape at 1/1 and 1/8 of the edges per call: finer items (8192 / 4096) lose at both sizes — the CTA path
 // costs more per element than the warp path.
 constexpr long long COOP_L0 = DCR_COOP_L0, COOP_G = DCR_COOP_G;
+// Round 2: with the long streams drained first (runs, L0 range) a warp can take longer streams without holding the tail
+// of a LARGE pass: 24576 saves 3 % at 1.17 M edges per call (3.77 -> 3.65 ms) but costs 8 % at 1/8 of them, where a
+// 24576-entry stream (0.25 ms on one warp) is a third of the pass — so the threshold follows the size of the call.
+#ifndef DCR_COOP_BIG
+#define DCR_COOP_BIG 24576
+#endif
+constexpr long long COOP_BIG = DCR_COOP_BIG, COOP_BIG_MIN_EDGES = 800000;
 // Inside the range of one tested endpoint the light edges are ordered by size bucket, heaviest first (stream > 2048,
 // > 512, the rest): warps that pull edges of a run from a shared counter then finish together.  Slot 0 of a vertex
 // counts its cooperative edges: they form a second group of the vertex, in the cooperative class of its degree.
@@ -197,6 +204,7 @@ struct PaperArgs {
     uint2* runs;           // [2][max_runs] (first position, length) of the runs of the group classes
     uint32_t max_runs;
     int group_ctas;        // CTAs of a group kernel (run sizing)
+    long long coop;        // stream length above which an edge is cooperative for THIS call (>= COOP_L0 / COOP_G)
     int n;
     int dense;             // 1: n is small enough for an exact bitmap of N(va) in shared memory (classes L0 + G1 only)
     uint32_t* gtables;     // class-X tables in global memory, gslots per CTA
@@ -361,7 +369,7 @@ __device__ __forceinline__ EdgeRole edge_role(const PaperArgs& a, int i, int j, 
     r.stream = swapped ? cb : ca;
     r.cls = degree_class(r.da, a.dense);
     r.slot = r.stream > SIZE_B1 ? 1 : (r.stream > SIZE_B2 ? 2 : 3);
-    if (r.cls == CL_L0 ? r.stream > COOP_L0 : (r.cls != CL_X && r.stream > COOP_G)) {
+    if (r.cls == CL_L0 ? r.stream > max(COOP_L0, a.coop) : (r.cls != CL_X && r.stream > max(COOP_G, a.coop))) {
         r.cls = coop_class_of(r.cls);                    // too long for one warp (L0 -> C1: the G1 kernel takes any degree below its own)
         r.slot = 0;
     }
@@ -1472,7 +1480,19 @@ __global__ void __launch_bounds__(L0_WARPS * 32, L0_CTAS_PER_SM) paper_light_war
 // s_acc: [0] tri (this part) [1] sq_b [2] g_b [3] next chunk [4] n_distinct [5] overflow [6] sq_a [7] g_a [8] "this
 // part finalises its split edge" [9] |T| [10] #big lists.  All threads call it; the caller synchronises the CTA before
 // the next use of s_acc.
-constexpr int TSET_WORDS = 1024, BIG_LIST = 2048, BIG_SLICE = 1024, MAX_BIG = 32;
+// (round 2: 15 % of the group kernel's stall samples sat on the barrier that ends the chunk loop — a warp whose chunk
+// holds a 2000-entry list keeps the other seven waiting; parking lists from 1024 entries on and slicing them 512 at a
+// time took the 1/8-range pass from 0.71 to 0.67 ms and the full pass from 3.65 to 3.63; 512 / 256 were no better)
+#ifndef DCR_BIG_LIST
+#define DCR_BIG_LIST 1024
+#endif
+#ifndef DCR_BIG_SLICE
+#define DCR_BIG_SLICE 512
+#endif
+#ifndef DCR_MAX_BIG
+#define DCR_MAX_BIG 64
+#endif
+constexpr int TSET_WORDS = 1024, BIG_LIST = DCR_BIG_LIST, BIG_SLICE = DCR_BIG_SLICE, MAX_BIG = DCR_MAX_BIG;
 template <int NWARPS, bool DENSE>
 __device__ __noinline__ void cta_edge(const PaperArgs& a, const Member<DENSE>& mem, uint32_t t, int va, int* st_all,
                                       uint32_t* tset_sh, uint32_t* hash_words, uint32_t hash_cap, uint32_t* q_all, int* s_acc,
@@ -1960,6 +1980,7 @@ static int paper_pass(const int32_t* rowptr, const int32_t* colidx, int n, int m
     a.runs = (uint2*)(base + L.runs);
     a.max_runs = L.max_runs;
     a.group_ctas = L.group_ctas;
+    a.coop = count >= COOP_BIG_MIN_EDGES ? COOP_BIG : 0;
     a.n = n;
     a.dense = use_dense_mode(n) ? 1 : 0;
     a.gtables = (uint32_t*)(base + L.gtables);
@@ -2197,7 +2218,7 @@ extern "C" int dcr_bfc_paper_sharded(const int32_t* rowptr, const int32_t* colid
                                   scratch, scratch_bytes, ev_edge_begin, nullptr, stream, false);
         if (rc) return rc;
     }
-    PaperArgs a;
+    PaperArgs a{};
     a.rowptr = rowptr; a.colidx = colidx; a.esrc = esrc; a.edst = edst;
     a.e_first = e_lo; a.e_stride = 1; a.count = count;
     a.out_tri = tri; a.out_sq_i = sq_i; a.out_sq_j = sq_j; a.out_gamma = gamma; a.out_bfc = bfc;
