@@ -2250,11 +2250,12 @@ __global__ void edge_cost_kernel(const int32_t* __restrict__ rowptr, const int64
     const int64_t ca = node_s[j] - di, cb = node_s[i] - dj;
     const bool swapped = cb < ca;                    // stream i's side
     const int64_t stream = swapped ? cb : ca, heads = swapped ? di : dj, da = swapped ? dj : di;
-    // Relative cost per streamed entry of the three paths, fitted to the measured edge-kernel times of 44 contiguous
-    // ranges of the arxiv-shaped edge list (profiles/cost_model_fit.py): warp path with the warp-private table (d_a <=
-    // 128) 1, warp path of the group kernel 2, one CTA per edge (stream > COOP) 4.5.
-    const int64_t w2 = stream > COOP_G ? 9 : (da > CLASS_DA0 ? 4 : 2);      // weights x 2
-    cost[e] = (w2 * stream) / 2 + 24 * heads + 160;
+    // Relative cost per streamed entry of the three paths, fitted (non-negative least squares, profiles/cost_model_fit.py)
+    // to the measured edge-kernel times of 44 contiguous ranges of the arxiv-shaped edge list: the d_a <= 128 warp path
+    // 0.5 (its kernel runs in the shadow of the group kernel), the group kernel's warp path 2.3 x (1 + d_a / 1400) — a
+    // hub's streams carry more true neighbours of the tested endpoint: more candidates per element —, one CTA per edge 2.3.
+    const int64_t w8 = stream > COOP_G ? 18 : (da > CLASS_DA0 ? 18 + da / 90 : 4);      // weights x 8
+    cost[e] = (w8 * stream) / 8 + 24 * heads + 160;
 }
 }  // namespace dcr
 

@@ -37,7 +37,8 @@ triv = np.minimum(deg[es], deg[ed]) <= 1
 coop = (stream > 16384) & ~triv
 l0 = (da <= 128) & ~coop & ~triv
 grp = (da > 128) & ~coop & ~triv
-F = np.stack([stream * l0, stream * grp, stream * coop, heads * ~triv, np.ones(E)], axis=1).astype(np.float64)
+F = np.stack([stream * l0, stream * grp, stream * coop, heads * ~triv, np.ones(E), stream * grp * da, stream * coop * da],
+             axis=1).astype(np.float64)
 P = np.concatenate([np.zeros((1, F.shape[1])), np.cumsum(F, axis=0)])
 lib = L.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -69,9 +70,17 @@ scale = A.max(axis=0)
 w, res = nnls(A / scale, t)
 w = w / scale
 pred = A @ w
-print(f"{name}: {len(t)} ranges; fit (ms per unit): wL {w[0]:.3e} wG {w[1]:.3e} wC {w[2]:.3e} wH {w[3]:.3e} wE {w[4]:.3e} t0 {w[5]:.3f} ms")
+print(f"{name}: {len(t)} ranges; fit (ms per unit): wL {w[0]:.3e} wG {w[1]:.3e} wC {w[2]:.3e} wH {w[3]:.3e} wE {w[4]:.3e} "
+      f"wG*da {w[5]:.3e} wC*da {w[6]:.3e} t0 {w[7]:.3f} ms")
 w = np.maximum(w, 1e-30)
 print(f"relative to wL: wG {w[1] / w[0]:.2f} wC {w[2] / w[0]:.2f} wH {w[3] / w[0]:.1f} wE {w[4] / w[0]:.1f}; "
       f"rms residual {np.sqrt(np.mean((pred - t) ** 2)) * 1e3:.1f} us, max {np.abs(pred - t).max() * 1e3:.1f} us")
 print("W=8 measured", np.round(t[4:12], 3), "predicted", np.round(pred[4:12], 3))
+# the same fit without the constant and with wL pinned by the light kernel's own rate (sum of work, what a cut balances)
+for cols, label in (([0, 1, 2, 5, 6], "L G C G*da C*da"), ([0, 1, 2], "L G C")):
+    X = A[:, cols]
+    sc2 = X.max(axis=0)
+    w2, _ = nnls(X / sc2, t - 0.15)
+    w2 = w2 / sc2
+    print(label, "no constant (t - 0.15 ms):", " ".join(f"{v:.3e}" for v in w2), "rms us", round(float(np.sqrt(np.mean((X @ w2 + 0.15 - t) ** 2))) * 1e3, 1))
 np.save(os.path.join(REPO, "gpurun_out", "cost_fit_A.npy"), np.column_stack([A, t]))
