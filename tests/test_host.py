@@ -143,3 +143,43 @@ def test_dense_entry_points_fail_loudly_without_cuda():
     big = torch.zeros(1100, 1100)                       # above the small-graph path: the CSR route
     with pytest.raises(DcrError):
         balanced_forman_curvature(big)
+
+
+def test_directed_and_classical_graph_setup_match_the_oracle_builders():
+    """dcr.graph.digraph_order / from_digraph_order / classical_order (vectorised numpy, product host code) against the
+    dict-based restatements of networkx / PyG behaviour in the oracle, on shuffled inputs."""
+    import warnings
+    from dcr import graph as G
+    from oracle.sdrf import edge_index_from_digraph, networkx_digraph
+    from oracle.sdrf_classical import networkx_adjacency_classical
+    from helpers import gnp
+    rng = np.random.default_rng(0)
+    for t in range(12):
+        n = 15 + t
+        ei = rng.integers(0, n, size=(2, 5 * n))
+        ei = ei[:, ei[0] != ei[1]]
+        ei = np.unique(ei, axis=1)
+        ei = ei[:, rng.permutation(ei.shape[1])]
+        s_rp, s_ord, p_rp, p_ord = G.digraph_order(ei, n)
+        succ, pred = networkx_digraph(ei, n)
+        for v in range(n):
+            assert list(succ[v]) == s_ord[s_rp[v]:s_rp[v + 1]].tolist()
+            assert list(pred[v]) == p_ord[p_rp[v]:p_rp[v + 1]].tolist()
+        assert np.array_equal(G.from_digraph_order(s_rp, s_ord), edge_index_from_digraph(succ))
+        und = gnp(n, 0.3, t)
+        und = und[:, rng.permutation(und.shape[1])]
+        rp, od = G.classical_order(und, n)
+        adj = networkx_adjacency_classical(und, n)
+        for v in range(n):
+            assert list(adj[v]) == od[rp[v]:rp[v + 1]].tolist()
+    # only the columns with v <= u survive to_networkx(..., to_undirected=True): an upper-triangle-only input is empty
+    up = gnp(20, 0.3, 1)
+    up = up[:, up[0] < up[1]]
+    rp, od = G.classical_order(up, 20)
+    assert od.size == 0 and rp[-1] == 0
+    with pytest.raises(NotImplementedError):           # a repeated directed edge would make A weighted
+        G.digraph_order(np.array([[0, 0, 1], [1, 1, 2]]), 3)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        G.digraph_order(np.array([[0, 1, 1], [1, 1, 2]]), 3)
+        assert any("self-loops" in str(x.message) for x in w)
