@@ -36,7 +36,7 @@ for name in ("arxiv", "squirrel"):
     tri = bfc.support(csr)
     out = bfc.cuda_flavour_edges(csr)
     t_sup = timed(lambda: bfc.support(csr, out=tri))
-    t_all = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=None))
+    t_all = timed(lambda: bfc.cuda_flavour(csr, want_fields=False, tri=bfc.support(csr, out=tri)))   # tri given: per-entry kernels
     t_e1 = timed(lambda: bfc.cuda_flavour_edges(csr, phases=1, out=out))
     t_e = timed(lambda: bfc.cuda_flavour_edges(csr, out=out))
     print(f"{name}: E={e} per-entry support {t_sup:.3f} ms, per-entry full {t_all:.3f} ms | edge-centric support "
