@@ -12,9 +12,11 @@
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no host sync) unless
  *     the comment says "synchronises"
  *   - return value: 0 = ok, non-zero = error (message via dcr_last_error(), thread-local)
- *   - graphs are undirected, simple (no self-loops, no multi-edges), node ids 0..n-1, given as a CSR with int32
- *     row offsets and int32 SORTED column indices; a "directed entry" is one slot of colidx, an "undirected
- *     edge" is a directed entry with row < col, numbered in CSR order (edge id)
+ *   - graphs are simple (no self-loops, no multi-edges), node ids 0..n-1, given as a CSR with int32 row offsets and
+ *     int32 SORTED column indices; unless a function says otherwise the graph is UNDIRECTED (both directions of every
+ *     edge present); a "directed entry" is one slot of colidx, an "undirected edge" is a directed entry with row < col,
+ *     numbered in CSR order (edge id).  The *_directed entry points and DCR_SDRF_MODE_BFC_DIRECTED take an asymmetric
+ *     0/1 adjacency as TWO sorted CSRs: successors (rows of A) and predecessors (rows of A^T)
  */
 #ifndef DCR_H_
 #define DCR_H_
