@@ -67,6 +67,8 @@ struct SdrfDev {
     int32_t* rstart;      // [n]
     int32_t* rlen;        // [n]
     int32_t* rcap;        // [n]
+    int32_t* selfl;       // [rows] 1: the node lists ITSELF among its neighbours (a self-loop of G that A does not have,
+                          //        sdrf_cuda_bfc.py:29 vs :31): one extra entry in the insertion-order row only
     int32_t* col;         // arena: sorted neighbour ids
     int32_t* ord;         // arena: neighbour ids in insertion order (same row offsets)
     int32_t* supp;        // arena: #common neighbours of the entry's edge (A2[i,j])
@@ -314,15 +316,16 @@ __device__ void shift_left3(const SdrfDev& S, int lo, int hi) {
 
 // make room for one more entry in row v (relocate to the arena top with doubled capacity when full)
 __device__ bool row_reserve(const SdrfDev& S, int v, LoopShared* sh) {
-    const int len = S.rlen[v], cap = S.rcap[v], start = S.rstart[v];
+    const int len = S.rlen[v], cap = S.rcap[v], start = S.rstart[v], self = S.selfl[v];
     __syncthreads();
-    if (len < cap) return true;
+    if (len + self < cap) return true;     // (the insertion-order row is `self` entries longer than the sorted one)
     const int ncap = max(2 * cap, 4);
     const int nstart = S.scalars[0];
     if ((long long)nstart + ncap > S.cap_total) return false;
-    for (int t = threadIdx.x; t < len; t += SDRF_THREADS) {
-        S.col[nstart + t] = S.col[start + t];
+    for (int t = threadIdx.x; t < len + self; t += SDRF_THREADS) {
         S.ord[nstart + t] = S.ord[start + t];
+        if (t >= len) continue;
+        S.col[nstart + t] = S.col[start + t];
         S.supp[nstart + t] = S.supp[start + t];
         S.c32[nstart + t] = S.c32[start + t];
         S.owner[nstart + t] = v;
@@ -351,7 +354,7 @@ __device__ bool row_insert(const SdrfDev& S, int v, int key, LoopShared* sh) {
         S.supp[pos] = 0;
         S.c32[pos] = 0.0f;
         S.owner[start + len] = v;
-        S.ord[start + len] = key;
+        S.ord[start + len + S.selfl[v]] = key;
         S.rlen[v] = len + 1;
     }
     __syncthreads();
@@ -364,12 +367,13 @@ __device__ void row_delete(const SdrfDev& S, int v, int key, LoopShared* sh) {
     const int pos = find_sorted(S.col, start, len, key);
     if (threadIdx.x == 0) sh->edit_pos = -1;
     __syncthreads();
-    for (int t = threadIdx.x; t < len; t += SDRF_THREADS)
+    const int olen = len + S.selfl[v];
+    for (int t = threadIdx.x; t < olen; t += SDRF_THREADS)
         if (S.ord[start + t] == key) sh->edit_pos = start + t;
     __syncthreads();
     const int opos = sh->edit_pos;
     shift_left3(S, pos + 1, start + len);
-    shift_left(S.ord, opos + 1, start + len);
+    shift_left(S.ord, opos + 1, start + olen);
     if (threadIdx.x == 0) {
         S.owner[start + len - 1] = -1;
         S.c32[start + len - 1] = 0.0f;    // free slots hold 0
@@ -629,8 +633,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
         if (tid == 0) {
             sh.can_add = 1; sh.do_remove = 0; sh.k = -1; sh.l = -1; sh.choice = -1; sh.chosen_flat = -1;
             sh.found_flat = 0x7fffffffffffffffLL;
-            sh.n_i = S.rlen[sh.x] + 1;                                        // successors of x (:45 / :48)
-            sh.n_j = S.rlen[(MODE == LOOP_DIRECTED ? S.n : 0) + sh.y] + 1;    // neighbours / predecessors of y (:46 / :49)
+            const int ry = (MODE == LOOP_DIRECTED ? S.n : 0) + sh.y;
+            sh.n_i = S.rlen[sh.x] + S.selfl[sh.x] + 1;                        // successors of x (:45 / :48) [+ x itself if it
+            sh.n_j = S.rlen[ry] + S.selfl[ry] + 1;                            //  has a self-loop in G], then x (:46 / :49)
         }
         __syncthreads();
         const int x = sh.x, y = sh.y;
@@ -654,7 +659,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             };
             if constexpr (MODE == LOOP_BFC) {
                 score_prepare(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score);
-                score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, put, n_i - 1, n_j - 1);
+                // x (y) sits at the end of its list — and, with a self-loop, once more inside it: then every row is checked
+                score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, put, S.selfl[x] ? -1 : n_i - 1,
+                            S.selfl[y] ? -1 : n_j - 1);
             } else if constexpr (MODE == LOOP_DIRECTED) {
                 directed_score_prepare(g, gin, x, y, nbI, n_i, nbJ, n_j, sc, &dsh, dred);
                 directed_score_cells(g, gin, x, y, nbI, n_i, nbJ, n_j, sc, &dsh, put);
@@ -807,8 +814,9 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             // BFC: fp32 compare, torch casts the Python float (:83); classical: Python int > float (sdrf_no_cuda.py:62)
             const bool above = (MODE == LOOP_CLASSICAL) ? ((double)sh.cmax > bound64) : (sh.cmax > bound32);
             if (above) {
-                if (!sh.have_max) sh.status = DCR_SDRF_REMOVE_NONEDGE;   // (0,0) fallback beat a negative bound
-                else sh.do_remove = 1;
+                if (sh.have_max) sh.do_remove = 1;
+                else if (MODE == LOOP_BFC && S.selfl[0]) sh.do_remove = 2;   // (0,0) fallback and G has the loop 0-0: it goes
+                else sh.status = DCR_SDRF_REMOVE_NONEDGE;                // (0,0) fallback beat a negative bound
             } else if (!sh.can_add) {
                 sh.stop = 1;
             }
@@ -835,7 +843,17 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             else toggle_supports<MODE == LOOP_BFC>(S, g, k, l, +1, &dirty_count, &sh);
             SDRF_TICK(4);   // supports + dirty (add)
         }
-        if (sh.do_remove) {                             // :84-88
+        if (sh.do_remove == 2) {                        // G.remove_edge(0, 0): only the insertion-order row changes (A[0,0] = 0 already)
+            const int start = S.rstart[0], olen = S.rlen[0] + 1;
+            if (tid == 0) sh.edit_pos = -1;
+            __syncthreads();
+            for (int t = tid; t < olen; t += SDRF_THREADS)
+                if (S.ord[start + t] == 0) sh.edit_pos = start + t;
+            __syncthreads();
+            shift_left(S.ord, sh.edit_pos + 1, start + olen);
+            if (tid == 0) S.selfl[0] = 0;
+            __syncthreads();
+        } else if (sh.do_remove) {                      // :84-88
             const int xr = sh.xr, yr = sh.yr;
             if constexpr (MODE == LOOP_DIRECTED) directed_mark_dirty(S, xr, yr, &dirty_count);
             else toggle_supports<MODE == LOOP_BFC>(S, g, xr, yr, -1, &dirty_count, &sh);
@@ -899,18 +917,27 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
 // ------------------------------------------------------------------------------------------------------------
 // export
 // ------------------------------------------------------------------------------------------------------------
-__global__ void sdrf_export_rowptr_kernel(SdrfDev S, int32_t* rowptr) {
+// with_self: row lengths of the INSERTION-ORDER rows (a node that lists itself has one entry more)
+__global__ void sdrf_export_rowptr_kernel(SdrfDev S, int32_t* rowptr, int with_self) {
     __shared__ Reduce red;
     // single CTA: chunked exclusive scan of rlen
     const int n = S.n;
     const int L = (n + SDRF_THREADS - 1) / SDRF_THREADS;
     const int lo = min(n, (int)threadIdx.x * L), hi = min(n, lo + L);
     long long s = 0;
-    for (int v = lo; v < hi; ++v) s += S.rlen[v];
+    for (int v = lo; v < hi; ++v) s += S.rlen[v] + (with_self ? S.selfl[v] : 0);
     long long total;
     long long off = block_exscan_ll(s, &total, &red);
-    for (int v = lo; v < hi; ++v) { rowptr[v] = (int32_t)off; off += S.rlen[v]; }
+    for (int v = lo; v < hi; ++v) { rowptr[v] = (int32_t)off; off += S.rlen[v] + (with_self ? S.selfl[v] : 0); }
     if (threadIdx.x == 0) rowptr[n] = (int32_t)total;
+}
+__global__ void sdrf_export_order_kernel(SdrfDev S, const int32_t* rowptr, int32_t* order_out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < S.n; v += warps) {
+        const int s = S.rstart[v], d = S.rlen[v] + S.selfl[v], o = rowptr[v];
+        for (int t = lane; t < d; t += 32) order_out[o + t] = S.ord[s + t];
+    }
 }
 __global__ void sdrf_export_rows_kernel(SdrfDev S, const int32_t* rowptr, int32_t* order_out, int32_t* colidx,
                                         float* c32, int32_t* tri) {
@@ -940,6 +967,7 @@ struct dcr_sdrf {
     void* slab;           // one allocation backing every array
     int32_t pending_n;
     int mode;             // DCR_SDRF_MODE_*
+    int64_t n_self;       // nodes that list themselves (self-loops of G)
 };
 
 template <class T>
@@ -959,16 +987,25 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     const bool directed = mode == DCR_SDRF_MODE_BFC_DIRECTED;
     if (directed && !in_rowptr_host) { set_error("dcr_sdrf_create: the directed mode needs the predecessor lists"); return 1; }
     const int rows = directed ? 2 * n : n;
-    const int64_t nnz = rowptr_host[n];
+    int64_t nnz = rowptr_host[n];             // (entries of the insertion-order lists; self entries are subtracted below)
     if (directed && in_rowptr_host[n] != nnz) { set_error("dcr_sdrf_create: successor / predecessor lists disagree"); return 1; }
     auto row_len = [&](int r) { return r < n ? rowptr_host[r + 1] - rowptr_host[r] : in_rowptr_host[r - n + 1] - in_rowptr_host[r - n]; };
     auto row_src = [&](int r) { return r < n ? order_host + rowptr_host[r] : in_order_host + in_rowptr_host[r - n]; };
-    std::vector<int32_t> rstart(rows), rlen(rows), rcap(rows);
-    int64_t sum_cap = 0;
+    std::vector<int32_t> rstart(rows), rlen(rows), rcap(rows), selfl(rows, 0);
+    int64_t sum_cap = 0, n_self = 0;
     int d1 = 0, d2 = 0;   // the two largest row lengths
     for (int v = 0; v < rows; ++v) {
-        const int len = row_len(v);
-        const int cap = len + std::max(2, len / 8);
+        int len = row_len(v);
+        if (mode == DCR_SDRF_MODE_BFC) {      // a node may list ITSELF once (a self-loop of G; A has none): insertion-order row only
+            const int32_t* src = row_src(v);
+            int hits = 0;
+            for (int t = 0; t < len; ++t) hits += src[t] == v;
+            if (hits > 1) { set_error("dcr_sdrf_create: node %d lists itself more than once", v); return 1; }
+            selfl[v] = hits;
+            n_self += hits;
+            len -= hits;
+        }
+        const int cap = len + selfl[v] + std::max(2, len / 8);
         rstart[v] = (int32_t)sum_cap;
         rlen[v] = len;
         rcap[v] = cap;
@@ -978,15 +1015,19 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     const int64_t cap_total = 5 * sum_cap + 8 * max_additions + 1024;
     if (cap_total > 0x7ffffff0LL) { set_error("dcr_sdrf_create: graph too large for a 32-bit arena"); return 1; }
     std::vector<int32_t> col(sum_cap, 0), ord(sum_cap, 0), owner(sum_cap, -1);
+    nnz -= n_self;
     for (int v = 0; v < rows; ++v) {
         const int len = rlen[v];
         const int32_t* src = row_src(v);
         const int self = v < n ? v : v - n;
-        for (int t = 0; t < len; ++t) {
-            if (src[t] < 0 || src[t] >= n || src[t] == self) { set_error("dcr_sdrf_create: bad neighbour id"); return 1; }
+        int filled = 0;
+        for (int t = 0; t < len + selfl[v]; ++t) {
+            if (src[t] < 0 || src[t] >= n || (src[t] == self && !selfl[v])) { set_error("dcr_sdrf_create: bad neighbour id"); return 1; }
             ord[rstart[v] + t] = src[t];
-            col[rstart[v] + t] = src[t];
-            owner[rstart[v] + t] = v;
+            if (src[t] == self) continue;
+            col[rstart[v] + filled] = src[t];
+            owner[rstart[v] + filled] = v;
+            ++filled;
         }
         std::sort(col.begin() + rstart[v], col.begin() + rstart[v] + len);
         for (int t = 1; t < len; ++t)
@@ -1005,6 +1046,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     }
     dcr_sdrf* s = new dcr_sdrf();
     s->mode = mode;
+    s->n_self = n_self;
     SdrfDev& D = s->dev;
     D.n = n;
     D.rows = rows;
@@ -1018,7 +1060,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     D.dirty_cap = (int)std::min<int64_t>(4 * (nnz + 2 * max_additions) + 4096, 0x3ffffff0LL);
     size_t bytes = 0;
     auto add = [&](size_t count, size_t elem) { bytes += (count * elem + 255) / 256 * 256; };
-    add(rows, 4); add(rows, 4); add(rows, 4);                // rstart rlen rcap
+    add(rows, 4); add(rows, 4); add(rows, 4); add(rows, 4);  // rstart rlen rcap selfl
     for (int i = 0; i < 6; ++i) add(cap_total, 4);           // col ord supp c32 owner flag
     add(8, 4);                                               // scalars
     for (int i = 0; i < 4; ++i) add(D.row_cap_max, 4);       // base1 base2 posI posJ
@@ -1029,6 +1071,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(sdrf slab)", __FILE__, __LINE__); }
     char* p = (char*)s->slab;
     D.rstart = carve<int32_t>(p, rows); D.rlen = carve<int32_t>(p, rows); D.rcap = carve<int32_t>(p, rows);
+    D.selfl = carve<int32_t>(p, rows);
     D.col = carve<int32_t>(p, cap_total); D.ord = carve<int32_t>(p, cap_total);
     D.supp = carve<int32_t>(p, cap_total); D.c32 = carve<float>(p, cap_total);
     D.owner = carve<int32_t>(p, cap_total); D.flag = carve<int32_t>(p, cap_total);
@@ -1049,6 +1092,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     SDRF_TRY(cudaMemcpy(D.rstart, rstart.data(), rows * 4, cudaMemcpyHostToDevice));
     SDRF_TRY(cudaMemcpy(D.rlen, rlen.data(), rows * 4, cudaMemcpyHostToDevice));
     SDRF_TRY(cudaMemcpy(D.rcap, rcap.data(), rows * 4, cudaMemcpyHostToDevice));
+    SDRF_TRY(cudaMemcpy(D.selfl, selfl.data(), rows * 4, cudaMemcpyHostToDevice));
     SDRF_TRY(cudaMemset(D.owner, 0xff, cap_total * 4));
     SDRF_TRY(cudaMemset(D.flag, 0, cap_total * 4));
     SDRF_TRY(cudaMemset(D.supp, 0, cap_total * 4));
@@ -1133,10 +1177,26 @@ extern "C" int dcr_sdrf_export(dcr_sdrf* s, int32_t* rowptr, int32_t* order_out,
                                float* c32_sorted, int32_t* tri_sorted, void* stream) {
     if (!s || !rowptr) { set_error("dcr_sdrf_export: bad arguments"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
-    sdrf_export_rowptr_kernel<<<1, SDRF_THREADS, 0, st>>>(s->dev, rowptr);
+    if (order_out && s->n_self > 0) {
+        set_error("dcr_sdrf_export: this state has nodes that list themselves; use dcr_sdrf_export_order for the "
+                  "insertion-order rows");
+        return 1;
+    }
+    sdrf_export_rowptr_kernel<<<1, SDRF_THREADS, 0, st>>>(s->dev, rowptr, 0);
     DCR_LAUNCH_CHECK();
     const int ctas = std::max(1, std::min((s->dev.n + 7) / 8, sm_count() * 8));
     sdrf_export_rows_kernel<<<ctas, 256, 0, st>>>(s->dev, rowptr, order_out, colidx_sorted, c32_sorted, tri_sorted);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcr_sdrf_export_order(dcr_sdrf* s, int32_t* rowptr_order, int32_t* order_out, void* stream) {
+    if (!s || !rowptr_order || !order_out) { set_error("dcr_sdrf_export_order: bad arguments"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    sdrf_export_rowptr_kernel<<<1, SDRF_THREADS, 0, st>>>(s->dev, rowptr_order, 1);
+    DCR_LAUNCH_CHECK();
+    const int ctas = std::max(1, std::min((s->dev.n + 7) / 8, sm_count() * 8));
+    sdrf_export_order_kernel<<<ctas, 256, 0, st>>>(s->dev, rowptr_order, order_out);
     DCR_LAUNCH_CHECK();
     return 0;
 }

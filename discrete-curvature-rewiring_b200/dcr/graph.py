@@ -46,15 +46,17 @@ def undirected_csr(edge_index, num_nodes: int | None = None):
     return rowptr.astype(np.int32), dst.astype(np.int32)
 
 
-def networkx_order(edge_index, num_nodes: int):
+def networkx_order(edge_index, num_nodes: int, keep_self_loops: bool = False):
     """Adjacency of ``to_networkx(data).to_undirected()`` in networkx insertion order.
 
     Returns ``(rowptr int32[n+1], order int32[nnz])``: ``order[rowptr[v]:rowptr[v+1]]`` lists the neighbours of
     ``v`` in the order ``G.neighbors(v)`` yields them.  A pair ``{u,v}`` enters both adjacency dicts when
     ``DiGraph.to_undirected`` first meets one of its directed edges, iterating sources in node order and, per
     source, successors in order of first appearance in ``edge_index``; so neighbours are ordered by that
-    first-touch time.  Self-loops are dropped (with a warning): the reference keeps them in ``G`` but not in ``A``
-    (sdrf_cuda_bfc.py:29 vs :31), a mismatch no shipped dataset exercises.
+    first-touch time.  Self-loops: the reference keeps them in ``G`` but not in ``A`` (sdrf_cuda_bfc.py:29 vs :31), so a
+    node with a self-loop lists ITSELF among its neighbours (and then once more at the end of its candidate list, :45-46).
+    ``keep_self_loops=True`` reproduces that — ``v`` appears in its own list at its insertion position (the BFC loop's
+    arena keeps such an entry in the insertion-order row only); otherwise they are dropped with a warning.
     """
     ei = _as_numpy_edge_index(edge_index)
     n = int(num_nodes)
@@ -62,7 +64,7 @@ def networkx_order(edge_index, num_nodes: int):
         n = int(ei.max()) + 1
     u, v = ei[0], ei[1]
     loops = u == v
-    if loops.any():
+    if loops.any() and not keep_self_loops:
         warnings.warn("self-loops dropped from the rewiring graph (the reference keeps them in G but not in A)")
         u, v = u[~loops], v[~loops]
     m = u.size
@@ -90,9 +92,10 @@ def networkx_order(edge_index, num_nodes: int):
     head[1:] = pk[1:] != pk[:-1]
     pk, tm = pk[head], tm[head]
     a, b = pk // n, pk % n
-    rows = np.concatenate([a, b])
-    cols = np.concatenate([b, a])
-    tms = np.concatenate([tm, tm])
+    two = a != b                                     # a self-loop enters ONE adjacency dict, once
+    rows = np.concatenate([a, b[two]])
+    cols = np.concatenate([b, a[two]])
+    tms = np.concatenate([tm, tm[two]])
     o = np.lexsort((tms, rows))
     rows, cols = rows[o], cols[o]
     rowptr = np.zeros(n + 1, dtype=np.int64)

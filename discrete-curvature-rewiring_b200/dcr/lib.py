@@ -74,6 +74,7 @@ SIGNATURES = {
     "dcr_sdrf_pending_improvements": (_I, [_P, _P, _L, _P]),
     "dcr_sdrf_nnz": (_L, [_P]),
     "dcr_sdrf_export": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "dcr_sdrf_export_order": (_I, [_P, _P, _P, _P]),
 }
 
 _lib = None

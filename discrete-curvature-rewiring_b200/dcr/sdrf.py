@@ -59,6 +59,8 @@ class SdrfState:
         else:
             irp = iod = None
         self._keep = (rp, od, irp, iod)
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(rp.astype(np.int64)))
+        self.n_self = int(np.count_nonzero(od[: rows.size] == rows)) if self.mode == L.SDRF_MODE_BFC else 0
         L.check(self.lib.dcr_sdrf_create_mode(self.n, self.mode, rp.ctypes.data, od.ctypes.data if od.size else 0,
                                               irp.ctypes.data if irp is not None else 0,
                                               iod.ctypes.data if iod is not None and iod.size else 0,
@@ -107,15 +109,22 @@ class SdrfState:
         nnz = self.nnz()
         dev = self.device
         rowptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+        if self.n_self and not with_curvature:
+            # nodes that list themselves (self-loops of G): the insertion-order rows are longer than the adjacency rows
+            order = torch.empty(max(nnz + self.n_self, 1), dtype=torch.int32, device=dev)
+            L.check(self.lib.dcr_sdrf_export_order(self.handle, rowptr.data_ptr(), order.data_ptr(), L.current_stream()),
+                    "dcr_sdrf_export_order")
+            rp = rowptr.cpu().numpy()
+            return rp, order[: int(rp[-1])].cpu().numpy()
         order = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
         col = c32 = tri = None
         if with_curvature:
             col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
             c32 = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
             tri = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-        L.check(self.lib.dcr_sdrf_export(self.handle, rowptr.data_ptr(), order.data_ptr(), L.ptr(col), L.ptr(c32),
-                                         L.ptr(tri), L.current_stream()), "dcr_sdrf_export")
-        out = (rowptr.cpu().numpy(), order[:nnz].cpu().numpy())
+        L.check(self.lib.dcr_sdrf_export(self.handle, rowptr.data_ptr(), 0 if self.n_self else order.data_ptr(), L.ptr(col),
+                                         L.ptr(c32), L.ptr(tri), L.current_stream()), "dcr_sdrf_export")
+        out = (rowptr.cpu().numpy(), order[:nnz].cpu().numpy() if not self.n_self else None)
         if with_curvature:
             out += (col[:nnz].cpu().numpy(), c32[:nnz].cpu().numpy(), tri[:nnz].cpu().numpy())
         return out
@@ -164,7 +173,7 @@ def sdrf(edge_index, num_nodes: int, loops: int, remove_edges: bool, removal_bou
     directed = False
     if curv_type == "bfc":
         if is_undirected:
-            rowptr, order = G.networkx_order(edge_index, num_nodes)
+            rowptr, order = G.networkx_order(edge_index, num_nodes, keep_self_loops=True)    # G keeps them (:31), A does not (:29)
             state = SdrfState(rowptr, order, max_additions=max(int(loops), 0))
         else:
             directed = True

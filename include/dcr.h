@@ -255,7 +255,11 @@ typedef struct dcr_sdrf_result {
 
 /* Build the device state from a host CSR in NETWORKX ADJACENCY ORDER (order_host[rowptr_host[v]..] lists the
  * neighbours of v in insertion order, sdrf_cuda_bfc.py:31-33,45-46); synchronises.  max_additions bounds the
- * number of edge insertions over the lifetime of the state (arena sizing). */
+ * number of edge insertions over the lifetime of the state (arena sizing).
+ * Self-loops: the reference keeps a self-loop of the input in G (:31) but not in A (:29), so such a node meets ITSELF
+ * in G.neighbors(v) and appears twice in its own candidate list (:45-46).  A list may therefore contain v itself, once,
+ * at its insertion position: the entry lives in the insertion-order row only (no adjacency entry, no curvature), is
+ * exported by dcr_sdrf_export_order, and is removed when the (0,0) fallback of the removal step hits a loop 0-0. */
 int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host, int64_t max_additions,
                     dcr_sdrf** out);
 /* The other loop flavours (DCR_SDRF_MODE_*).  BFC_DIRECTED: rowptr/order list the SUCCESSORS of every node in
@@ -283,6 +287,10 @@ int64_t dcr_sdrf_nnz(dcr_sdrf* s);
  * (`order_out`), plus, in SORTED order per row, colidx / curvature (fp32, cuda flavour) / support. */
 int dcr_sdrf_export(dcr_sdrf* s, int32_t* rowptr, int32_t* order_out, int32_t* colidx_sorted, float* c32_sorted,
                     int32_t* tri_sorted, void* stream);
+
+/* Insertion-order rows INCLUDING the self entries (see dcr_sdrf_create): rowptr_order[n+1] and order_out[rowptr_order[n]]
+ * (at most nnz + n entries).  dcr_sdrf_export refuses order_out for a state that has self entries. */
+int dcr_sdrf_export_order(dcr_sdrf* s, int32_t* rowptr_order, int32_t* order_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -419,8 +419,43 @@ def gen_sdrf_classical(out):
     print("sdrf_classical_seq:", len(cases), "cases")
 
 
+def gen_sdrf_selfloops(out):
+    """Inputs WITH self-loops (the WebKB datasets carry some): the reference keeps them in ``G`` (sdrf_cuda_bfc.py:31) but
+    not in ``A`` (:29), so a node with a self-loop appears twice in its own candidate list (:45-46) and the loop survives
+    into the output ``edge_index`` (:93)."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for q, (g, loops, bound, tau, seed, n_self) in enumerate([
+            (nx.gnp_random_graph(14, 0.25, seed=3), 8, 0.5, float("inf"), 51, 3),
+            (nx.gnp_random_graph(16, 0.22, seed=5), 8, 0.3, 4, 52, 4),
+            (nx.barbell_graph(5, 2), 8, 1.2, 7, 53, 2),
+            (nx.gnp_random_graph(18, 0.2, seed=9), 8, 100.0, float("inf"), 54, 18)]):
+        ei = sorted_symmetric_edge_index(g)
+        n = g.number_of_nodes()
+        who = rng.choice(n, size=min(n_self, n), replace=False)
+        ei = np.concatenate([ei, np.stack([who, who])], axis=1)
+        ei = ei[:, rng.permutation(ei.shape[1])]            # self-loops at arbitrary insertion positions
+        cases.append((f"self{q}", ei, n, loops, bound, tau, seed))
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, ei, n, loops, bound, tau, seed in cases:
+        eo, log, uni = run_reference_rewire(ei, n, loops, bound, tau, seed)
+        pack[f"{name}/edge_index"] = ei
+        pack[f"{name}/n"] = np.int64(n)
+        pack[f"{name}/loops"] = np.int64(loops)
+        pack[f"{name}/bound"] = np.float64(bound)
+        pack[f"{name}/tau"] = np.float64(tau)
+        pack[f"{name}/uniforms"] = uni
+        pack[f"{name}/out"] = eo
+        pack[f"{name}/log"] = log
+        print(f"  sdrf-selfloops {name}: n={n} loops={loops} log={len(log)}", flush=True)
+    np.savez_compressed(out, **pack)
+    print("sdrf_selfloop_seq:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical"]
+    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical", "sdrf_selfloops"]
+    if "sdrf_selfloops" in which:
+        gen_sdrf_selfloops(os.path.join(HERE, "sdrf_selfloop_seq.npz"))
     if "sdrf_classical" in which:
         gen_sdrf_classical(os.path.join(HERE, "sdrf_classical_seq.npz"))
     if "paper_ints" in which:

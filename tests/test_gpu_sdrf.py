@@ -215,3 +215,51 @@ def test_sdrf_negative_bound_removes_nonedge_raises_like_networkx():
     assert bfc_cuda_dense(dense_of(ei, n))["C"].max() <= 0
     with pytest.raises(nx.NetworkXError):
         sdrf.sdrf(ei, n, 2, True, -1.0, float("inf"), uniforms=np.array([0.5, 0.5]))
+
+
+def _with_self_loops(ei, n, k, seed):
+    rng = np.random.default_rng(seed)
+    who = rng.choice(n, size=min(k, n), replace=False)
+    out = np.concatenate([ei, np.stack([who, who])], axis=1)
+    return out[:, rng.permutation(out.shape[1])]
+
+
+def test_sdrf_inputs_with_self_loops_follow_the_reference_quirk():
+    """The reference keeps self-loops in G but not in A (sdrf_cuda_bfc.py:29 vs :31): a node with a self-loop is in its own
+    neighbour list, hence twice in its candidate list, and the loop survives into the output.  Oracle (which reproduces
+    the unmodified reference on such inputs, tests/golden/sdrf_selfloop_seq.npz), goldens and — when present — the
+    reference's own kernels."""
+    from dcr import sdrf
+    from oracle.sdrf import sdrf_oracle
+    for s, tau in enumerate([float("inf"), 6, 30]):
+        n = 16 + 7 * s
+        ei = _with_self_loops(gnp(n, 0.22, 900 + s), n, 3 + 2 * s, s)
+        glog = _run_both(ei, n, 14, [0.5, 0.3, 0.1][s], tau, 80 + s)
+        assert len(glog) > 0
+    # every node carries a loop, node 0 included; a negative bound makes the (0,0) fallback remove the loop 0-0
+    n = 12
+    ei = _with_self_loops(sym_edge_index([(i, (i + 1) % n) for i in range(n)], n), n, n, 5)
+    _run_both(ei, n, 6, -5.0, float("inf"), 3)
+    z = golden("sdrf_selfloop_seq.npz")
+    agreeing = 0
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        args = (int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]), float(z[f"{name}/tau"]))
+        uni = z[f"{name}/uniforms"]
+        want, _ = sdrf_oracle(ei, n, *args, uni, rounding="compiled")
+        if not np.array_equal(want, z[f"{name}/out"]):
+            continue          # a near-tie the simulator's all-fp32 rounding breaks differently
+        agreeing += 1
+        got = sdrf.sdrf(ei, n, *args, uniforms=uni)
+        assert np.array_equal(got, z[f"{name}/out"]), name
+        assert int((got[0] == got[1]).sum()) > 0
+    assert agreeing >= 2
+    from oracle import ref_gpu
+    if ref_gpu.available():
+        n = 30
+        ei = _with_self_loops(gnp(n, 0.2, 31), n, 6, 9)
+        uni = np.random.RandomState(2).random_sample(12)
+        want, wlog = ref_gpu.sdrf_reference_gpu(ei, n, 12, True, 0.4, 9, uni)
+        got, log = sdrf.sdrf(ei, n, 12, True, 0.4, 9, uniforms=uni, return_log=True)
+        assert [tuple(int(v) for v in r) for r in log] == _oracle_log_tuples(wlog)
+        assert np.array_equal(got, want)

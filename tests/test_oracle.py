@@ -83,6 +83,19 @@ def _mutations(log):
     return np.array(mine, dtype=np.int64).reshape(-1, 3)
 
 
+def test_sdrf_oracle_reproduces_reference_on_inputs_with_self_loops():
+    """Quirk D.1: G keeps self-loops (sdrf_cuda_bfc.py:31), A drops them (:29) — the unmodified reference on four graphs with
+    self-loops at arbitrary insertion positions (sequence + output, which still contains the loops)."""
+    z = golden("sdrf_selfloop_seq.npz")
+    for name in _names(z):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        out, log = sdrf_oracle(ei, n, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]),
+                               float(z[f"{name}/tau"]), z[f"{name}/uniforms"], rounding="sim32", verify_a2_every=1)
+        assert np.array_equal(_mutations(log), z[f"{name}/log"]), name
+        assert np.array_equal(out, z[f"{name}/out"]), name
+        assert int((out[0] == out[1]).sum()) > 0
+
+
 def test_sdrf_classical_oracle_reproduces_reference_sequences():
     """rewiring/sdrf_no_cuda.py:9-68 with '1d' / 'augmented' / 'haantjes' (SURVEY.md §8f-4): add/remove sequence and
     output edge_index of the UNMODIFIED reference, greedy and stochastic."""
