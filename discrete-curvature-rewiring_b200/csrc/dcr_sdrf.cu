@@ -659,6 +659,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             };
             if constexpr (MODE == LOOP_BFC) {
                 score_prepare(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score);
+                SDRF_TICK(7);   // (profile build: scoring = prepare [7] + cells [1])
                 // x (y) sits at the end of its list — and, with a self-loop, once more inside it: then every row is checked
                 score_cells(g, S.supp, x, y, nbI, n_i, nbJ, n_j, sc, &sh.score, put, S.selfl[x] ? -1 : n_i - 1,
                             S.selfl[y] ? -1 : n_j - 1);

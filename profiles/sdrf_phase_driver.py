@@ -13,8 +13,9 @@ for name, loops in (("cora", 1000), ("wisconsin", 136)):
     res, log = st.run(loops, True, 0.95, 163, torch.from_numpy(uni).cuda())
     torch.cuda.synchronize()
     lib.dcr_sdrf_phase_cycles(buf, 1)
-    names = ["argmin/max", "scoring", "selection", "insert rows", "supports+dirty(add)", "removal", "refresh"]
-    tot = sum(buf[:7])
+    names = ["argmin/max", "scoring: cells", "selection", "insert rows", "supports+dirty(add)", "removal", "refresh",
+             "scoring: prepare"]
+    tot = sum(buf[:8])
     print(name, res["iterations_done"], "iters; cycles/iter", tot // max(res["iterations_done"], 1))
     for i, nm in enumerate(names):
         print(f"   {nm:22s} {100*buf[i]/tot:5.1f}%  {buf[i]//res['iterations_done']:8d} cyc/iter")
