@@ -816,7 +816,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             const bool above = (MODE == LOOP_CLASSICAL) ? ((double)sh.cmax > bound64) : (sh.cmax > bound32);
             if (above) {
                 if (sh.have_max) sh.do_remove = 1;
-                else if (MODE == LOOP_BFC && S.selfl[0]) sh.do_remove = 2;   // (0,0) fallback and G has the loop 0-0: it goes
+                else if (MODE != LOOP_CLASSICAL && S.selfl[0]) sh.do_remove = 2;   // (0,0) fallback and G has the loop 0-0: it goes
                 else sh.status = DCR_SDRF_REMOVE_NONEDGE;                // (0,0) fallback beat a negative bound
             } else if (!sh.can_add) {
                 sh.stop = 1;
@@ -844,16 +844,18 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             else toggle_supports<MODE == LOOP_BFC>(S, g, k, l, +1, &dirty_count, &sh);
             SDRF_TICK(4);   // supports + dirty (add)
         }
-        if (sh.do_remove == 2) {                        // G.remove_edge(0, 0): only the insertion-order row changes (A[0,0] = 0 already)
-            const int start = S.rstart[0], olen = S.rlen[0] + 1;
-            if (tid == 0) sh.edit_pos = -1;
-            __syncthreads();
-            for (int t = tid; t < olen; t += SDRF_THREADS)
-                if (S.ord[start + t] == 0) sh.edit_pos = start + t;
-            __syncthreads();
-            shift_left(S.ord, sh.edit_pos + 1, start + olen);
-            if (tid == 0) S.selfl[0] = 0;
-            __syncthreads();
+        if (sh.do_remove == 2) {                        // G.remove_edge(0, 0): only the insertion-order rows change (A[0,0] = 0 already)
+            for (int row = 0; row <= (MODE == LOOP_DIRECTED ? S.n : 0); row += max(S.n, 1)) {   // node 0's row(s)
+                const int start = S.rstart[row], olen = S.rlen[row] + 1;
+                if (tid == 0) sh.edit_pos = -1;
+                __syncthreads();
+                for (int t = tid; t < olen; t += SDRF_THREADS)
+                    if (S.ord[start + t] == 0) sh.edit_pos = start + t;
+                __syncthreads();
+                shift_left(S.ord, sh.edit_pos + 1, start + olen);
+                if (tid == 0) S.selfl[row] = 0;
+                __syncthreads();
+            }
         } else if (sh.do_remove) {                      // :84-88
             const int xr = sh.xr, yr = sh.yr;
             if constexpr (MODE == LOOP_DIRECTED) directed_mark_dirty(S, xr, yr, &dirty_count);
@@ -997,13 +999,14 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     int d1 = 0, d2 = 0;   // the two largest row lengths
     for (int v = 0; v < rows; ++v) {
         int len = row_len(v);
-        if (mode == DCR_SDRF_MODE_BFC) {      // a node may list ITSELF once (a self-loop of G; A has none): insertion-order row only
-            const int32_t* src = row_src(v);
+        if (mode == DCR_SDRF_MODE_BFC || directed) {   // a node may list ITSELF once (a self-loop of G; A has none):
+            const int32_t* src = row_src(v);           // insertion-order row only (directed: successor AND predecessor row)
+            const int me = v < n ? v : v - n;
             int hits = 0;
-            for (int t = 0; t < len; ++t) hits += src[t] == v;
-            if (hits > 1) { set_error("dcr_sdrf_create: node %d lists itself more than once", v); return 1; }
+            for (int t = 0; t < len; ++t) hits += src[t] == me;
+            if (hits > 1) { set_error("dcr_sdrf_create: node %d lists itself more than once", me); return 1; }
             selfl[v] = hits;
-            n_self += hits;
+            if (v < n) n_self += hits;                 // (counted once per node: the successor / neighbour rows)
             len -= hits;
         }
         const int cap = len + selfl[v] + std::max(2, len / 8);
@@ -1016,7 +1019,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     const int64_t cap_total = 5 * sum_cap + 8 * max_additions + 1024;
     if (cap_total > 0x7ffffff0LL) { set_error("dcr_sdrf_create: graph too large for a 32-bit arena"); return 1; }
     std::vector<int32_t> col(sum_cap, 0), ord(sum_cap, 0), owner(sum_cap, -1);
-    nnz -= n_self;
+    nnz -= n_self;                            // (directed: successor entries; the predecessor rows mirror them)
     for (int v = 0; v < rows; ++v) {
         const int len = rlen[v];
         const int32_t* src = row_src(v);
@@ -1035,6 +1038,8 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
             if (col[rstart[v] + t] == col[rstart[v] + t - 1]) { set_error("dcr_sdrf_create: duplicate neighbour"); return 1; }
     }
     if (directed) {   // the predecessor rows must be the transpose of the successor rows
+        for (int v = 0; v < n; ++v)
+            if (selfl[v] != selfl[n + v]) { set_error("dcr_sdrf_create: successor / predecessor lists disagree"); return 1; }
         for (int v = 0; v < n; ++v)
             for (int t = 0; t < rlen[v]; ++t) {
                 const int w = col[rstart[v] + t];

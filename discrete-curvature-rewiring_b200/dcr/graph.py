@@ -137,11 +137,12 @@ def _rows_in_time_order(rows: np.ndarray, cols: np.ndarray, n: int):
     return rowptr.astype(np.int32), cols[o].astype(np.int32)
 
 
-def digraph_order(edge_index, num_nodes: int):
+def digraph_order(edge_index, num_nodes: int, keep_self_loops: bool = False):
     """Successor and predecessor lists of ``to_networkx(data)`` — a ``DiGraph`` filled by ``add_edge(u, v)`` in column
     order (rewiring/sdrf_cuda_bfc.py:31; is_undirected=False keeps it directed) — in networkx insertion order:
     ``(succ_rowptr, succ_order, pred_rowptr, pred_order)``.  ``G.successors(x)`` / ``G.predecessors(y)`` (:48-49) yield
-    exactly these orders.  Self-loops are dropped with a warning (the reference keeps them in ``G`` but not in ``A``);
+    exactly these orders.  Self-loops: kept with ``keep_self_loops=True`` (``v`` then sits in its own successor AND
+    predecessor list, like in the reference's ``G``; ``A`` has no diagonal), otherwise dropped with a warning;
     a repeated directed pair raises: ``to_dense_adj`` would sum it into a weight 2 (:29), which the 0/1 kernels do not
     model."""
     ei = _as_numpy_edge_index(edge_index)
@@ -150,7 +151,7 @@ def digraph_order(edge_index, num_nodes: int):
         n = int(ei.max()) + 1
     u, v = ei[0], ei[1]
     loops = u == v
-    if loops.any():
+    if loops.any() and not keep_self_loops:
         warnings.warn("self-loops dropped from the rewiring graph (the reference keeps them in G but not in A)")
         u, v = u[~loops], v[~loops]
     if u.size and np.unique(u * n + v).size != u.size:

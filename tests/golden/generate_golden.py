@@ -452,7 +452,33 @@ def gen_sdrf_selfloops(out):
     print("sdrf_selfloop_seq:", len(cases), "cases")
 
 
+def gen_sdrf_directed_selfloops(out):
+    """is_undirected=False on digraphs WITH self-loops: kept in the DiGraph (successors AND predecessors of the node), not
+    in A."""
+    rng = np.random.default_rng(91)
+    cases = []
+    for q, (n, m, loops, bound, tau, seed, n_self) in enumerate([(12, 30, 6, 0.3, 5, 61, 3), (14, 40, 6, 0.5, float("inf"), 62, 4),
+                                                                  (10, 36, 6, -5.0, float("inf"), 63, 10)]):
+        ei = rng.integers(0, n, size=(2, m))
+        ei = ei[:, ei[0] != ei[1]]
+        ei = np.unique(ei, axis=1)
+        who = rng.choice(n, size=n_self, replace=False)
+        ei = np.concatenate([ei, np.stack([who, who])], axis=1)
+        ei = ei[:, rng.permutation(ei.shape[1])]
+        cases.append((f"dself{q}", ei, n, loops, bound, tau, seed))
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, ei, n, loops, bound, tau, seed in cases:
+        eo, log, uni = run_reference_directed(ei, n, loops, bound, tau, seed)
+        for key, val in (("edge_index", ei), ("n", np.int64(n)), ("loops", np.int64(loops)), ("bound", np.float64(bound)),
+                         ("tau", np.float64(tau)), ("uniforms", uni), ("out", eo), ("log", log)):
+            pack[f"{name}/{key}"] = val
+        print(f"  sdrf-directed-selfloops {name}: n={n} loops={loops} log={len(log)}", flush=True)
+    np.savez_compressed(out, **pack)
+
+
 if __name__ == "__main__":
+    if "sdrf_directed_selfloops" in sys.argv[1:]:
+        gen_sdrf_directed_selfloops(os.path.join(HERE, "sdrf_directed_selfloop_seq.npz"))
     which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical", "sdrf_selfloops"]
     if "sdrf_selfloops" in which:
         gen_sdrf_selfloops(os.path.join(HERE, "sdrf_selfloop_seq.npz"))

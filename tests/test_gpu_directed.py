@@ -214,3 +214,35 @@ def test_directed_dropin_signature_and_rejections():
     data.num_nodes = n
     with pytest.raises(NotImplementedError):
         sdrf_cuda_bfc(data, 3, True, 0.4, 6, False, uniforms=uni)
+
+
+def test_directed_sdrf_inputs_with_self_loops():
+    """Self-loops stay in the reference's DiGraph (a node is its own successor and predecessor) but not in A: oracle,
+    goldens of the unmodified reference, and a negative bound that lets the (0,0) fallback delete the loop 0 -> 0."""
+    from dcr import sdrf
+    from oracle.sdrf import sdrf_oracle
+    rng = np.random.default_rng(3)
+    for s, tau in enumerate([float("inf"), 7]):
+        n = 14 + 8 * s
+        ei = random_digraph(n, 4 * n, 200 + s)
+        who = rng.choice(n, size=4 + s, replace=False)
+        ei = np.concatenate([ei, np.stack([who, who])], axis=1)
+        ei = ei[:, rng.permutation(ei.shape[1])]
+        _run_both(ei, n, 12, 0.3, tau, 90 + s)
+    n = 8
+    ring = np.array([[i, (i + 1) % n] for i in range(n)]).T
+    ei = np.concatenate([ring, np.stack([np.arange(n), np.arange(n)])], axis=1)      # a directed ring: every C is <= 0
+    _run_both(ei, n, 4, -5.0, float("inf"), 1)
+    z = golden("sdrf_directed_selfloop_seq.npz")
+    agreeing = 0
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        args = (int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]), float(z[f"{name}/tau"]))
+        uni = z[f"{name}/uniforms"]
+        want, _ = sdrf_oracle(ei, n, *args, uni, rounding="compiled", is_undirected=False)
+        if not np.array_equal(want, z[f"{name}/out"]):
+            continue
+        agreeing += 1
+        got = sdrf.sdrf(ei, n, *args, uniforms=uni, is_undirected=False)
+        assert np.array_equal(got, z[f"{name}/out"]), name
+    assert agreeing >= 2

@@ -96,6 +96,16 @@ def test_sdrf_oracle_reproduces_reference_on_inputs_with_self_loops():
         assert int((out[0] == out[1]).sum()) > 0
 
 
+def test_sdrf_oracle_directed_mode_with_self_loops():
+    z = golden("sdrf_directed_selfloop_seq.npz")
+    for name in _names(z):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        out, log = sdrf_oracle(ei, n, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]), float(z[f"{name}/tau"]),
+                               z[f"{name}/uniforms"], rounding="sim32", verify_a2_every=1, is_undirected=False)
+        assert np.array_equal(_mutations(log), z[f"{name}/log"]), name
+        assert np.array_equal(out, z[f"{name}/out"]), name
+
+
 def test_sdrf_classical_oracle_reproduces_reference_sequences():
     """rewiring/sdrf_no_cuda.py:9-68 with '1d' / 'augmented' / 'haantjes' (SURVEY.md §8f-4): add/remove sequence and
     output edge_index of the UNMODIFIED reference, greedy and stochastic."""
