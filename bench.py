@@ -753,12 +753,16 @@ def run_ours(args):
         except Exception as exc:
             line["dense"] = {"unavailable": repr(exc)[:300]}
     if args.workload == "arxiv" and not args.no_cuda_flavour:
-        try:
-            cf = cuda_flavour_bench(args, torch, dist, csr, esrc, edst, rowptr, world, rank, dev, flush)
-        except Exception as exc:
-            if world > 1:
-                raise
-            cf = {"unavailable": repr(exc)[:300]}
+        if world > 1 and sh.mode != "peer":
+            # the sharded cuda flavour exchanges through peer memory only; every rank took the same (NCCL) route above
+            cf = {"unavailable": "peer-memory exchange unavailable on this box (the paper-flavour pass fell back to NCCL)"}
+        else:
+            try:
+                cf = cuda_flavour_bench(args, torch, dist, csr, esrc, edst, rowptr, world, rank, dev, flush)
+            except Exception as exc:
+                if world > 1:
+                    raise
+                cf = {"unavailable": repr(exc)[:300]}
         if rank == 0:
             line["cuda_flavour"] = cf
     if rank == 0 and not args.no_sdrf:
