@@ -453,10 +453,21 @@ __device__ __forceinline__ float entry_curvature(const SdrfDev& S, int a, int b,
 // classical curvature of an entry from the maintained degrees / support (curvature/classical_curvatures.py:15-28);
 // small integers, exact in fp32
 __device__ __forceinline__ float classical_curvature(const SdrfDev& S, int a, int b, int slot_ab) {
-    const int base = 4 - S.rlen[a] - S.rlen[b];
-    if (S.ctype == 0) return (float)base;                         // '1d'
-    if (S.ctype == 1) return (float)(base + 3 * S.supp[slot_ab]);  // 'augmented'
-    return (float)S.supp[slot_ab];                                // 'haantjes'
+    // a self-loop of G counts twice in G.degree and makes the node its own neighbour: for an EDGE (a,b) each looped
+    // endpoint is one more common neighbour (a in N(b) and in N'(a) = N(a) + {a})
+    const int la = S.selfl[a], lb = S.selfl[b];
+    const int base = 4 - (S.rlen[a] + 2 * la) - (S.rlen[b] + 2 * lb);
+    const int tri = S.supp[slot_ab] + la + lb;
+    if (S.ctype == 0) return (float)base;                 // '1d'
+    if (S.ctype == 1) return (float)(base + 3 * tri);      // 'augmented'
+    return (float)tri;                                    // 'haantjes'
+}
+// curvature of the loop edge (u,u) itself (compute_curvature_edge with v1 = v2 = u): degree d + 2, N'(u) ∩ N'(u) = d + 1
+__device__ __forceinline__ float classical_loop_curvature(const SdrfDev& S, int u) {
+    const int d = S.rlen[u];
+    if (S.ctype == 0) return (float)(4 - 2 * (d + 2));
+    if (S.ctype == 1) return (float)(4 - 2 * (d + 2) + 3 * (d + 1));
+    return (float)(d + 1);
 }
 
 // Directed loop: entries whose curvature may change when the entry k -> l is toggled (call while it is PRESENT).
@@ -562,6 +573,12 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
                 vmin = fminf(vmin, v);
                 vmax = fmaxf(vmax, v);
             }
+            for (int u = tid; u < S.n; u += SDRF_THREADS) {     // the loop edges (u,u) of G.edges
+                if (!S.selfl[u]) continue;
+                const float v = classical_loop_curvature(S, u);
+                vmin = fminf(vmin, v);
+                vmax = fmaxf(vmax, v);
+            }
             vmin = block_best(Best{vmin, 0ull}, &sh.red).v;
             vmax = -block_best(Best{-vmax, 0ull}, &sh.red).v;
             if (!(vmin <= vmax)) {                              // no edges: min() of an empty sequence
@@ -577,19 +594,30 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
                 if (v == vmin) umin = min(umin, (unsigned long long)o);
                 if (v == vmax) umax = min(umax, (unsigned long long)o);
             }
+            for (int u = tid; u < S.n; u += SDRF_THREADS) {
+                if (!S.selfl[u]) continue;
+                const float v = classical_loop_curvature(S, u);
+                if (v == vmin) umin = min(umin, (unsigned long long)u);
+                if (v == vmax) umax = min(umax, (unsigned long long)u);
+            }
             const int xu = (int)block_best(Best{0.0f, umin}, &sh.red).key;
             const int xru = (int)block_best(Best{0.0f, umax}, &sh.red).key;
             unsigned long long pmin = ~0ull, pmax = ~0ull;
             {
+                // (the insertion-order row holds the node itself where its loop was added: G.edges reports it there)
                 const int st = S.rstart[xu], len = S.rlen[xu];
-                for (int t = tid; t < len; t += SDRF_THREADS) {
+                for (int t = tid; t < len + S.selfl[xu]; t += SDRF_THREADS) {
                     const int v = S.ord[st + t];
-                    if (v > xu && S.c32[find_sorted(S.col, st, len, v)] == vmin) pmin = min(pmin, (unsigned long long)t);
+                    const bool hit = v == xu ? classical_loop_curvature(S, xu) == vmin
+                                             : (v > xu && S.c32[find_sorted(S.col, st, len, v)] == vmin);
+                    if (hit) pmin = min(pmin, (unsigned long long)t);
                 }
                 const int st2 = S.rstart[xru], len2 = S.rlen[xru];
-                for (int t = tid; t < len2; t += SDRF_THREADS) {
+                for (int t = tid; t < len2 + S.selfl[xru]; t += SDRF_THREADS) {
                     const int v = S.ord[st2 + t];
-                    if (v > xru && S.c32[find_sorted(S.col, st2, len2, v)] == vmax) pmax = min(pmax, (unsigned long long)t);
+                    const bool hit = v == xru ? classical_loop_curvature(S, xru) == vmax
+                                              : (v > xru && S.c32[find_sorted(S.col, st2, len2, v)] == vmax);
+                    if (hit) pmax = min(pmax, (unsigned long long)t);
                 }
             }
             pmin = block_best(Best{0.0f, pmin}, &sh.red).key;
@@ -815,7 +843,7 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
             // BFC: fp32 compare, torch casts the Python float (:83); classical: Python int > float (sdrf_no_cuda.py:62)
             const bool above = (MODE == LOOP_CLASSICAL) ? ((double)sh.cmax > bound64) : (sh.cmax > bound32);
             if (above) {
-                if (sh.have_max) sh.do_remove = 1;
+                if (sh.have_max) sh.do_remove = (MODE == LOOP_CLASSICAL && sh.xr == sh.yr) ? 3 : 1;   // 3: the maximum is a loop edge
                 else if (MODE != LOOP_CLASSICAL && S.selfl[0]) sh.do_remove = 2;   // (0,0) fallback and G has the loop 0-0: it goes
                 else sh.status = DCR_SDRF_REMOVE_NONEDGE;                // (0,0) fallback beat a negative bound
             } else if (!sh.can_add) {
@@ -856,6 +884,18 @@ sdrf_loop_kernel(SdrfDev S, int loops, int remove_edges, float bound32, double b
                 if (tid == 0) S.selfl[row] = 0;
                 __syncthreads();
             }
+        } else if (sh.do_remove == 3) {                 // classical loop: G.remove_edge(u, u) — degree - 2, u no longer its own neighbour
+            const int u = sh.xr, start = S.rstart[u], len = S.rlen[u];
+            if (tid == 0) sh.edit_pos = -1;
+            __syncthreads();
+            for (int t = tid; t < len + 1; t += SDRF_THREADS)
+                if (S.ord[start + t] == u) sh.edit_pos = start + t;
+            __syncthreads();
+            shift_left(S.ord, sh.edit_pos + 1, start + len + 1);
+            if (tid == 0) S.selfl[u] = 0;
+            __syncthreads();
+            for (int t = tid; t < len; t += SDRF_THREADS) push_dirty(S, &dirty_count, u, S.col[start + t]);   // every edge at u changes
+            __syncthreads();
         } else if (sh.do_remove) {                      // :84-88
             const int xr = sh.xr, yr = sh.yr;
             if constexpr (MODE == LOOP_DIRECTED) directed_mark_dirty(S, xr, yr, &dirty_count);
@@ -999,7 +1039,7 @@ static int sdrf_create_impl(int n, int mode, const int32_t* rowptr_host, const i
     int d1 = 0, d2 = 0;   // the two largest row lengths
     for (int v = 0; v < rows; ++v) {
         int len = row_len(v);
-        if (mode == DCR_SDRF_MODE_BFC || directed) {   // a node may list ITSELF once (a self-loop of G; A has none):
+        {                                              // a node may list ITSELF once (a self-loop of G; A has none):
             const int32_t* src = row_src(v);           // insertion-order row only (directed: successor AND predecessor row)
             const int me = v < n ? v : v - n;
             int hits = 0;

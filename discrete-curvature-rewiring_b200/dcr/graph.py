@@ -170,27 +170,29 @@ def from_digraph_order(rowptr: np.ndarray, order: np.ndarray) -> np.ndarray:
     return np.stack([rows, np.asarray(order, dtype=np.int64)])
 
 
-def classical_order(edge_index, num_nodes: int):
+def classical_order(edge_index, num_nodes: int, keep_self_loops: bool = False):
     """Adjacency of ``to_networkx(data, node_attrs=['x'], to_undirected=True)`` (rewiring/sdrf_no_cuda.py:19) in networkx
     insertion order: PyG 2.0.3 skips every column with ``v > u`` and calls ``add_edge(u, v)`` for the others, in column
-    order — an edge listed only as ``(u, v)`` with ``u < v`` is therefore lost, like in the reference.  Self-loops are
-    dropped with a warning (the reference would keep them).  Returns ``(rowptr int32[n+1], order int32[nnz])``."""
+    order — an edge listed only as ``(u, v)`` with ``u < v`` is therefore lost, like in the reference.  Self-loops:
+    kept with ``keep_self_loops=True`` (``u`` then sits in its own list where ``add_edge(u, u)`` happened), otherwise
+    dropped with a warning.  Returns ``(rowptr int32[n+1], order int32[nnz])``."""
     ei = _as_numpy_edge_index(edge_index)
     n = int(num_nodes)
     if ei.size and int(ei.max()) >= n:
         n = int(ei.max()) + 1
     u, v = ei[0], ei[1]
-    if (u == v).any():
+    if (u == v).any() and not keep_self_loops:
         warnings.warn("self-loops dropped from the rewiring graph (the reference's sdrf_no_cuda would keep them)")
-    keep = v < u
+    keep = (v <= u) if keep_self_loops else (v < u)       # a column (u, u) passes PyG's `v > u` filter: add_edge(u, u)
     u, v = u[keep], v[keep]
     if u.size == 0:
         return np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32)
     u, v = _first_occurrences(u, v, n)
     t = np.arange(u.size, dtype=np.int64)
-    rows = np.concatenate([u, v])
-    cols = np.concatenate([v, u])
-    tm = np.concatenate([t, t])
+    two = u != v                                           # a loop enters one adjacency dict, once
+    rows = np.concatenate([u, v[two]])
+    cols = np.concatenate([v, u[two]])
+    tm = np.concatenate([t, t[two]])
     o = np.lexsort((tm, rows))
     rowptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=n), out=rowptr[1:])

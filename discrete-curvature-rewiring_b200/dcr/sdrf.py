@@ -60,8 +60,7 @@ class SdrfState:
             irp = iod = None
         self._keep = (rp, od, irp, iod)
         rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(rp.astype(np.int64)))
-        self.n_self = int(np.count_nonzero(od[: rows.size] == rows)) \
-            if self.mode in (L.SDRF_MODE_BFC, L.SDRF_MODE_BFC_DIRECTED) else 0
+        self.n_self = int(np.count_nonzero(od[: rows.size] == rows))      # nodes that list themselves (self-loops of G)
         L.check(self.lib.dcr_sdrf_create_mode(self.n, self.mode, rp.ctypes.data, od.ctypes.data if od.size else 0,
                                               irp.ctypes.data if irp is not None else 0,
                                               iod.ctypes.data if iod is not None and iod.size else 0,
@@ -182,7 +181,7 @@ def sdrf(edge_index, num_nodes: int, loops: int, remove_edges: bool, removal_bou
             state = SdrfState(s_rp, s_ord, max_additions=max(int(loops), 0), mode=L.SDRF_MODE_BFC_DIRECTED,
                               in_rowptr=p_rp, in_order=p_ord)
     elif curv_type in CLASSICAL_MODES:
-        rowptr, order = G.classical_order(edge_index, num_nodes)
+        rowptr, order = G.classical_order(edge_index, num_nodes, keep_self_loops=True)
         state = SdrfState(rowptr, order, max_additions=max(int(loops), 0), mode=CLASSICAL_MODES[curv_type])
     else:
         raise Exception(f"Method {curv_type} not available.")    # classical_curvatures.py:27-28

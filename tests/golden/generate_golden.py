@@ -452,6 +452,33 @@ def gen_sdrf_selfloops(out):
     print("sdrf_selfloop_seq:", len(cases), "cases")
 
 
+def gen_sdrf_classical_selfloops(out):
+    """sdrf_no_cuda on inputs WITH self-loops: a loop is an edge of G.edges with a curvature of its own (degree counts it
+    twice, the node is its own neighbour), can be the minimum / maximum edge and can be removed."""
+    rng = np.random.default_rng(123)
+    cases = []
+    q = 0
+    for ct, bound in (("1d", -3.0), ("augmented", 0.5), ("haantjes", 0.5)):
+        for g, loops, tau, seed, n_self in ((nx.gnp_random_graph(14, 0.25, seed=3), 8, float("inf"), 71, 3),
+                                            (nx.gnp_random_graph(16, 0.22, seed=5), 8, 2, 72, 5),
+                                            (nx.barbell_graph(5, 2), 8, 1, 73, 12)):
+            ei = sorted_symmetric_edge_index(g)
+            n = g.number_of_nodes()
+            who = rng.choice(n, size=min(n_self, n), replace=False)
+            ei = np.concatenate([ei, np.stack([who, who])], axis=1)
+            ei = ei[:, rng.permutation(ei.shape[1])]
+            cases.append((f"cself{q}_{ct}", ei, n, ct, loops, bound, tau, seed))
+            q += 1
+    pack = {"names": np.array([c[0] for c in cases])}
+    for name, ei, n, ct, loops, bound, tau, seed in cases:
+        eo, log, uni = run_reference_classical(ei, n, ct, loops, bound, tau, seed)
+        for key, val in (("edge_index", ei), ("n", np.int64(n)), ("curv_type", np.array(ct)), ("loops", np.int64(loops)),
+                         ("bound", np.float64(bound)), ("tau", np.float64(tau)), ("uniforms", uni), ("out", eo), ("log", log)):
+            pack[f"{name}/{key}"] = val
+        print(f"  sdrf-classical-selfloops {name}: n={n} log={len(log)}", flush=True)
+    np.savez_compressed(out, **pack)
+
+
 def gen_sdrf_directed_selfloops(out):
     """is_undirected=False on digraphs WITH self-loops: kept in the DiGraph (successors AND predecessors of the node), not
     in A."""
@@ -477,6 +504,8 @@ def gen_sdrf_directed_selfloops(out):
 
 
 if __name__ == "__main__":
+    if "sdrf_classical_selfloops" in sys.argv[1:]:
+        gen_sdrf_classical_selfloops(os.path.join(HERE, "sdrf_classical_selfloop_seq.npz"))
     if "sdrf_directed_selfloops" in sys.argv[1:]:
         gen_sdrf_directed_selfloops(os.path.join(HERE, "sdrf_directed_selfloop_seq.npz"))
     which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical", "sdrf_selfloops"]

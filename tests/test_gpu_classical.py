@@ -103,3 +103,32 @@ def test_classical_dropin_signature_errors_and_one_direction_quirk():
     data2.x = data.x
     with pytest.raises(ValueError):
         sdrf_no_cuda(data2, "1d", 2, True, 0.0, 1, uniforms=uni)
+
+
+def test_classical_inputs_with_self_loops():
+    """sdrf_no_cuda keeps self-loops: a loop is an edge of G.edges with its own curvature (it can be the minimum edge and
+    it can be removed), counts twice in the degree and makes the node its own neighbour.  Goldens of the unmodified
+    reference (tests/golden/sdrf_classical_selfloop_seq.npz) and the oracle on random graphs."""
+    from dcr import sdrf
+    z = golden("sdrf_classical_selfloop_seq.npz")
+    for name in (str(s) for s in z["names"]):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        got, log = sdrf.sdrf(ei, n, int(z[f"{name}/loops"]), True, float(z[f"{name}/bound"]), float(z[f"{name}/tau"]),
+                             uniforms=z[f"{name}/uniforms"], return_log=True, curv_type=str(z[f"{name}/curv_type"]))
+        seq = []
+        for r in log:
+            if r[3] >= 0:
+                seq.append((1, int(r[3]), int(r[4])))
+            if r[6] >= 0:
+                seq.append((-1, int(r[6]), int(r[7])))
+        assert np.array_equal(np.array(seq, dtype=np.int64).reshape(-1, 3), z[f"{name}/log"]), name
+        assert np.array_equal(got, z[f"{name}/out"]), name
+    rng = np.random.default_rng(8)
+    for s, (ct, bound) in enumerate([("1d", -4.0), ("augmented", 0.5), ("haantjes", 1.5), ("augmented", 100.0)]):
+        n = 18 + 5 * s
+        ei = gnp(n, 0.2, 700 + s)
+        who = rng.choice(n, size=5 + 3 * s, replace=False)
+        ei = np.concatenate([ei, np.stack([who, who])], axis=1)
+        ei = ei[:, rng.permutation(ei.shape[1])]
+        for tau in (float("inf"), 2):
+            _run_both(ei, n, ct, 16, bound, tau, 60 + s)

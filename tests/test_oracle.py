@@ -121,6 +121,17 @@ def test_sdrf_classical_oracle_reproduces_reference_sequences():
         assert np.array_equal(_mutations(log), z[f"{name}/log"]), name
         assert np.array_equal(out, z[f"{name}/out"]), name
     assert seen == {"1d", "augmented", "haantjes"}
+    z = golden("sdrf_classical_selfloop_seq.npz")       # inputs with self-loops: loops as minimum edges, loops removed
+    loop_min = loop_removed = 0
+    for name in _names(z):
+        ei, n = z[f"{name}/edge_index"], int(z[f"{name}/n"])
+        out, log = sdrf_classical_oracle(ei, n, str(z[f"{name}/curv_type"]), int(z[f"{name}/loops"]), True,
+                                         float(z[f"{name}/bound"]), float(z[f"{name}/tau"]), z[f"{name}/uniforms"])
+        assert np.array_equal(_mutations(log), z[f"{name}/log"]), name
+        assert np.array_equal(out, z[f"{name}/out"]), name
+        loop_min += sum(r["x"] == r["y"] for r in log)
+        loop_removed += sum(r["removed"] is not None and r["removed"][0] == r["removed"][1] for r in log)
+    assert loop_min > 0 and loop_removed > 0
 
 
 # (graph, edge) -> cuda (d_i, d_j, A2ij, sharp, lam, C) ; paper (tri, sq1, sq2, gamma, bfc)
