@@ -264,10 +264,13 @@ int dcr_sdrf_create(int n, const int32_t* rowptr_host, const int32_t* order_host
                     dcr_sdrf** out);
 /* The other loop flavours (DCR_SDRF_MODE_*).  BFC_DIRECTED: rowptr/order list the SUCCESSORS of every node in
  * networkx insertion order (G.successors, sdrf_cuda_bfc.py:48) and in_rowptr/in_order the PREDECESSORS (G.predecessors,
- * :49); the graph must be simple (no self-loops, no repeated entries: to_dense_adj would sum them into a weight).
+ * :49); no repeated entries (to_dense_adj would sum them into a weight); a node with a self-loop lists itself in BOTH
+ * its successor and its predecessor list (see dcr_sdrf_create).
  * 1D / AUGMENTED / HAANTJES: the loop of sdrf_no_cuda over the undirected graph rowptr/order (adjacency order of
  * to_networkx(data, to_undirected=True)); in_* are ignored.  dcr_sdrf_run's log record then holds the (x, y) of
- * min(G.edges) (x < y), the sorted (k, l) that was added and the removed edge; removal_bound is compared in fp64. */
+ * min(G.edges) (x <= y), the sorted (k, l) that was added and the removed edge; removal_bound is compared in fp64.
+ * Here a node that lists itself has a LOOP EDGE (u,u) of G.edges with a curvature of its own (degree + 2, the node its
+ * own neighbour): it can be the minimum edge (x == y) and the removed edge. */
 int dcr_sdrf_create_mode(int n, int mode, const int32_t* rowptr_host, const int32_t* order_host,
                          const int32_t* in_rowptr_host, const int32_t* in_order_host, int64_t max_additions,
                          dcr_sdrf** out);
