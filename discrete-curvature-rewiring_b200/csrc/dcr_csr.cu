@@ -64,6 +64,31 @@ __global__ void scatter_dense_kernel(const int32_t* __restrict__ rowptr, const i
     for (int p = b + lane; p < e; p += 32) r[colidx[p]] = vals[p];
 }
 
+// The undirected edge list (row < col entries in CSR order) of a symmetric sorted CSR, derived on the device so that an
+// end-to-end caller uploads the CSR only.  upper_count: entries of row v beyond the diagonal; upper_fill: one warp per row
+// writes its edges at the row's offset (exclusive prefix sum of the counts, done by the caller).
+__global__ void csr_upper_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                                       int64_t* __restrict__ counts) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int b = rowptr[v], len = rowptr[v + 1] - b;
+    counts[v] = len - lower_bound(colidx, b, len, v + 1);
+}
+__global__ void csr_upper_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n,
+                                      const int64_t* __restrict__ offsets_incl, int32_t* __restrict__ esrc,
+                                      int32_t* __restrict__ edst) {
+    const int lane = threadIdx.x & 31;
+    const int v = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (v >= n) return;
+    const int e = rowptr[v + 1];
+    const int64_t end = offsets_incl[v], cnt = end - (v ? offsets_incl[v - 1] : 0);
+    const int first = e - (int)cnt;                        // the row is sorted: its entries > v are its last `cnt`
+    for (int t = lane; t < (int)cnt; t += 32) {
+        esrc[end - cnt + t] = v;
+        edst[end - cnt + t] = colidx[first + t];
+    }
+}
+
 }  // namespace dcr
 
 using namespace dcr;
@@ -93,6 +118,21 @@ extern "C" int dcr_scatter_dense(const int32_t* rowptr, const int32_t* colidx, i
                                  void* stream) {
     if (n <= 0) return 0;
     scatter_dense_kernel<<<warp_per_row_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n, vals, C);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcr_csr_upper_count(const int32_t* rowptr, const int32_t* colidx, int n, int64_t* counts, void* stream) {
+    if (n <= 0) return 0;
+    csr_upper_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n, counts);
+    DCR_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int dcr_csr_upper_fill(const int32_t* rowptr, const int32_t* colidx, int n, const int64_t* offsets_incl,
+                                  int32_t* esrc, int32_t* edst, void* stream) {
+    if (n <= 0) return 0;
+    csr_upper_fill_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n,
+                                                                                                   offsets_incl, esrc, edst);
     DCR_LAUNCH_CHECK();
     return 0;
 }

@@ -273,9 +273,11 @@ class ShardedCudaBFC:
 
 
 class HostShardedPaperBFC:
-    """End to end on host buffers: pinned host CSR + edge list in, one host result block (shared by the ranks) out.
+    """End to end on host buffers: pinned host CSR (+ optionally the edge list) in, one host result block (shared by the
+    ranks) out.
 
-    Per pass and rank: H2D of ``rowptr``/``colidx`` (the graph is replicated) and of the rank's slice of the edge list,
+    Per pass and rank: H2D of ``rowptr``/``colidx`` (the graph is replicated; the undirected edge list is derived from it
+    on the device unless the caller uploads one),
     the work-balanced range computed from the uploaded graph on the device (one 8-byte read-back of the rank's own
     bounds), the pass over that range, D2H of the rank's slice of the five result arrays into the shared block.  No
     device-side gather: the consumer is the host.  Layout of the block: bfc f64[E] | tri | sq_i | sq_j | gamma int32[E].
@@ -332,17 +334,27 @@ class HostShardedPaperBFC:
         return {"bfc": b[: e * 8].view(torch.float64), "tri": ints[:e], "sq_i": ints[e:2 * e], "sq_j": ints[2 * e:3 * e],
                 "gamma": ints[3 * e:4 * e]}
 
-    def run(self, h_rowptr, h_col, h_esrc, h_edst):
+    def run(self, h_rowptr, h_col, h_esrc=None, h_edst=None):
         """One end-to-end pass (pinned host tensors in).  Enqueues on the current stream, with one small blocking
-        read-back (the rank's bounds) in the middle; the rank's slice of ``host_block`` is complete when the stream is."""
+        read-back (the rank's bounds) in the middle; the rank's slice of ``host_block`` is complete when the stream is.
+        Without ``h_esrc / h_edst`` the undirected edge list (row < col entries, CSR order) is derived on the device from
+        the uploaded CSR — half the host-to-device bytes."""
         lib = L.load()
         st = L.current_stream()
         E, W = self.n_edges, self.world
         self.d_rowptr.copy_(h_rowptr, non_blocking=True)
         self.d_col.copy_(h_col, non_blocking=True)
         # every rank needs the whole edge list once to find its cut points (the cost of an edge needs both endpoints)
-        self.d_esrc.copy_(h_esrc, non_blocking=True)
-        self.d_edst.copy_(h_edst, non_blocking=True)
+        self._uploaded_edges = h_esrc is not None
+        if h_esrc is not None:
+            self.d_esrc.copy_(h_esrc, non_blocking=True)
+            self.d_edst.copy_(h_edst, non_blocking=True)
+        else:
+            L.check(lib.dcr_csr_upper_count(self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.n, self.node_s.data_ptr(),
+                                            st), "dcr_csr_upper_count")
+            self.node_s[: self.n].cumsum_(0)                       # (node_s is free until the cost kernels)
+            L.check(lib.dcr_csr_upper_fill(self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.n, self.node_s.data_ptr(),
+                                           self.d_esrc.data_ptr(), self.d_edst.data_ptr(), st), "dcr_csr_upper_fill")
         if W > 1:
             L.check(lib.dcr_bfc_paper_edge_cost(self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.n,
                                                 self.d_esrc.data_ptr(), self.d_edst.data_ptr(), E, self.cost.data_ptr(),
@@ -369,7 +381,7 @@ class HostShardedPaperBFC:
     def bytes_per_pass(self):
         """(h2d, d2h) bytes of this rank for the last pass."""
         lo, hi = self.bounds if self.bounds else (0, self.n_edges)
-        h2d = 4 * (self.n + 1) + 4 * self.nnz + 8 * self.n_edges
+        h2d = 4 * (self.n + 1) + 4 * self.nnz + (8 * self.n_edges if getattr(self, "_uploaded_edges", True) else 0)
         return h2d, 24 * (hi - lo) + (16 if self.world > 1 else 0)
 
     def close(self):

@@ -37,6 +37,8 @@ SIGNATURES = {
     "dcr_dense_count": (_I, [_P, _I, _P, _P, _P]),
     "dcr_dense_fill": (_I, [_P, _I, _P, _P, _P]),
     "dcr_scatter_dense": (_I, [_P, _P, _I, _P, _P, _P]),
+    "dcr_csr_upper_count": (_I, [_P, _P, _I, _P, _P]),
+    "dcr_csr_upper_fill": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "dcr_bfc_support": (_I, [_P, _P, _I, _P, _L, _L, _P]),
     "dcr_bfc_cuda_flavour": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),
     "dcr_bfc_cuda_flavour_directed": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _L, _L, _P]),

@@ -68,6 +68,15 @@ int dcr_dense_fill(const float* A, int n, const int32_t* rowptr, int32_t* colidx
 int dcr_scatter_dense(const int32_t* rowptr, const int32_t* colidx, int n, const float* vals, float* C,
                       void* stream);
 
+/* The undirected edge list of a symmetric sorted CSR — the entries with row < col, in CSR order: edge e = (esrc[e],
+ * edst[e]) — derived on the device (what `for v1, v2 in G.edges` enumerates, curvature/bfc_naive.py:49, for a graph
+ * given as a CSR).  dcr_csr_upper_count writes per row the number of entries beyond the diagonal (int64); the caller
+ * turns them into INCLUSIVE prefix sums (offsets_incl[v] = edges of rows 0..v); dcr_csr_upper_fill writes the nnz/2
+ * edges.  Lets an end-to-end caller upload rowptr / colidx only. */
+int dcr_csr_upper_count(const int32_t* rowptr, const int32_t* colidx, int n, int64_t* counts, void* stream);
+int dcr_csr_upper_fill(const int32_t* rowptr, const int32_t* colidx, int n, const int64_t* offsets_incl, int32_t* esrc,
+                       int32_t* edst, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * cuda-flavour BFC over CSR.  Replaces _balanced_forman_curvature (curvature/bfc_cuda.py:11-48) and its host
  * wrapper balanced_forman_curvature (:51-65) for symmetric 0/1 adjacency without self-loops.

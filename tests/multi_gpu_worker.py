@@ -69,7 +69,7 @@ def main():
         hs = ddist.HostShardedPaperBFC(n, col.size, esrc.size, csr.max_degree)
         h = (pin(rowptr.astype(np.int32)), pin(col), pin(esrc), pin(edst))
         for it in range(2):
-            lo, hi = hs.run(*h)
+            lo, hi = hs.run(*(h if it == 0 else h[:2]))     # second pass: CSR only, edge list derived on the device
             torch.cuda.synchronize()
             dist.barrier()
             hv = hs.host_views()

@@ -457,6 +457,18 @@ def test_host_end_to_end_pass_single_rank():
     hv = hs.host_views()
     for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
         assert np.array_equal(hv[k].numpy(), full[k].cpu().numpy()), k
+    # the CSR alone: the undirected edge list (row < col entries, CSR order) is derived on the device
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        hv[k].zero_()
+    h2d_full = hs.bytes_per_pass()[0]
+    hs.d_esrc.fill_(-1)
+    hs.d_edst.fill_(-1)
+    hs.run(pin(rowptr.astype(np.int32)), pin(col))
+    torch.cuda.synchronize()
+    assert np.array_equal(hs.d_esrc.cpu().numpy(), esrc) and np.array_equal(hs.d_edst.cpu().numpy(), edst)
+    for k in ("tri", "sq_i", "sq_j", "gamma", "bfc"):
+        assert np.array_equal(hv[k].numpy(), full[k].cpu().numpy()), k
+    assert hs.bytes_per_pass()[0] == h2d_full - 8 * esrc.size
     hs.close()
 
 
