@@ -183,3 +183,26 @@ def test_directed_and_classical_graph_setup_match_the_oracle_builders():
         warnings.simplefilter("always")
         G.digraph_order(np.array([[0, 1, 1], [1, 1, 2]]), 3)
         assert any("self-loops" in str(x.message) for x in w)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): one JSON line with the contract keys, the identical
+    `config` dict our arm uses, and no libdcr.so in the process."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "cora",
+                        "--steps", "1", "--warmup", "0", "--cpu-budget", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "bfc_edges_per_sec" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference")
+    sys.path.insert(0, REPO)
+    import bench
+    assert d["config"] == bench.base_config("cora", d["config"]["nodes"], d["config"]["undirected_edges"], 1)
