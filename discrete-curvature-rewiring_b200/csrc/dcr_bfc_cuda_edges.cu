@@ -11,7 +11,7 @@
 //   * pass 2 repeats the intersection, reads the two supports at the matched positions through `eid` (directed entry
 //     -> undirected edge id, built once per graph), and evaluates the closing formula once,
 //   * edges whose shorter row has >= HEAVY_MIN entries (hub-hub edges; a few thousand of a million, but each would
-//     hold one warp for the length of the whole pass) go to a second launch with one CTA per edge.
+//     hold one warp for the length of the whole pass) are taken FIRST, one CTA per edge, by the same persistent launch.
 // Multi-GPU: contiguous edge ranges, graph replicated; pass 2 needs the supports of OTHER ranks'
 // edges, so pass 1 stores each support into every rank's buffer (dcr_comm: CUDA-IPC peer memory over NVLink — the
 // all-gather of `tri` is fused into the kernel), the ranks meet on device-side flags, and pass 2 delivers the results
@@ -87,35 +87,33 @@ __device__ __forceinline__ int edge_support(const EdgeArgs& a, int i, int j, int
     return warp_sum(c);
 }
 
-template <int HEAVY>
-__global__ void __launch_bounds__(CE_THREADS) edges_support_kernel(EdgeArgs a, CommView c, int wait_ready) {
+// One persistent launch per pass: every CTA first takes hub-hub edges (one CTA per edge, block-strided over the list
+// built by the set-up kernel), then its warps take the ordinary edges — the hub edges start first and no second launch
+// waits for the tail of the first.
+__global__ void __launch_bounds__(CE_THREADS) edges_support_kernel(EdgeArgs a, CommView c) {
     __shared__ int red[2];
     __shared__ int s_last;
-    if (c.world > 1 && wait_ready) {      // the peers' buffers are free to take this pass
+    if (c.world > 1) {                    // the peers' buffers are free to take this pass
         CommFlags* fl = comm_flags(c.peers[c.rank], c.flag_off);
         if (threadIdx.x < c.world && threadIdx.x != c.rank) comm_spin(fl, &fl->ready[threadIdx.x], c.epoch);
         __syncthreads();
     }
-    if (HEAVY) {
-        const int nh = a.heavy[0];
-        for (int h = blockIdx.x; h < nh; h += gridDim.x) {
-            const int64_t e = a.heavy[8 + h];
-            if (e < a.lo || e >= a.hi) continue;
-            const int t = edge_support<1>(a, a.esrc[e], a.edst[e], red);
-            if (threadIdx.x == 0) { a.tri[e] = t; peers_store32(c, 0, e, t); }
-        }
-    } else {
-        const int lane = threadIdx.x & 31;
-        const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        for (int64_t e = a.lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < a.hi; e += warps) {
-            const int i = a.esrc[e], j = a.edst[e];
-            if (is_heavy(a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j])) continue;
-            const int t = edge_support<0>(a, i, j, red);
-            if (lane == 0) { a.tri[e] = t; peers_store32(c, 0, e, t); }
-        }
+    const int nh = a.heavy[0];
+    for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+        const int64_t e = a.heavy[8 + h];
+        if (e < a.lo || e >= a.hi) continue;
+        const int t = edge_support<1>(a, a.esrc[e], a.edst[e], red);
+        if (threadIdx.x == 0) { a.tri[e] = t; peers_store32(c, 0, e, t); }
     }
-    if (HEAVY) comm_block_done(c, &s_last, c.epoch);      // the heavy launch follows the light one on the stream
-    else if (c.world > 1) __threadfence_system();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = a.lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < a.hi; e += warps) {
+        const int i = a.esrc[e], j = a.edst[e];
+        if (is_heavy(a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j])) continue;
+        const int t = edge_support<0>(a, i, j, red);
+        if (lane == 0) { a.tri[e] = t; peers_store32(c, 0, e, t); }
+    }
+    comm_block_done(c, &s_last, c.epoch);
 }
 
 // ---- pass 2: "support == 1" counts at the common neighbours + closing formula ----------------------------------
@@ -157,7 +155,6 @@ __device__ __forceinline__ void edge_closing(const EdgeArgs& a, const CommView& 
     }
 }
 
-template <int HEAVY>
 __global__ void __launch_bounds__(CE_THREADS) edges_closing_kernel(EdgeArgs a, CommView c, unsigned int wait_epoch) {
     __shared__ int red[2];
     __shared__ int s_last;
@@ -166,23 +163,20 @@ __global__ void __launch_bounds__(CE_THREADS) edges_closing_kernel(EdgeArgs a, C
         if (threadIdx.x < c.world && threadIdx.x != c.rank) comm_spin(fl, &fl->done[threadIdx.x], wait_epoch);
         __syncthreads();
     }
-    if (HEAVY) {
-        const int nh = a.heavy[0];
-        for (int h = blockIdx.x; h < nh; h += gridDim.x) {
-            const int64_t e = a.heavy[8 + h];
-            if (e < a.lo || e >= a.hi) continue;
-            edge_closing<1>(a, c, e, red);
-        }
-    } else {
-        const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        for (int64_t e = a.lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < a.hi; e += warps) {
-            const int i = a.esrc[e], j = a.edst[e];
-            if (is_heavy(a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j])) continue;
-            edge_closing<0>(a, c, e, red);
-        }
+    const int nh = a.heavy[0];
+    for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+        const int64_t e = a.heavy[8 + h];
+        if (e < a.lo || e >= a.hi) continue;
+        edge_closing<1>(a, c, e, red);
     }
-    if (HEAVY) comm_block_done(c, &s_last, c.epoch);
-    else if (c.world > 1) __threadfence_system();
+    __syncthreads();
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = a.lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < a.hi; e += warps) {
+        const int i = a.esrc[e], j = a.edst[e];
+        if (is_heavy(a.rowptr[i + 1] - a.rowptr[i], a.rowptr[j + 1] - a.rowptr[j])) continue;
+        edge_closing<0>(a, c, e, red);
+    }
+    comm_block_done(c, &s_last, c.epoch);
 }
 
 }  // namespace dcr
@@ -219,20 +213,16 @@ static int edges_run(const int32_t* rowptr, const int32_t* colidx, const int32_t
     CommView v;
     v.peers = nullptr; v.rank = 0; v.world = 1; v.chunk = 0; v.flag_off = 0; v.epoch = 0;
     unsigned int epoch_support = 0;
-    const int light = edges_grid(count), heavy = sm_count() * 2;
+    const int grid = edges_grid(count);
     if (phases & 1) {
         if (c) { v = comm_view(c, ++c->epoch); epoch_support = v.epoch; }
         if (c && c->world > 1) { comm_ready_kernel<<<1, COMM_MAX_WORLD, 0, st>>>(v); DCR_LAUNCH_CHECK(); }
-        edges_support_kernel<0><<<light, CE_THREADS, 0, st>>>(a, v, 1);
-        DCR_LAUNCH_CHECK();
-        edges_support_kernel<1><<<heavy, CE_THREADS, 0, st>>>(a, v, 0);
+        edges_support_kernel<<<grid, CE_THREADS, 0, st>>>(a, v);
         DCR_LAUNCH_CHECK();
     }
     if (phases & 2) {
         if (c) v = comm_view(c, ++c->epoch);
-        edges_closing_kernel<0><<<light, CE_THREADS, 0, st>>>(a, v, epoch_support);
-        DCR_LAUNCH_CHECK();
-        edges_closing_kernel<1><<<heavy, CE_THREADS, 0, st>>>(a, v, epoch_support);
+        edges_closing_kernel<<<grid, CE_THREADS, 0, st>>>(a, v, epoch_support);
         DCR_LAUNCH_CHECK();
         if (c && c->world > 1) { comm_wait_kernel<<<1, COMM_MAX_WORLD, 0, st>>>(v); DCR_LAUNCH_CHECK(); }
     }
