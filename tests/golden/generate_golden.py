@@ -17,7 +17,12 @@ What is executed, all imported from ``/root/reference`` without edits:
 
 The simulator evaluates the closing formula in fp32 (numpy>=2), i.e. the oracle's ``"sim32"`` rounding model;
 the compiled kernel's fp64/two-rounding dataflow is pinned separately from its PTX.
-Outputs: ``paper_kat.npz``, ``cuda_kat.npz``, ``sdrf_seq.npz`` (a few hundred KB in total).
+  * ``rewiring.sdrf_cuda_bfc.sdrf_cuda_bfc(..., is_undirected=False)`` and ``rewire(data, '1d' | 'augmented' | 'haantjes', ...)``
+    (``rewiring/sdrf_no_cuda.py``) the same way; all three loops also on inputs WITH self-loops
+
+Outputs: ``paper_kat.npz``, ``paper_ints_kat.npz``, ``cuda_kat.npz``, ``sdrf_seq.npz``, ``sdrf_directed_seq.npz``,
+``sdrf_classical_seq.npz``, ``sdrf_selfloop_seq.npz``, ``sdrf_directed_selfloop_seq.npz``, ``sdrf_classical_selfloop_seq.npz``
+(a few hundred KB in total).
 """
 from __future__ import annotations
 
