@@ -509,22 +509,19 @@ def gen_sdrf_directed_selfloops(out):
 
 
 if __name__ == "__main__":
-    if "sdrf_classical_selfloops" in sys.argv[1:]:
-        gen_sdrf_classical_selfloops(os.path.join(HERE, "sdrf_classical_selfloop_seq.npz"))
-    if "sdrf_directed_selfloops" in sys.argv[1:]:
-        gen_sdrf_directed_selfloops(os.path.join(HERE, "sdrf_directed_selfloop_seq.npz"))
-    which = sys.argv[1:] or ["paper", "paper_ints", "cuda", "sdrf", "sdrf_directed", "sdrf_classical", "sdrf_selfloops"]
-    if "sdrf_selfloops" in which:
-        gen_sdrf_selfloops(os.path.join(HERE, "sdrf_selfloop_seq.npz"))
-    if "sdrf_classical" in which:
-        gen_sdrf_classical(os.path.join(HERE, "sdrf_classical_seq.npz"))
-    if "paper_ints" in which:
-        gen_paper_ints(os.path.join(HERE, "paper_ints_kat.npz"))
-    if "sdrf_directed" in which:
-        gen_sdrf_directed(os.path.join(HERE, "sdrf_directed_seq.npz"))
-    if "paper" in which:
-        gen_paper(os.path.join(HERE, "paper_kat.npz"))
-    if "cuda" in which:
-        gen_cuda(os.path.join(HERE, "cuda_kat.npz"))
-    if "sdrf" in which:
-        gen_sdrf(os.path.join(HERE, "sdrf_seq.npz"))
+    JOBS = [("sdrf_classical_selfloops", gen_sdrf_classical_selfloops, "sdrf_classical_selfloop_seq.npz"),
+            ("sdrf_directed_selfloops", gen_sdrf_directed_selfloops, "sdrf_directed_selfloop_seq.npz"),
+            ("sdrf_selfloops", gen_sdrf_selfloops, "sdrf_selfloop_seq.npz"),
+            ("sdrf_classical", gen_sdrf_classical, "sdrf_classical_seq.npz"),
+            ("paper_ints", gen_paper_ints, "paper_ints_kat.npz"),
+            ("sdrf_directed", gen_sdrf_directed, "sdrf_directed_seq.npz"),
+            ("paper", gen_paper, "paper_kat.npz"),
+            ("cuda", gen_cuda, "cuda_kat.npz"),
+            ("sdrf", gen_sdrf, "sdrf_seq.npz")]
+    which = sys.argv[1:] or [name for name, _, _ in JOBS]
+    unknown = set(which) - {name for name, _, _ in JOBS}
+    if unknown:
+        raise SystemExit(f"unknown fixture(s) {sorted(unknown)}; choose from {[name for name, _, _ in JOBS]}")
+    for name, fn, out in JOBS:
+        if name in which:
+            fn(os.path.join(HERE, out))
